@@ -1,0 +1,195 @@
+"""ctypes binding of ``libb2a.so`` (C ABI in ``include/b2a.h``).
+
+This is the ONLY compute path of the package: there is no CPU fallback.  Importing this module
+does not need a GPU (so symbol/ABI checks run anywhere); creating an :class:`Engine` does, and
+fails loudly when the library or a CUDA device is missing.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+from typing import Optional
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libb2a.so"
+
+KIND_MEL, KIND_MFCC, KIND_CQT = 0, 1, 2
+IN_I16, IN_F32 = 0, 1
+PAD_CONSTANT, PAD_REFLECT = 0, 1
+TABLE_WINDOW, TABLE_MEL_DENSE, TABLE_DCT, TABLE_DECIM_TAPS, TABLE_CQT_LENGTHS, TABLE_CQT_BASIS = range(6)
+
+EXPORTED_SYMBOLS = [
+    "b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
+    "b2a_run_host", "b2a_last_launch_count", "b2a_alloc_pinned", "b2a_free_pinned",
+    "b2a_get_table", "b2a_cqt_geometry", "b2a_last_error", "b2a_abi_version", "b2a_device_count",
+]
+
+
+class B2AError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libb2a error {code}: {msg}")
+        self.code = code
+
+
+class B2AConfig(C.Structure):
+    _fields_ = [
+        ("kind", C.c_int32), ("input_dtype", C.c_int32), ("sample_rate", C.c_int32),
+        ("n_samples", C.c_int32), ("n_fft", C.c_int32), ("hop_length", C.c_int32),
+        ("n_mels", C.c_int32), ("n_mfcc", C.c_int32), ("n_bins", C.c_int32),
+        ("bins_per_octave", C.c_int32), ("fmin", C.c_double), ("pad_mode", C.c_int32),
+        ("top_db", C.c_float), ("reserved", C.c_int32 * 8),
+    ]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen libb2a.so and declare prototypes.  Raises if the library has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: build it with `python -m audio_edge_ml_pipeline_b200.build` "
+            "(there is no CPU fallback for this package)")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    lib.b2a_default_config.argtypes = [i32, C.POINTER(B2AConfig)]
+    lib.b2a_create.argtypes = [C.POINTER(B2AConfig), i32, C.POINTER(vp)]
+    lib.b2a_destroy.argtypes = [vp]
+    lib.b2a_out_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    lib.b2a_run_device.argtypes = [vp, vp, i64, vp, vp]
+    lib.b2a_run_host.argtypes = [vp, vp, i64, vp]
+    lib.b2a_last_launch_count.argtypes = [vp]
+    lib.b2a_last_launch_count.restype = i64
+    lib.b2a_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(vp)]
+    lib.b2a_free_pinned.argtypes = [vp]
+    lib.b2a_get_table.argtypes = [vp, i32, vp, C.POINTER(i64)]
+    lib.b2a_cqt_geometry.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp]
+    lib.b2a_last_error.restype = C.c_char_p
+    for name in ("b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
+                 "b2a_run_host", "b2a_alloc_pinned", "b2a_free_pinned", "b2a_get_table",
+                 "b2a_cqt_geometry", "b2a_abi_version", "b2a_device_count"):
+        getattr(lib, name).restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise B2AError(rc, load_library().b2a_last_error().decode(errors="replace"))
+
+
+def default_config(kind: int) -> B2AConfig:
+    cfg = B2AConfig()
+    _check(load_library().b2a_default_config(kind, C.byref(cfg)))
+    return cfg
+
+
+def device_count() -> int:
+    return int(load_library().b2a_device_count())
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory owned by the library."""
+
+    def __init__(self, shape, dtype):
+        self._lib = load_library()
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        _check(self._lib.b2a_alloc_pinned(nbytes, C.byref(p)))
+        self._ptr = p
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def close(self) -> None:
+        if self._ptr is not None:
+            self.array = None
+            self._lib.b2a_free_pinned(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One (device, configuration) handle of libb2a."""
+
+    def __init__(self, cfg: B2AConfig, device: int = 0):
+        self._lib = load_library()
+        self.cfg = cfg
+        self.device = device
+        h = C.c_void_p()
+        _check(self._lib.b2a_create(C.byref(cfg), device, C.byref(h)))
+        self._h = h
+        rows, frames = C.c_int32(), C.c_int32()
+        _check(self._lib.b2a_out_shape(h, C.byref(rows), C.byref(frames)))
+        self.rows, self.frames = rows.value, frames.value
+        self.in_dtype = np.int16 if cfg.input_dtype == IN_I16 else np.float32
+
+    # -- lifecycle ------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None:
+            self._lib.b2a_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- compute --------------------------------------------------------------------------
+    def run_host(self, clips: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """clips: (N, n_samples) int16/float32 host array -> (N, rows, frames) float32."""
+        clips = np.ascontiguousarray(clips, dtype=self.in_dtype)
+        if clips.ndim != 2 or clips.shape[1] != self.cfg.n_samples:
+            raise ValueError(f"clips must be (N, {self.cfg.n_samples}), got {clips.shape}")
+        n = clips.shape[0]
+        if out is None:
+            out = np.empty((n, self.rows, self.frames), dtype=np.float32)
+        elif out.shape != (n, self.rows, self.frames) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous float32 (N, rows, frames)")
+        _check(self._lib.b2a_run_host(self._h, clips.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def run_device(self, d_clips: int, n_clips: int, d_out: int, stream: int = 0) -> None:
+        """Raw device pointers (e.g. torch ``tensor.data_ptr()``); asynchronous on ``stream``."""
+        _check(self._lib.b2a_run_device(self._h, C.c_void_p(d_clips), n_clips, C.c_void_p(d_out),
+                                        C.c_void_p(stream)))
+
+    @property
+    def last_launch_count(self) -> int:
+        return int(self._lib.b2a_last_launch_count(self._h))
+
+    # -- introspection ----------------------------------------------------------------------
+    def table(self, which: int) -> np.ndarray:
+        n = C.c_int64(0)
+        _check(self._lib.b2a_get_table(self._h, which, None, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float32)
+        _check(self._lib.b2a_get_table(self._h, which, out.ctypes.data, C.byref(n)))
+        return out
+
+    def cqt_geometry(self):
+        no, nf = C.c_int32(), C.c_int32()
+        _check(self._lib.b2a_cqt_geometry(self._h, C.byref(no), C.byref(nf), None, None, None))
+        a = np.zeros(no.value, np.int32)
+        b = np.zeros(no.value, np.int32)
+        c = np.zeros(no.value, np.int32)
+        _check(self._lib.b2a_cqt_geometry(self._h, C.byref(no), C.byref(nf), a.ctypes.data, b.ctypes.data,
+                                          c.ctypes.data))
+        return dict(n_octaves=no.value, n_filters=nf.value, n_fft=a, hop=b, sig_len=c)

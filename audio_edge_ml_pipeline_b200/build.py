@@ -1,0 +1,75 @@
+"""In-tree build of ``libb2a.so`` (hand-written sm_100a CUDA kernels + the C ABI of include/b2a.h).
+
+``python -m audio_edge_ml_pipeline_b200.build`` or ``build_lib()``; nvcc cross-compiles without a
+GPU.  The built library stays inside the package directory (git-ignored, shipped by gpurun).
+"""
+
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libb2a.so"
+SOURCES = ["api.cu", "frontend.cu", "cqt.cu", "tables.cpp"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc() -> str:
+    cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(cand).exists():
+        raise RuntimeError("nvcc not found: cannot build libb2a.so")
+    return cand
+
+
+def _fingerprint() -> str:
+    h = hashlib.sha256()
+    for p in sorted(list(CSRC.glob("*")) + [PKG.parent / "include" / "b2a.h", Path(__file__)]):
+        if p.is_file():
+            h.update(p.name.encode())
+            h.update(p.read_bytes())
+    return h.hexdigest()
+
+
+def build_lib(force: bool = False, verbose: bool = False) -> Path:
+    """Compile (if sources changed) and return the path of libb2a.so."""
+    stamp = PKG / ".libb2a.stamp"
+    fp = _fingerprint()
+    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == fp:
+        return LIB
+    nvcc = _nvcc()
+    objdir = PKG / "build"
+    objdir.mkdir(exist_ok=True)
+    flags = list(NVCC_FLAGS)
+    procs = []
+    objs = []
+    for src in SOURCES:
+        obj = objdir / (src.rsplit(".", 1)[0] + ".o")
+        objs.append(str(obj))
+        cmd = [nvcc, *flags, "-I", str(PKG.parent / "include"), "-c", str(CSRC / src), "-o", str(obj)]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            print(out.decode(errors="replace"))
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}")
+    subprocess.run([nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"],
+                   check=True)
+    stamp.write_text(fp)
+    return LIB
+
+
+if __name__ == "__main__":
+    import sys
+
+    print(build_lib(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,371 @@
+// api.cu — implementation of the C ABI declared in include/b2a.h.
+//
+// Reference interface each entry point stands in for (all in /root/reference):
+//   b2a_create / b2a_default_config  <- extractor constructors
+//        src/preprocessing/feature_extraction/audio/deep.py:98-110, 219-233, 290-302
+//   b2a_run_host / b2a_run_device    <- the librosa calls inside the three extract() bodies
+//        deep.py:126-134 (mel), 249-260 (cqt), 318-328 (mfcc)
+//   b2a_out_shape                    <- "n_frames = 1 + n_samples // hop"  CLAUDE.md:90
+#include "../../include/b2a.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "cqt.h"
+#include "frontend.h"
+#include "tables.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                      \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return fail(e__ == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA,        \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+    } while (0)
+
+template <typename T>
+cudaError_t upload(const std::vector<T>& v, T** d) {
+    *d = nullptr;
+    if (v.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)d, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+int ilog2(int x) {
+    int l = 0;
+    while ((1 << l) < x) ++l;
+    return l;
+}
+
+}  // namespace
+
+struct b2a_handle {
+    b2a_config cfg{};
+    int device = 0, sm_count = 0;
+    int rows = 0, frames = 0, log2nc = 0;
+    size_t in_elem = 2;
+    int64_t last_launches = 0;
+    // host copies (introspection)
+    std::vector<float> window, mel_dense, dct;
+    b2a::BandedMel mel;
+    // device tables (mel / mfcc)
+    float* d_window = nullptr;
+    float2* d_tw = nullptr;
+    float2* d_tw2 = nullptr;
+    int* d_k0 = nullptr;
+    int* d_cnt = nullptr;
+    int* d_off = nullptr;
+    float* d_w = nullptr;
+    float* d_dct = nullptr;
+    float* d_inter = nullptr;
+    int grid_cap = 0;
+    // cqt
+    b2a::CqtPlan cqt;
+    b2a::CqtDevice cqtdev;
+    // run_host resources
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    void* d_in[2] = {nullptr, nullptr};
+    float* d_out[2] = {nullptr, nullptr};
+    int64_t chunk_clips = 0;
+};
+
+extern "C" {
+
+const char* b2a_last_error(void) { return g_err.c_str(); }
+int b2a_abi_version(void) { return B2A_ABI_VERSION; }
+
+int b2a_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int b2a_default_config(int32_t kind, b2a_config* c) {
+    if (!c) return fail(B2A_EINVAL, "cfg is NULL");
+    std::memset(c, 0, sizeof(*c));
+    c->kind = kind;
+    c->input_dtype = B2A_IN_I16;
+    c->pad_mode = B2A_PAD_CONSTANT;
+    c->top_db = 80.0f;
+    switch (kind) {
+        case B2A_KIND_MEL:   // deep.py:98-105
+            c->sample_rate = 16000; c->n_mels = 40; c->n_fft = 512; c->hop_length = 160; break;
+        case B2A_KIND_MFCC:  // deep.py:290-297 (+ librosa.feature.mfcc n_mels default)
+            c->sample_rate = 22050; c->n_mfcc = 40; c->n_fft = 1024; c->hop_length = 512; c->n_mels = 128; break;
+        case B2A_KIND_CQT:   // deep.py:219-227
+            c->sample_rate = 22050; c->hop_length = 512; c->n_bins = 84; c->bins_per_octave = 12; c->fmin = 0.0; break;
+        default: return fail(B2A_EINVAL, "unknown kind");
+    }
+    return B2A_OK;
+}
+
+int b2a_destroy(b2a_handle* h) {
+    if (!h) return B2A_OK;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 2; ++i) {
+        if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
+        cudaFree(h->d_in[i]); cudaFree(h->d_out[i]);
+    }
+    cudaFree(h->d_window); cudaFree(h->d_tw); cudaFree(h->d_tw2);
+    cudaFree(h->d_k0); cudaFree(h->d_cnt); cudaFree(h->d_off); cudaFree(h->d_w);
+    cudaFree(h->d_dct); cudaFree(h->d_inter);
+    b2a::cqt_device_free(&h->cqtdev);
+    delete h;
+    return B2A_OK;
+}
+
+int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
+    if (!cfg || !out) return fail(B2A_EINVAL, "cfg/out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        return fail(B2A_ENODEVICE, "no CUDA device visible: this library has no CPU path");
+    }
+    if (device < 0 || device >= ndev) return fail(B2A_EINVAL, "device index out of range");
+    for (int r : cfg->reserved) if (r != 0) return fail(B2A_EINVAL, "reserved fields must be zero");
+    if (cfg->input_dtype != B2A_IN_I16 && cfg->input_dtype != B2A_IN_F32) return fail(B2A_EINVAL, "input_dtype");
+    if (cfg->sample_rate <= 0 || cfg->hop_length <= 0 || cfg->n_samples <= 0)
+        return fail(B2A_EINVAL, "sample_rate, hop_length and n_samples must be positive");
+    if (!(cfg->top_db > 0.f)) return fail(B2A_EINVAL, "top_db must be positive");
+
+    b2a_handle* h = new (std::nothrow) b2a_handle();
+    if (!h) return fail(B2A_ENOMEM, "host allocation failed");
+    h->cfg = *cfg;
+    h->device = device;
+    h->in_elem = cfg->input_dtype == B2A_IN_I16 ? 2 : 4;
+    auto bail = [&](int code, const std::string& m) { b2a_destroy(h); return fail(code, m); };
+#define CU_TRY_H(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e__ = (expr);                                                               \
+        if (e__ != cudaSuccess)                                                                 \
+            return bail(e__ == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA,              \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
+    } while (0)
+
+    CU_TRY_H(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU_TRY_H(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return bail(B2A_ENODEVICE, "device is not sm_100-class (kernels are built for sm_100a only)");
+    h->sm_count = prop.multiProcessorCount;
+    h->frames = 1 + cfg->n_samples / cfg->hop_length;
+
+    if (cfg->kind == B2A_KIND_MEL || cfg->kind == B2A_KIND_MFCC) {
+        const int n_fft = cfg->n_fft;
+        if (n_fft != 256 && n_fft != 512 && n_fft != 1024 && n_fft != 2048)
+            return bail(B2A_EINVAL, "n_fft must be one of 256, 512, 1024, 2048");
+        if (cfg->n_samples < n_fft)      // deep.py:119 min_samples=n_fft
+            return bail(B2A_EINVAL, "n_samples must be >= n_fft (deep.py pads to n_fft)");
+        if (cfg->n_mels <= 0 || cfg->n_mels > 512) return bail(B2A_EINVAL, "n_mels out of range");
+        if (cfg->pad_mode != B2A_PAD_CONSTANT && cfg->pad_mode != B2A_PAD_REFLECT) return bail(B2A_EINVAL, "pad_mode");
+        const bool mfcc = cfg->kind == B2A_KIND_MFCC;
+        if (mfcc && (cfg->n_mfcc <= 0 || cfg->n_mfcc > cfg->n_mels)) return bail(B2A_EINVAL, "n_mfcc must be in [1, n_mels]");
+        h->log2nc = ilog2(n_fft / 2);
+        h->rows = mfcc ? cfg->n_mfcc : cfg->n_mels;
+        const int NC = n_fft / 2, n_bins = NC + 1;
+        h->window = b2a::hann_periodic(n_fft);
+        h->mel_dense = b2a::mel_filterbank(cfg->sample_rate, n_fft, cfg->n_mels);
+        h->mel = b2a::band_mel(h->mel_dense, cfg->n_mels, n_bins);
+        if (mfcc) {
+            h->dct = b2a::dct2_ortho(cfg->n_mfcc, cfg->n_mels);
+            const int F = h->log2nc <= 8 ? 32 : 16;
+            if ((size_t)cfg->n_mels * 32 > (size_t)F * (NC + 1))
+                return bail(B2A_EINVAL, "n_mels too large for this n_fft in the mfcc kernel");
+        }
+        const size_t smem = b2a::front_smem_bytes(h->log2nc, cfg->hop_length, cfg->n_mels, (int)h->mel.w.size());
+        if (smem > (size_t)prop.sharedMemPerBlockOptin)
+            return bail(B2A_EINVAL, "hop_length/n_fft/n_mels combination exceeds shared memory");
+        std::vector<float> tw = b2a::twiddles(NC, NC);
+        std::vector<float> tw2 = b2a::twiddles(2 * NC, NC / 2 + 1);
+        CU_TRY_H(upload(h->window, &h->d_window));
+        CU_TRY_H(upload(tw, (float**)&h->d_tw));
+        CU_TRY_H(upload(tw2, (float**)&h->d_tw2));
+        CU_TRY_H(upload(h->mel.k0, &h->d_k0));
+        CU_TRY_H(upload(h->mel.cnt, &h->d_cnt));
+        CU_TRY_H(upload(h->mel.off, &h->d_off));
+        if (h->mel.w.empty()) h->mel.w.push_back(0.f);
+        CU_TRY_H(upload(h->mel.w, &h->d_w));
+        h->grid_cap = h->sm_count * b2a::front_ctas_per_sm(h->log2nc);
+        if (mfcc) {
+            CU_TRY_H(upload(h->dct, &h->d_dct));
+            CU_TRY_H(cudaMalloc((void**)&h->d_inter, (size_t)h->grid_cap * cfg->n_mels * h->frames * sizeof(float)));
+        }
+    } else if (cfg->kind == B2A_KIND_CQT) {
+        if (cfg->n_samples < 2 * cfg->hop_length)   // deep.py:242-243 min_samples = 2*hop
+            return bail(B2A_EINVAL, "n_samples must be >= 2*hop_length (deep.py pads to 2*hop)");
+        const char* perr = nullptr;
+        if (!b2a::build_cqt_plan(cfg->sample_rate, cfg->hop_length, cfg->n_bins, cfg->bins_per_octave,
+                                 cfg->fmin, cfg->n_samples, &h->cqt, &perr))
+            return bail(B2A_EINVAL, perr ? perr : "cqt plan failed");
+        h->rows = cfg->n_bins;
+        h->frames = h->cqt.n_frames;
+        std::string cerr;
+        const int rc = b2a::cqt_device_init(h->cqt, *cfg, h->sm_count, (size_t)prop.sharedMemPerBlockOptin,
+                                            &h->cqtdev, &cerr);
+        if (rc != 0) return bail(rc, cerr);
+    } else {
+        return bail(B2A_EINVAL, "unknown kind");
+    }
+    *out = h;
+    return B2A_OK;
+#undef CU_TRY_H
+}
+
+int b2a_out_shape(const b2a_handle* h, int32_t* rows, int32_t* frames) {
+    if (!h) return fail(B2A_EINVAL, "handle is NULL");
+    if (rows) *rows = h->rows;
+    if (frames) *frames = h->frames;
+    return B2A_OK;
+}
+
+int64_t b2a_last_launch_count(const b2a_handle* h) { return h ? h->last_launches : 0; }
+
+static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, float* d_out,
+                           cudaStream_t st, int64_t* launches) {
+    if (n_clips == 0) return B2A_OK;
+    if (h->cfg.kind == B2A_KIND_CQT) {
+        std::string cerr;
+        const int rc = b2a::cqt_run(h->cqt, h->cfg, &h->cqtdev, d_clips, n_clips, d_out, st, launches, &cerr);
+        if (rc != 0) return fail(rc, cerr);
+        return B2A_OK;
+    }
+    b2a::FrontParams p{};
+    p.clips = d_clips; p.out = d_out; p.inter = h->d_inter;
+    p.window = h->d_window; p.tw = h->d_tw; p.tw2 = h->d_tw2;
+    p.mel_k0 = h->d_k0; p.mel_cnt = h->d_cnt; p.mel_off = h->d_off; p.mel_w = h->d_w;
+    p.dct = h->d_dct;
+    p.n_clips = n_clips; p.n_samples = h->cfg.n_samples; p.hop = h->cfg.hop_length;
+    p.n_frames = h->frames; p.n_mels = h->cfg.n_mels; p.mel_nnz = (int)h->mel.w.size();
+    p.n_mfcc = h->cfg.n_mfcc; p.pad_mode = h->cfg.pad_mode; p.top_db = h->cfg.top_db;
+    const int grid = (int)std::min<int64_t>(n_clips, h->grid_cap);
+    CU_TRY(b2a::launch_front(p, h->log2nc, h->cfg.input_dtype == B2A_IN_I16,
+                             h->cfg.kind == B2A_KIND_MFCC ? 1 : 0, grid, st));
+    *launches += 1;
+    return B2A_OK;
+}
+
+int b2a_run_device(b2a_handle* h, const void* d_clips, int64_t n_clips, float* d_out, void* stream) {
+    if (!h) return fail(B2A_EINVAL, "handle is NULL");
+    if (n_clips < 0) return fail(B2A_EINVAL, "n_clips < 0");
+    if (n_clips > 0 && (!d_clips || !d_out)) return fail(B2A_EINVAL, "NULL buffer");
+    CU_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    return run_device_impl(h, d_clips, n_clips, d_out, (cudaStream_t)stream, &h->last_launches);
+}
+
+int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out) {
+    if (!h) return fail(B2A_EINVAL, "handle is NULL");
+    if (n_clips < 0) return fail(B2A_EINVAL, "n_clips < 0");
+    if (n_clips == 0) { h->last_launches = 0; return B2A_OK; }
+    if (!clips || !out) return fail(B2A_EINVAL, "NULL buffer");
+    CU_TRY(cudaSetDevice(h->device));
+    const size_t in_clip = (size_t)h->cfg.n_samples * h->in_elem;
+    const size_t out_clip = (size_t)h->rows * h->frames * sizeof(float);
+    if (!h->streams[0]) {
+        // ~64 MiB of input per chunk, two chunks in flight
+        int64_t cc = (int64_t)((64u << 20) / in_clip);
+        cc = std::max<int64_t>(1, std::min<int64_t>(cc, 4096));
+        h->chunk_clips = cc;
+        for (int i = 0; i < 2; ++i) {
+            CU_TRY(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+            CU_TRY(cudaMalloc(&h->d_in[i], in_clip * cc));
+            CU_TRY(cudaMalloc((void**)&h->d_out[i], out_clip * cc));
+        }
+    }
+    h->last_launches = 0;
+    int rc = B2A_OK;
+    int64_t done = 0;
+    for (int c = 0; done < n_clips; ++c) {
+        const int s = c & 1;
+        const int64_t nb = std::min<int64_t>(h->chunk_clips, n_clips - done);
+        const unsigned char* src = (const unsigned char*)clips + (size_t)done * in_clip;
+        float* dst = (float*)((unsigned char*)out + (size_t)done * out_clip);
+        CU_TRY(cudaMemcpyAsync(h->d_in[s], src, in_clip * nb, cudaMemcpyHostToDevice, h->streams[s]));
+        rc = run_device_impl(h, h->d_in[s], nb, h->d_out[s], h->streams[s], &h->last_launches);
+        if (rc != B2A_OK) break;
+        CU_TRY(cudaMemcpyAsync(dst, h->d_out[s], out_clip * nb, cudaMemcpyDeviceToHost, h->streams[s]));
+        done += nb;
+    }
+    cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
+    cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
+    if (rc != B2A_OK) return rc;
+    CU_TRY(e0);
+    CU_TRY(e1);
+    return B2A_OK;
+}
+
+int b2a_alloc_pinned(size_t bytes, void** out) {
+    if (!out) return fail(B2A_EINVAL, "out is NULL");
+    *out = nullptr;
+    CU_TRY(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocPortable));
+    return B2A_OK;
+}
+
+int b2a_free_pinned(void* p) {
+    if (p) CU_TRY(cudaFreeHost(p));
+    return B2A_OK;
+}
+
+int b2a_get_table(const b2a_handle* h, int32_t which, float* dst, int64_t* count) {
+    if (!h || !count) return fail(B2A_EINVAL, "handle/count is NULL");
+    std::vector<float> tmp;
+    const std::vector<float>* src = nullptr;
+    switch (which) {
+        case B2A_TABLE_WINDOW: src = &h->window; break;
+        case B2A_TABLE_MEL_DENSE: src = &h->mel_dense; break;
+        case B2A_TABLE_DCT: src = &h->dct; break;
+        case B2A_TABLE_DECIM_TAPS: {
+            for (double v : b2a::decimator_taps()) tmp.push_back((float)v);
+            src = &tmp; break;
+        }
+        case B2A_TABLE_CQT_LENGTHS: {
+            for (double v : h->cqt.lengths) tmp.push_back((float)v);
+            src = &tmp; break;
+        }
+        case B2A_TABLE_CQT_BASIS: {
+            for (const auto& o : h->cqt.oct) tmp.insert(tmp.end(), o.basis.begin(), o.basis.end());
+            src = &tmp; break;
+        }
+        default: return fail(B2A_EINVAL, "unknown table");
+    }
+    const int64_t need = (int64_t)src->size();
+    if (dst) {
+        if (*count < need) { *count = need; return fail(B2A_EINVAL, "destination too small"); }
+        std::memcpy(dst, src->data(), (size_t)need * sizeof(float));
+    }
+    *count = need;
+    return B2A_OK;
+}
+
+int b2a_cqt_geometry(const b2a_handle* h, int32_t* n_octaves, int32_t* n_filters, int32_t* n_fft,
+                     int32_t* hop, int32_t* sig_len) {
+    if (!h) return fail(B2A_EINVAL, "handle is NULL");
+    if (h->cfg.kind != B2A_KIND_CQT) return fail(B2A_EINVAL, "not a cqt handle");
+    if (n_octaves) *n_octaves = h->cqt.n_octaves;
+    if (n_filters) *n_filters = h->cqt.n_filters;
+    for (int i = 0; i < h->cqt.n_octaves; ++i) {
+        if (n_fft) n_fft[i] = h->cqt.oct[i].n_fft;
+        if (hop) hop[i] = h->cqt.oct[i].hop;
+        if (sig_len) sig_len[i] = h->cqt.oct[i].sig_len;
+    }
+    return B2A_OK;
+}
+
+}  // extern "C"

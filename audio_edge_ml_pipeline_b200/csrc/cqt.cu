@@ -1,0 +1,465 @@
+// cqt.cu — audio_cqt on the GPU: 2:1 decimation cascade, per-octave rectangular-window STFT
+// times the sparsified wavelet basis, amplitude_to_db(ref=max) + min-max.  sm_100a only.
+//
+// Follows librosa.cqt == vqt(gamma=0) as the reference calls it (deep.py:249-260): octaves are
+// processed top-down; each octave's response is  basis_o . STFT(y_o; n_fft_o, hop_o, ones)  and
+// y_{o+1} = sqrt(2) * decimate2(y_o).  The decimator is this project's stand-in for soxr_hq
+// (tables.h: decimator_taps; DESIGN.md "CQT decimator").
+//
+// The basis product is a 12 x 129 complex matrix with ~147 non-zeros against [129 x frames]: as a
+// dense GEMM it would be 10x the flops of the banded form and needs fp32-grade accuracy 80 dB
+// below the peak, so it runs on the CUDA cores as a banded complex dot product, not on tcgen05.
+#include "cqt.h"
+#include "fft_core.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace b2a {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+// ------------------------------------------------------------------------------------------
+// 2:1 decimator:  out[m] = sqrt(2) * sum_j h[j] y[2m + 191 - j],  j = 0..382, zero-extended.
+// Polyphase: A[q] = y[2q+191] meets the even taps, B[q] = y[2q+190] the odd taps.
+// ------------------------------------------------------------------------------------------
+constexpr int kDecThreads = 128;
+constexpr int kDecR = 16;                       // consecutive outputs per thread
+constexpr int kDecTile = kDecThreads * kDecR;   // outputs per CTA
+constexpr int kDecU = 8;                        // taps per register-window step
+constexpr int kDecHalf = 192;                   // taps per phase (odd phase zero-padded)
+constexpr int kDecLocal = kDecTile + kDecHalf;  // staged polyphase samples per phase
+
+__device__ __forceinline__ int dpad(int q) { return q + (q >> 5); }
+
+template <bool I16>
+__global__ void __launch_bounds__(kDecThreads) cqt_decimate_kernel(
+    const void* __restrict__ in, size_t in_stride, int in_len, float* __restrict__ out,
+    size_t out_stride, int out_len, const float* __restrict__ taps) {
+    __shared__ float sA[kDecLocal + kDecLocal / 32 + 2];
+    __shared__ float sB[kDecLocal + kDecLocal / 32 + 2];
+    __shared__ float sh[2 * kDecHalf];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.x * kDecTile;
+    const size_t clip = blockIdx.y;
+    // contiguous input range feeding this tile: n = nstart + idx, idx in [0, 2*kDecLocal)
+    const int nstart = 2 * (m0 - (kDecHalf - 1)) + 190;
+    for (int idx = tid; idx < 2 * kDecLocal; idx += kDecThreads) {
+        const int nn = nstart + idx;
+        float v = 0.f;
+        if (nn >= 0 && nn < in_len) {
+            if (I16) v = (float)((const int16_t*)in)[clip * in_stride + nn] * (1.0f / 32768.0f);
+            else v = ((const float*)in)[clip * in_stride + nn];
+        }
+        const int l = idx >> 1;
+        if (idx & 1) sA[dpad(l)] = v; else sB[dpad(l)] = v;
+    }
+    for (int i = tid; i < 2 * kDecHalf; i += kDecThreads) sh[i] = (i < kDecimTaps) ? taps[i] : 0.f;
+    __syncthreads();
+
+    float acc[kDecR];
+#pragma unroll
+    for (int r = 0; r < kDecR; ++r) acc[r] = 0.f;
+    const int lb = tid * kDecR + (kDecHalf - 1);     // local index of A[m_0], B[m_0]
+#pragma unroll 1
+    for (int i0 = 0; i0 < kDecHalf; i0 += kDecU) {
+        float xa[kDecR + kDecU - 1], xb[kDecR + kDecU - 1];
+        const int l0 = lb - i0 - (kDecU - 1);
+#pragma unroll
+        for (int d = 0; d < kDecR + kDecU - 1; ++d) { xa[d] = sA[dpad(l0 + d)]; xb[d] = sB[dpad(l0 + d)]; }
+#pragma unroll
+        for (int u = 0; u < kDecU; ++u) {
+            const float he = sh[2 * (i0 + u)], ho = sh[2 * (i0 + u) + 1];
+#pragma unroll
+            for (int r = 0; r < kDecR; ++r) {
+                acc[r] = fmaf(he, xa[r - u + kDecU - 1], acc[r]);
+                acc[r] = fmaf(ho, xb[r - u + kDecU - 1], acc[r]);
+            }
+        }
+    }
+    float* o = out + clip * out_stride;
+#pragma unroll
+    for (int r = 0; r < kDecR; ++r) {
+        const int m = m0 + tid * kDecR + r;
+        if (m < out_len) o[m] = acc[r] * 1.41421356237309504880f;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// One octave: rectangular-window STFT (centre zero-pad) -> banded complex basis -> |.|/sqrt(len)
+// ------------------------------------------------------------------------------------------
+struct OctParams {
+    const void* in; size_t in_stride; int in_len;
+    int hop, n_frames, n_rows, row0, nnz;
+    const float2* tw; const float2* tw2;
+    const float2* basis; const int* k0; const int* cnt; const int* off;
+    const float* inv_sqrt_len;
+    float* out; size_t out_stride;            // out[clip*out_stride + row*n_frames + t]
+    unsigned int* clip_max; unsigned int* clip_min;
+};
+
+template <int LOG2NC> struct OctCfg {
+    using G = FftGeom<LOG2NC>;
+    static constexpr int F = (LOG2NC <= 8) ? 32 : 16;
+    static constexpr int FR = kThreads / G::T;
+    static constexpr int ROUNDS = F / FR;
+    static constexpr int SSTRIDE = G::NC + 1;        // float2 per frame in the spectrum tile
+};
+
+static size_t oct_smem_bytes(int log2nc, int hop, int n_rows, int nnz) {
+    const int NC = 1 << log2nc, n_fft = 2 * NC, T = NC / 16;
+    const int F = (log2nc <= 8) ? 32 : 16, FR = kThreads / T;
+    const size_t fstride = hop >= n_fft ? (size_t)n_fft : (size_t)hop;
+    size_t cl = fstride * (F - 1) + n_fft;
+    cl = (cl + 7) & ~(size_t)7;
+    size_t b = cl * 4 + (size_t)FR * (NC + NC / 16) * 8 + (size_t)F * (NC + 1) * 8;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)NC * 8 + (size_t)(NC / 2 + 1) * 8 + (size_t)nnz * 8 + (size_t)n_rows * 12 + 128 * 4;
+    return b + 64;
+}
+
+template <int LOG2NC, bool I16>
+__global__ void __launch_bounds__(kThreads) cqt_octave_kernel(OctParams p) {
+    using G = FftGeom<LOG2NC>;
+    using C = OctCfg<LOG2NC>;
+    constexpr int NC = G::NC, NFFT = G::NFFT, T = G::T, F = C::F, FR = C::FR;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const bool per_frame = p.hop >= NFFT;               // frames do not overlap: stage frame by frame
+    const int fstride = per_frame ? NFFT : p.hop;
+    const int cl = (fstride * (F - 1) + NFFT + 7) & ~7;
+    float* s_audio = reinterpret_cast<float*>(smem_raw);
+    float2* s_xch = reinterpret_cast<float2*>(s_audio + cl);
+    float2* s_spec = s_xch + FR * G::XSTRIDE;
+    uintptr_t q = reinterpret_cast<uintptr_t>(s_spec + F * C::SSTRIDE);
+    q = (q + 15) & ~(uintptr_t)15;
+    float2* s_tw = reinterpret_cast<float2*>(q);
+    float2* s_tw2 = s_tw + NC;
+    float2* s_basis = s_tw2 + NC / 2 + 1;
+    int* s_k0 = reinterpret_cast<int*>(s_basis + p.nnz);
+    int* s_cnt = s_k0 + p.n_rows;
+    int* s_off = s_cnt + p.n_rows;
+    float* s_red = reinterpret_cast<float*>(s_off + p.n_rows);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < NC; i += kThreads) s_tw[i] = p.tw[i];
+    for (int i = tid; i < NC / 2 + 1; i += kThreads) s_tw2[i] = p.tw2[i];
+    for (int i = tid; i < p.nnz; i += kThreads) s_basis[i] = p.basis[i];
+    for (int i = tid; i < p.n_rows; i += kThreads) { s_k0[i] = p.k0[i]; s_cnt[i] = p.cnt[i]; s_off[i] = p.off[i]; }
+
+    const size_t clip = blockIdx.y;
+    const int t0 = blockIdx.x * F;
+    const int n = p.in_len;
+    // ---- stage samples (zero outside [0, n)) ---------------------------------------------------
+    if (per_frame) {
+        for (int i = tid; i < F * NFFT; i += kThreads) {
+            const int f = i / NFFT, o = i % NFFT;
+            const int s = (t0 + f) * p.hop - NFFT / 2 + o;
+            float v = 0.f;
+            if (s >= 0 && s < n) {
+                if (I16) v = (float)((const int16_t*)p.in)[clip * p.in_stride + s] * (1.0f / 32768.0f);
+                else v = ((const float*)p.in)[clip * p.in_stride + s];
+            }
+            s_audio[i] = v;
+        }
+    } else {
+        const int c0 = t0 * p.hop - NFFT / 2;
+        for (int i = tid; i < cl; i += kThreads) {
+            const int s = c0 + i;
+            float v = 0.f;
+            if (s >= 0 && s < n) {
+                if (I16) v = (float)((const int16_t*)p.in)[clip * p.in_stride + s] * (1.0f / 32768.0f);
+                else v = ((const float*)p.in)[clip * p.in_stride + s];
+            }
+            s_audio[i] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- packed real FFT per frame -> spectrum tile -------------------------------------------
+    const int j = tid % T, slot = tid / T;
+    const bool even = (fstride & 1) == 0;
+#pragma unroll 1
+    for (int r = 0; r < C::ROUNDS; ++r) {
+        const int f = r * FR + slot;
+        float2* xb = s_xch + slot * G::XSTRIDE;
+        {
+            float2 v[16];
+            const float* a = s_audio + f * fstride + 2 * j;
+            if (even) {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) v[t] = *reinterpret_cast<const float2*>(a + 2 * T * t);
+            } else {
+#pragma unroll
+                for (int t = 0; t < 16; ++t) v[t] = make_float2(a[2 * T * t], a[2 * T * t + 1]);
+            }
+            Dft<16>::run(v);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) xb[xpad(16 * j + t)] = v[t];
+        }
+        frame_sync<T>();
+        fft_tail_passes<LOG2NC, false>(xb, s_tw, nullptr, j);
+        {
+            float2* sp = s_spec + f * C::SSTRIDE;
+#pragma unroll
+            for (int r2 = 0; r2 < 8; ++r2) {
+                const int k = j + T * r2;
+                float2 xk, xnk;
+                rfft_split(xb[xpad(k)], xb[xpad((NC - k) & (NC - 1))], s_tw2[k], xk, xnk);
+                sp[k] = make_float2(0.5f * xk.x, 0.5f * xk.y);
+                sp[NC - k] = make_float2(0.5f * xnk.x, 0.5f * xnk.y);
+            }
+            if (j == 0) {
+                const float2 A = xb[xpad(NC / 2)];
+                sp[NC / 2] = make_float2(A.x, -A.y);
+            }
+        }
+        frame_sync<T>();
+    }
+    __syncthreads();
+
+    // ---- banded complex basis product: item = (row, frame), frame fastest ---------------------
+    float vmax = 0.f, vmin = 3.0e38f;
+    for (int i = tid; i < p.n_rows * F; i += kThreads) {
+        const int b = i / F, f = i % F;
+        const float2* x = s_spec + f * C::SSTRIDE + s_k0[b];
+        const float2* g = s_basis + s_off[b];
+        const int cnt = s_cnt[b];
+        float ar = 0.f, ai = 0.f;
+        for (int qk = 0; qk < cnt; ++qk) {
+            const float2 gg = g[qk], xx = x[qk];
+            ar = fmaf(gg.x, xx.x, ar); ar = fmaf(-gg.y, xx.y, ar);
+            ai = fmaf(gg.x, xx.y, ai); ai = fmaf(gg.y, xx.x, ai);
+        }
+        const int t = t0 + f;
+        if (t < p.n_frames) {
+            const int row = p.row0 + b;
+            const float mag = sqrtf(ar * ar + ai * ai) * p.inv_sqrt_len[row];
+            p.out[clip * p.out_stride + (size_t)row * p.n_frames + t] = mag;
+            vmax = fmaxf(vmax, mag);
+            vmin = fminf(vmin, mag);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    }
+    if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < kThreads / 32; ++w) { vmax = fmaxf(vmax, s_red[w]); vmin = fminf(vmin, s_red[32 + w]); }
+        atomicMax(p.clip_max + clip, __float_as_uint(vmax));     // magnitudes are >= 0
+        atomicMin(p.clip_min + clip, __float_as_uint(vmin));
+    }
+}
+
+// amplitude_to_db(ref=np.max, amin=1e-5, top_db) then _normalize (deep.py:259-260)
+__global__ void __launch_bounds__(kThreads) cqt_finalize_kernel(float* out, size_t out_stride, int total,
+                                                               const unsigned int* clip_max,
+                                                               const unsigned int* clip_min, float top_db) {
+    const size_t clip = blockIdx.x;
+    const float mx = __uint_as_float(clip_max[clip]), mn = __uint_as_float(clip_min[clip]);
+    auto db = [](float pw) { return 3.01029995663981195f * __log2f(fmaxf(pw, 1e-10f)); };
+    const float vref = db(mx * mx);
+    const float lo = fmaxf(db(mn * mn) - vref, -top_db);
+    const float range = (0.0f - lo) + 1e-8f;
+    float* o = out + clip * out_stride;
+    for (int i = threadIdx.x; i < total; i += kThreads) {
+        const float m = o[i];
+        const float L = fmaxf(db(m * m) - vref, -top_db);
+        o[i] = __fdiv_rn(L - lo, range);
+    }
+}
+
+__global__ void cqt_init_minmax(unsigned int* mx, unsigned int* mn, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { mx[i] = 0u; mn[i] = 0x7f7fffffu; }
+}
+
+template <int LOG2NC>
+cudaError_t launch_oct(const OctParams& p, bool i16, dim3 grid, size_t smem, cudaStream_t st) {
+    if (i16) {
+        auto k = cqt_octave_kernel<LOG2NC, true>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, kThreads, smem, st>>>(p);
+    } else {
+        auto k = cqt_octave_kernel<LOG2NC, false>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<grid, kThreads, smem, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t up(const std::vector<T>& v, T** d) {
+    *d = nullptr;
+    if (v.empty()) return cudaSuccess;
+    cudaError_t e = cudaMalloc((void**)d, v.size() * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
+
+}  // namespace
+
+#define CQ_TRY(expr)                                                                       \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            *err = std::string(#expr) + ": " + cudaGetErrorString(e__);                    \
+            return e__ == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA;              \
+        }                                                                                  \
+    } while (0)
+
+void cqt_device_free(CqtDevice* d) {
+    cudaFree(d->scratch); cudaFree(d->taps); cudaFree(d->inv_sqrt_len);
+    cudaFree(d->clip_max); cudaFree(d->clip_min);
+    for (int i = 0; i < 16; ++i) { cudaFree(d->tw[i]); cudaFree(d->tw2[i]); }
+    for (auto& o : d->oct) { cudaFree(o.basis); cudaFree(o.k0); cudaFree(o.cnt); cudaFree(o.off); }
+    *d = CqtDevice();
+}
+
+int cqt_device_init(const CqtPlan& plan, const b2a_config& cfg, int sm_count, size_t smem_optin,
+                    CqtDevice* dev, std::string* err) {
+    dev->sm_count = sm_count;
+    // decimator taps (float32 of the double design)
+    {
+        std::vector<float> t;
+        for (double v : decimator_taps()) t.push_back((float)v);
+        CQ_TRY(up(t, &dev->taps));
+    }
+    {
+        std::vector<float> isl;
+        for (double l : plan.lengths) isl.push_back((float)(1.0 / std::sqrt(l)));
+        CQ_TRY(up(isl, &dev->inv_sqrt_len));
+    }
+    // scratch layout per clip: early-downsample outputs, then one signal per decimated octave
+    size_t off = 0;
+    int len = cfg.n_samples;
+    for (int e = 0; e < plan.n_early; ++e) {
+        len = (len + 1) / 2;
+        dev->early_offs.push_back(off);
+        dev->early_lens.push_back(len);
+        off += ((size_t)len + 3) & ~(size_t)3;
+    }
+    dev->oct.resize(plan.n_octaves);
+    size_t cur_off = plan.n_early ? dev->early_offs.back() : (size_t)-1;   // (size_t)-1: the input itself
+    for (int i = 0; i < plan.n_octaves; ++i) {
+        const CqtOctave& o = plan.oct[i];
+        CqtOctaveDev& od = dev->oct[i];
+        od.sig_off = cur_off;
+        od.log2nc = ilog2(o.n_fft / 2);
+        if (od.log2nc < 7 || od.log2nc > 9) {
+            *err = "cqt: per-octave n_fft " + std::to_string(o.n_fft) + " unsupported (256..1024)";
+            return B2A_EINVAL;
+        }
+        // band each row of the sparsified basis
+        const int n_bins = o.n_fft / 2 + 1;
+        std::vector<float2> bw;
+        std::vector<int> k0(o.n_rows), cnt(o.n_rows), offv(o.n_rows);
+        for (int r = 0; r < o.n_rows; ++r) {
+            int lo = n_bins, hi = -1;
+            for (int k = 0; k < n_bins; ++k) {
+                const float re = o.basis[((size_t)r * n_bins + k) * 2], im = o.basis[((size_t)r * n_bins + k) * 2 + 1];
+                if (re != 0.f || im != 0.f) { lo = std::min(lo, k); hi = std::max(hi, k); }
+            }
+            offv[r] = (int)bw.size();
+            if (hi < 0) { k0[r] = 0; cnt[r] = 0; continue; }
+            k0[r] = lo; cnt[r] = hi - lo + 1;
+            for (int k = lo; k <= hi; ++k)
+                bw.push_back(make_float2(o.basis[((size_t)r * n_bins + k) * 2], o.basis[((size_t)r * n_bins + k) * 2 + 1]));
+        }
+        od.nnz = (int)bw.size();
+        if (bw.empty()) bw.push_back(make_float2(0.f, 0.f));
+        CQ_TRY(up(bw, &od.basis));
+        CQ_TRY(up(k0, &od.k0));
+        CQ_TRY(up(cnt, &od.cnt));
+        CQ_TRY(up(offv, &od.off));
+        if (oct_smem_bytes(od.log2nc, o.hop, o.n_rows, od.nnz) > smem_optin) {
+            *err = "cqt: octave working set exceeds shared memory";
+            return B2A_EINVAL;
+        }
+        if (!dev->tw[od.log2nc]) {
+            const int NC = o.n_fft / 2;
+            std::vector<float> a = twiddles(NC, NC), b = twiddles(2 * NC, NC / 2 + 1);
+            CQ_TRY(up(a, (float**)&dev->tw[od.log2nc]));
+            CQ_TRY(up(b, (float**)&dev->tw2[od.log2nc]));
+        }
+        if (o.decimate_after && i + 1 < plan.n_octaves) {
+            cur_off = off;
+            off += ((size_t)((o.sig_len + 1) / 2) + 3) & ~(size_t)3;
+        }
+    }
+    dev->scratch_per_clip = off;
+    dev->chunk_clips = 1024;
+    if (off) CQ_TRY(cudaMalloc((void**)&dev->scratch, dev->chunk_clips * off * sizeof(float)));
+    CQ_TRY(cudaMalloc((void**)&dev->clip_max, dev->chunk_clips * sizeof(unsigned int)));
+    CQ_TRY(cudaMalloc((void**)&dev->clip_min, dev->chunk_clips * sizeof(unsigned int)));
+    return 0;
+}
+
+int cqt_run(const CqtPlan& plan, const b2a_config& cfg, CqtDevice* dev, const void* d_clips,
+            int64_t n_clips, float* d_out, cudaStream_t st, int64_t* launches, std::string* err) {
+    const bool in_i16 = cfg.input_dtype == B2A_IN_I16;
+    const size_t in_elem = in_i16 ? 2 : 4;
+    const int rows = cfg.n_bins, nfr = plan.n_frames;
+    const size_t out_stride = (size_t)rows * nfr;
+    for (int64_t c0 = 0; c0 < n_clips; c0 += dev->chunk_clips) {
+        const int nb = (int)std::min<int64_t>(dev->chunk_clips, n_clips - c0);
+        const void* in = (const unsigned char*)d_clips + (size_t)c0 * cfg.n_samples * in_elem;
+        float* out = d_out + (size_t)c0 * out_stride;
+        cqt_init_minmax<<<(nb + 255) / 256, 256, 0, st>>>(dev->clip_max, dev->clip_min, nb);
+        CQ_TRY(cudaGetLastError());
+        ++*launches;
+        // current signal descriptor
+        const void* sig = in; size_t sig_stride = cfg.n_samples; int sig_len = cfg.n_samples; bool sig_i16 = in_i16;
+        auto decimate = [&](size_t dst_off, int dst_len) -> cudaError_t {
+            float* dst = dev->scratch + dst_off;
+            dim3 grid((dst_len + kDecTile - 1) / kDecTile, nb);
+            if (sig_i16) cqt_decimate_kernel<true><<<grid, kDecThreads, 0, st>>>(sig, sig_stride, sig_len, dst, dev->scratch_per_clip, dst_len, dev->taps);
+            else cqt_decimate_kernel<false><<<grid, kDecThreads, 0, st>>>(sig, sig_stride, sig_len, dst, dev->scratch_per_clip, dst_len, dev->taps);
+            ++*launches;
+            sig = dst; sig_stride = dev->scratch_per_clip; sig_len = dst_len; sig_i16 = false;
+            return cudaGetLastError();
+        };
+        for (int e = 0; e < plan.n_early; ++e) CQ_TRY(decimate(dev->early_offs[e], dev->early_lens[e]));
+        for (int i = 0; i < plan.n_octaves; ++i) {
+            const CqtOctave& o = plan.oct[i];
+            const CqtOctaveDev& od = dev->oct[i];
+            OctParams p{};
+            p.in = sig; p.in_stride = sig_stride; p.in_len = sig_len;
+            p.hop = o.hop; p.n_frames = nfr; p.n_rows = o.n_rows; p.row0 = o.row0; p.nnz = od.nnz;
+            p.tw = dev->tw[od.log2nc]; p.tw2 = dev->tw2[od.log2nc];
+            p.basis = od.basis; p.k0 = od.k0; p.cnt = od.cnt; p.off = od.off;
+            p.inv_sqrt_len = dev->inv_sqrt_len;
+            p.out = out; p.out_stride = out_stride;
+            p.clip_max = dev->clip_max; p.clip_min = dev->clip_min;
+            const int F = od.log2nc <= 8 ? 32 : 16;
+            dim3 grid((nfr + F - 1) / F, nb);
+            const size_t smem = oct_smem_bytes(od.log2nc, o.hop, o.n_rows, od.nnz);
+            cudaError_t e = cudaSuccess;
+            switch (od.log2nc) {
+                case 7: e = launch_oct<7>(p, sig_i16, grid, smem, st); break;
+                case 8: e = launch_oct<8>(p, sig_i16, grid, smem, st); break;
+                case 9: e = launch_oct<9>(p, sig_i16, grid, smem, st); break;
+                default: e = cudaErrorInvalidValue;
+            }
+            CQ_TRY(e);
+            ++*launches;
+            if (o.decimate_after && i + 1 < plan.n_octaves)
+                CQ_TRY(decimate(dev->oct[i + 1].sig_off, (sig_len + 1) / 2));
+        }
+        cqt_finalize_kernel<<<nb, kThreads, 0, st>>>(out, out_stride, rows * nfr, dev->clip_max, dev->clip_min, cfg.top_db);
+        CQ_TRY(cudaGetLastError());
+        ++*launches;
+    }
+    return 0;
+}
+
+}  // namespace b2a

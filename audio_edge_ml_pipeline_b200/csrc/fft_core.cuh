@@ -1,0 +1,193 @@
+// fft_core.cuh — register-resident radix-2/4/8/16 butterflies and the per-frame real FFT.
+//
+// A real frame of n_fft = 2*NC samples is packed as NC complex points z[n] = x[2n] + i x[2n+1],
+// transformed by a Stockham autosort FFT whose passes keep 16 complex points per thread in
+// registers (T = NC/16 threads per frame, passes exchange through padded shared memory), and
+// un-packed by the usual split step X[k] = E[k] + W_{2NC}^k O[k].
+//
+//   NC = 128 : radix 16, 8          (n_fft  256, CQT)
+//   NC = 256 : radix 16, 16         (n_fft  512, the headline log-mel configuration)
+//   NC = 512 : radix 16, 16, 2      (n_fft 1024)
+//   NC = 1024: radix 16, 16, 4      (n_fft 2048)
+//
+// Replaces scipy.fft.rfft inside librosa.stft (reference call site deep.py:126-132).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace b2a {
+
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+// multiply by -i
+__device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+#define B2A_SQRT1_2 0.70710678118654752440f
+#define B2A_COS_PI_8 0.92387953251128675613f
+#define B2A_SIN_PI_8 0.38268343236508977173f
+
+// In-place forward DFT (e^{-2 pi i nk/N}), natural order in and out.
+template <int N> struct Dft;
+
+template <> struct Dft<1> {
+    static __device__ __forceinline__ void run(float2*) {}
+};
+template <> struct Dft<2> {
+    static __device__ __forceinline__ void run(float2* v) {
+        const float2 a = v[0], b = v[1];
+        v[0] = cadd(a, b); v[1] = csub(a, b);
+    }
+};
+template <> struct Dft<4> {
+    static __device__ __forceinline__ void run(float2* v) {
+        const float2 t0 = cadd(v[0], v[2]), t1 = csub(v[0], v[2]);
+        const float2 t2 = cadd(v[1], v[3]), t3 = cmul_mi(csub(v[1], v[3]));
+        v[0] = cadd(t0, t2); v[2] = csub(t0, t2);
+        v[1] = cadd(t1, t3); v[3] = csub(t1, t3);
+    }
+};
+template <> struct Dft<8> {
+    static __device__ __forceinline__ void run(float2* v) {
+        float2 e[4] = {v[0], v[2], v[4], v[6]};
+        float2 o[4] = {v[1], v[3], v[5], v[7]};
+        Dft<4>::run(e); Dft<4>::run(o);
+        // W8^1 = s(1 - i), W8^2 = -i, W8^3 = s(-1 - i)
+        const float2 o1 = make_float2((o[1].x + o[1].y) * B2A_SQRT1_2, (o[1].y - o[1].x) * B2A_SQRT1_2);
+        const float2 o2 = cmul_mi(o[2]);
+        const float2 o3 = make_float2((o[3].y - o[3].x) * B2A_SQRT1_2, -(o[3].x + o[3].y) * B2A_SQRT1_2);
+        v[0] = cadd(e[0], o[0]); v[4] = csub(e[0], o[0]);
+        v[1] = cadd(e[1], o1);   v[5] = csub(e[1], o1);
+        v[2] = cadd(e[2], o2);   v[6] = csub(e[2], o2);
+        v[3] = cadd(e[3], o3);   v[7] = csub(e[3], o3);
+    }
+};
+template <> struct Dft<16> {
+    static __device__ __forceinline__ void run(float2* v) {
+        float2 e[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+        Dft<8>::run(e); Dft<8>::run(o);
+        const float c1 = B2A_COS_PI_8, s1 = B2A_SIN_PI_8, s = B2A_SQRT1_2;
+        // W16^k = (cos(k pi/8), -sin(k pi/8))
+        const float2 t1 = cmul(o[1], make_float2(c1, -s1));
+        const float2 t2 = make_float2((o[2].x + o[2].y) * s, (o[2].y - o[2].x) * s);
+        const float2 t3 = cmul(o[3], make_float2(s1, -c1));
+        const float2 t4 = cmul_mi(o[4]);
+        const float2 t5 = cmul(o[5], make_float2(-s1, -c1));
+        const float2 t6 = make_float2((o[6].y - o[6].x) * s, -(o[6].x + o[6].y) * s);
+        const float2 t7 = cmul(o[7], make_float2(-c1, -s1));
+        v[0] = cadd(e[0], o[0]); v[8]  = csub(e[0], o[0]);
+        v[1] = cadd(e[1], t1);   v[9]  = csub(e[1], t1);
+        v[2] = cadd(e[2], t2);   v[10] = csub(e[2], t2);
+        v[3] = cadd(e[3], t3);   v[11] = csub(e[3], t3);
+        v[4] = cadd(e[4], t4);   v[12] = csub(e[4], t4);
+        v[5] = cadd(e[5], t5);   v[13] = csub(e[5], t5);
+        v[6] = cadd(e[6], t6);   v[14] = csub(e[6], t6);
+        v[7] = cadd(e[7], t7);   v[15] = csub(e[7], t7);
+    }
+};
+
+// Exchange-buffer padding: one float2 of padding after every 16 keeps the stride-16 (pass 1
+// store) and unit-stride (pass 2 load) patterns conflict-free for 64-bit accesses.
+__device__ __forceinline__ int xpad(int i) { return i + (i >> 4); }
+
+template <int LOG2NC> struct FftGeom {
+    static constexpr int NC = 1 << LOG2NC;          // complex points
+    static constexpr int NFFT = 2 * NC;             // real frame length
+    static constexpr int T = NC / 16;               // threads per frame
+    static constexpr int R1 = (LOG2NC >= 8) ? 16 : (1 << (LOG2NC - 4));
+    static constexpr int R2 = (LOG2NC > 8) ? (1 << (LOG2NC - 8)) : 1;
+    static constexpr int XSTRIDE = NC + NC / 16;    // float2 per frame slot in the exchange buffer
+    static constexpr int PSTRIDE = NC + 1;          // floats per frame in the power tile (odd)
+    static_assert(LOG2NC >= 7 && LOG2NC <= 10, "n_fft must be 256..2048");
+};
+
+// Synchronise the T threads that share one frame.
+template <int T> __device__ __forceinline__ void frame_sync() {
+    if constexpr (T <= 32) __syncwarp(); else __syncthreads();
+}
+
+// Passes 2.. of the packed FFT on one frame.  `xb` is this frame's exchange slot holding the
+// output of pass 1 (index 16*j + t, padded); on return it holds Z[0..NC) in natural order.
+// `tw` = exp(-2 pi i k / NC), k in [0, NC), in shared memory.  `tw1` (optional) = this thread's
+// pass-2 twiddles hoisted to registers by the caller when R1 == 16 && 16/R1 == 1.
+template <int LOG2NC, bool HOISTED>
+__device__ __forceinline__ void fft_tail_passes(float2* __restrict__ xb, const float2* __restrict__ tw,
+                                                const float2* tw1, int j) {
+    using G = FftGeom<LOG2NC>;
+    constexpr int NC = G::NC, T = G::T, R1 = G::R1, R2 = G::R2;
+    float2 v[16];
+    // ---- pass 2: radix R1, Ns = 16 --------------------------------------------------------
+    {
+        constexpr int NB = 16 / R1;                 // butterflies per thread
+        constexpr int STR = NC / R1;                // input stride
+        constexpr int TWS = NC / (16 * R1);         // twiddle index scale
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int jb = j + T * u;
+            const int k = jb & 15;
+#pragma unroll
+            for (int t = 0; t < R1; ++t) {
+                float2 x = xb[xpad(jb + t * STR)];
+                if (t > 0) {
+                    const float2 w = HOISTED ? tw1[t - 1] : tw[(t * k) * TWS];
+                    x = cmul(x, w);
+                }
+                v[u * R1 + t] = x;
+            }
+            Dft<R1>::run(&v[u * R1]);
+        }
+        frame_sync<T>();
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int jb = j + T * u;
+            const int k = jb & 15;
+            const int base = (jb - k) * R1 + k;
+#pragma unroll
+            for (int t = 0; t < R1; ++t) xb[xpad(base + t * 16)] = v[u * R1 + t];
+        }
+        frame_sync<T>();
+    }
+    // ---- pass 3: radix R2, Ns = 256 -------------------------------------------------------
+    if constexpr (R2 > 1) {
+        constexpr int NB = 16 / R2;
+        constexpr int STR = NC / R2;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int jb = j + T * u;               // in [0, NC/R2) = [0, 256)
+            const int k = jb & 255;
+#pragma unroll
+            for (int t = 0; t < R2; ++t) {
+                float2 x = xb[xpad(jb + t * STR)];
+                if (t > 0) x = cmul(x, tw[t * k]);  // NC/(256*R2) == 1
+                v[u * R2 + t] = x;
+            }
+            Dft<R2>::run(&v[u * R2]);
+        }
+        frame_sync<T>();
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int jb = j + T * u;
+            const int k = jb & 255;
+            const int base = (jb - k) * R2 + k;
+#pragma unroll
+            for (int t = 0; t < R2; ++t) xb[xpad(base + t * 256)] = v[u * R2 + t];
+        }
+        frame_sync<T>();
+    }
+}
+
+// Split step for one (k, NC-k) pair of the packed transform.
+//   A = Z[k], Bz = Z[NC-k] (Z[NC] == Z[0]), w = exp(-i pi k / NC)
+//   returns 2*X[k] in xk and 2*X[NC-k] in xnk  (the factor 2 is removed by the caller)
+__device__ __forceinline__ void rfft_split(float2 A, float2 Bz, float2 w, float2& xk, float2& xnk) {
+    const float2 E = make_float2(A.x + Bz.x, A.y - Bz.y);
+    const float2 O = make_float2(A.y + Bz.y, Bz.x - A.x);
+    const float2 Tt = cmul(O, w);
+    xk = make_float2(E.x + Tt.x, E.y + Tt.y);
+    xnk = make_float2(E.x - Tt.x, -(E.y - Tt.y));
+}
+
+}  // namespace b2a

@@ -1,0 +1,347 @@
+// frontend.cu — fused STFT -> power -> mel -> dB -> normalise kernels (audio_mel_spec,
+// audio_mfcc_seq).  sm_100a only.
+//
+// One persistent CTA owns one clip at a time (clips are independent; the only reductions —
+// ref=np.max, min/max, per-coefficient mean/std — are per clip: deep.py:64-67,133,326-328).
+// Per tile of F frames:
+//   1. stage the samples the tile touches into shared memory ONCE as fp32 (int16 -> x/32768
+//      exactly as librosa.load does; frames overlap n_fft/hop times so this amortises the
+//      conversion), zeros (or the reflected sample) outside [0, n_samples): librosa.stft
+//      centre padding, deep.py:126-132 via melspectrogram;
+//   2. per frame: window x packed real FFT (fft_core.cuh) -> |X|^2 into a [frame][bin] tile;
+//   3. banded mel dot products (lane = frame, so filter weights are warp-uniform) -> 10 log10;
+//      raw dB goes to global memory (L2-resident, re-read by the same CTA a few us later) and
+//      the running per-clip max / min stay in registers.
+// Then per clip: power_to_db(ref=max, top_db) + min-max (mel) or top_db clip + DCT-II +
+// per-row z-score (mfcc), rewriting the L2-hot tile in place.
+#include "frontend.h"
+#include "fft_core.cuh"
+
+#include <cstdint>
+
+namespace b2a {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ float db10(float s) {
+    // 10*log10(max(amin, s)); lg2.approx abs error 2^-22 -> < 1e-5 dB, 1e-7 of the 80 dB range
+    return 3.01029995663981195f * __log2f(fmaxf(s, 1e-10f));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <bool I16>
+__device__ __forceinline__ float load_sample(const void* clip, int s, int n, int pad_mode) {
+    if (s < 0 || s >= n) {
+        if (pad_mode == 0) return 0.f;
+        s = (s < 0) ? -s : 2 * (n - 1) - s;      // np.pad(mode="reflect")
+        if (s < 0 || s >= n) return 0.f;
+    }
+    if (I16) return (float)((const int16_t*)clip)[s] * (1.0f / 32768.0f);
+    return ((const float*)clip)[s];
+}
+
+// Stage samples [c0, c0+len) of one clip into smem as fp32.
+template <bool I16>
+__device__ __forceinline__ void stage_audio(float* __restrict__ dst, const void* __restrict__ clip,
+                                            long long clip_elem0, int c0, int len, int n, int pad_mode,
+                                            bool base_aligned) {
+    constexpr int V = I16 ? 8 : 4;               // elements per 16-byte load
+    const bool aligned = base_aligned && (((clip_elem0 + c0) & (V - 1)) == 0);
+    const int groups = (len + V - 1) / V;
+    for (int g = threadIdx.x; g < groups; g += kThreads) {
+        const int i = g * V, s = c0 + i;
+        if (aligned && s >= 0 && s + V <= n && i + V <= len) {
+            if (I16) {
+                const int4 raw = __ldg(reinterpret_cast<const int4*>((const int16_t*)clip + s));
+                const int r[4] = {raw.x, raw.y, raw.z, raw.w};
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    f[2 * e] = (float)(short)(r[e] & 0xffff) * (1.0f / 32768.0f);
+                    f[2 * e + 1] = (float)(r[e] >> 16) * (1.0f / 32768.0f);
+                }
+                *reinterpret_cast<float4*>(dst + i) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(dst + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
+            } else {
+                *reinterpret_cast<float4*>(dst + i) =
+                    __ldg(reinterpret_cast<const float4*>((const float*)clip + s));
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < V; ++e)
+                if (i + e < len) dst[i + e] = load_sample<I16>(clip, s + e, n, pad_mode);
+        }
+    }
+}
+
+template <int LOG2NC> struct FrontCfg {
+    using G = FftGeom<LOG2NC>;
+    static constexpr int F = (LOG2NC <= 8) ? 32 : 16;                 // frames per tile
+    static constexpr int FR = kThreads / G::T;                        // frames per FFT round
+    static constexpr int ROUNDS = (F + FR - 1) / FR;
+    static constexpr int MINB = (LOG2NC <= 8) ? 2 : 1;
+};
+
+size_t front_smem_bytes(int log2nc, int hop, int n_mels, int mel_nnz) {
+    const int NC = 1 << log2nc, n_fft = 2 * NC, T = NC / 16;
+    const int F = (log2nc <= 8) ? 32 : 16;
+    const int FR = kThreads / T;
+    const int slots = FR < F ? FR : F;
+    size_t cl = (size_t)hop * (F - 1) + n_fft;
+    cl = (cl + 7) & ~(size_t)7;
+    size_t b = 0;
+    b += cl * 4;                                        // audio
+    b += (size_t)slots * (NC + NC / 16) * 8;            // exchange
+    b += (size_t)F * (NC + 1) * 4;                      // power tile
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)NC * 8;                                // tw
+    b += (size_t)(NC / 2 + 1) * 8;                      // tw2
+    b += (size_t)n_mels * 3 * 4 + (size_t)mel_nnz * 4;  // banded mel
+    b += 128 * 4;                                       // reduction scratch
+    return b + 64;
+}
+
+template <int LOG2NC, bool I16, int KIND>
+__global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel(FrontParams p) {
+    using G = FftGeom<LOG2NC>;
+    using C = FrontCfg<LOG2NC>;
+    constexpr int NC = G::NC, NFFT = G::NFFT, T = G::T, F = C::F, FR = C::FR;
+    constexpr int SLOTS = FR;
+    static_assert(FR <= F && F % FR == 0, "tile must be a whole number of FFT rounds");
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int cl = (p.hop * (F - 1) + NFFT + 7) & ~7;
+    float* s_audio = reinterpret_cast<float*>(smem_raw);
+    float2* s_xch = reinterpret_cast<float2*>(s_audio + cl);
+    float* s_pow = reinterpret_cast<float*>(s_xch + SLOTS * G::XSTRIDE);
+    uintptr_t q = reinterpret_cast<uintptr_t>(s_pow + F * G::PSTRIDE);
+    q = (q + 15) & ~(uintptr_t)15;
+    float2* s_tw = reinterpret_cast<float2*>(q);
+    float2* s_tw2 = s_tw + NC;
+    int* s_k0 = reinterpret_cast<int*>(s_tw2 + NC / 2 + 1);
+    int* s_cnt = s_k0 + p.n_mels;
+    int* s_off = s_cnt + p.n_mels;
+    float* s_w = reinterpret_cast<float*>(s_off + p.n_mels);
+    float* s_red = s_w + p.mel_nnz;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // ---- per-CTA tables ---------------------------------------------------------------------
+    for (int i = tid; i < NC; i += kThreads) s_tw[i] = p.tw[i];
+    for (int i = tid; i < NC / 2 + 1; i += kThreads) s_tw2[i] = p.tw2[i];
+    for (int i = tid; i < p.n_mels; i += kThreads) { s_k0[i] = p.mel_k0[i]; s_cnt[i] = p.mel_cnt[i]; s_off[i] = p.mel_off[i]; }
+    for (int i = tid; i < p.mel_nnz; i += kThreads) s_w[i] = p.mel_w[i];
+
+    // ---- per-thread constants (loop invariant over frames and clips) -----------------------
+    const int j = tid % T;                 // position inside the frame's thread group
+    const int slot = tid / T;              // frame slot inside an FFT round
+    float2 win[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int n = j + T * t;
+        win[t] = make_float2(__ldg(p.window + 2 * n), __ldg(p.window + 2 * n + 1));
+    }
+    constexpr bool HOIST = (LOG2NC == 8);
+    float2 tw1[HOIST ? 15 : 1];
+    if constexpr (HOIST) {
+#pragma unroll
+        for (int t = 1; t < 16; ++t) tw1[t - 1] = p.tw[t * j];
+    }
+    __syncthreads();
+
+    const int n = p.n_samples, nfr = p.n_frames, n_mels = p.n_mels;
+    const bool hop_even = (p.hop & 1) == 0;
+    const size_t esz = I16 ? 2 : 4;
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
+
+    for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
+        const long long clip_elem0 = clip * (long long)n;
+        const void* cptr = (const unsigned char*)p.clips + (size_t)clip_elem0 * esz;
+        float* inter = (KIND == 0) ? p.out + (size_t)clip * n_mels * nfr
+                                   : p.inter + (size_t)blockIdx.x * n_mels * nfr;
+        float vmax = -3.0e38f, vmin = 3.0e38f;
+
+        for (int t0 = 0; t0 < nfr; t0 += F) {
+            // (1) stage audio for frames [t0, t0+F)
+            stage_audio<I16>(s_audio, cptr, clip_elem0, t0 * p.hop - NFFT / 2, cl, n, p.pad_mode, base_aligned);
+            __syncthreads();
+
+            // (2) FFT rounds
+#pragma unroll 1
+            for (int r = 0; r < C::ROUNDS; ++r) {
+                const int f = r * FR + slot;               // frame inside the tile
+                float2* xb = s_xch + slot * G::XSTRIDE;
+                {
+                    float2 v[16];
+                    const float* a = s_audio + f * p.hop + 2 * j;
+                    if (hop_even) {
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const float2 x = *reinterpret_cast<const float2*>(a + 2 * T * t);
+                            v[t] = make_float2(x.x * win[t].x, x.y * win[t].y);
+                        }
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 16; ++t)
+                            v[t] = make_float2(a[2 * T * t] * win[t].x, a[2 * T * t + 1] * win[t].y);
+                    }
+                    Dft<16>::run(v);
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) xb[xpad(16 * j + t)] = v[t];
+                }
+                frame_sync<T>();
+                fft_tail_passes<LOG2NC, HOIST>(xb, s_tw, tw1, j);
+                {
+                    float* pw = s_pow + f * G::PSTRIDE;
+#pragma unroll
+                    for (int r2 = 0; r2 < 8; ++r2) {
+                        const int k = j + T * r2;
+                        const float2 A = xb[xpad(k)];
+                        const float2 B = xb[xpad((NC - k) & (NC - 1))];
+                        float2 xk, xnk;
+                        rfft_split(A, B, s_tw2[k], xk, xnk);
+                        pw[k] = 0.25f * (xk.x * xk.x + xk.y * xk.y);
+                        pw[NC - k] = 0.25f * (xnk.x * xnk.x + xnk.y * xnk.y);
+                    }
+                    if (j == 0) {
+                        const float2 A = xb[xpad(NC / 2)];
+                        pw[NC / 2] = A.x * A.x + A.y * A.y;      // X[NC/2] = conj(Z[NC/2])
+                    }
+                }
+                frame_sync<T>();
+            }
+            __syncthreads();
+
+            // (3) mel bands for the tile: item = (band, frame), frame fastest
+            for (int i = tid; i < n_mels * F; i += kThreads) {
+                const int m = i / F, f = i % F;
+                const float* pf = s_pow + f * G::PSTRIDE + s_k0[m];
+                const float* w = s_w + s_off[m];
+                const int cnt = s_cnt[m];
+                float acc = 0.f;
+#pragma unroll 4
+                for (int qk = 0; qk < cnt; ++qk) acc = fmaf(w[qk], pf[qk], acc);
+                const int t = t0 + f;
+                if (t < nfr) {
+                    const float v = db10(acc);
+                    inter[(size_t)m * nfr + t] = v;
+                    vmax = fmaxf(vmax, v);
+                    vmin = fminf(vmin, v);
+                }
+            }
+            // no barrier needed here: the next stage_audio only touches s_audio, and every thread
+            // passes the barrier after it only once its own mel items are done.
+        }
+
+        // ---- per-clip reductions ---------------------------------------------------------------
+        vmax = warp_max(vmax); vmin = warp_min(vmin);
+        if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
+        __syncthreads();      // also makes the tile's global writes visible to the whole CTA
+        {
+            float a = (lane < kThreads / 32) ? s_red[lane] : -3.0e38f;
+            float b = (lane < kThreads / 32) ? s_red[32 + lane] : 3.0e38f;
+            vmax = warp_max(a); vmin = warp_min(b);
+        }
+
+        if constexpr (KIND == 0) {
+            // power_to_db(ref=np.max, top_db) then _normalize  (deep.py:133-134, :64-67)
+            const float lo = fmaxf(vmin - vmax, -p.top_db);
+            const float range = (0.0f - lo) + 1e-8f;
+            const int total = n_mels * nfr;
+            if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(inter) & 15) == 0)) {
+                float4* o4 = reinterpret_cast<float4*>(inter);
+                for (int i = tid; i < total / 4; i += kThreads) {
+                    float4 v = o4[i];
+                    v.x = __fdiv_rn(fmaxf(v.x - vmax, -p.top_db) - lo, range);
+                    v.y = __fdiv_rn(fmaxf(v.y - vmax, -p.top_db) - lo, range);
+                    v.z = __fdiv_rn(fmaxf(v.z - vmax, -p.top_db) - lo, range);
+                    v.w = __fdiv_rn(fmaxf(v.w - vmax, -p.top_db) - lo, range);
+                    o4[i] = v;
+                }
+            } else {
+                for (int i = tid; i < total; i += kThreads)
+                    inter[i] = __fdiv_rn(fmaxf(inter[i] - vmax, -p.top_db) - lo, range);
+            }
+        } else {
+            // librosa.feature.mfcc: power_to_db(ref=1.0, top_db) -> DCT-II ortho -> rows [0, n_mfcc)
+            // then deep.py:326-328 per-row z-score.
+            float* outc = p.out + (size_t)clip * p.n_mfcc * nfr;
+            const float thr = vmax - p.top_db;
+            float* s_l = s_pow;                       // [n_mels][32] tile of clipped dB
+            for (int t0 = 0; t0 < nfr; t0 += 32) {
+                __syncthreads();
+                for (int i = tid; i < n_mels * 32; i += kThreads) {
+                    const int m = i >> 5, f = i & 31, t = t0 + f;
+                    s_l[i] = (t < nfr) ? fmaxf(inter[(size_t)m * nfr + t], thr) : 0.f;
+                }
+                __syncthreads();
+                for (int i = tid; i < p.n_mfcc * 32; i += kThreads) {
+                    const int k = i >> 5, f = i & 31, t = t0 + f;
+                    const float* d = p.dct + (size_t)k * n_mels;
+                    float acc = 0.f;
+#pragma unroll 4
+                    for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(d + m), s_l[m * 32 + f], acc);
+                    if (t < nfr) outc[(size_t)k * nfr + t] = acc;
+                }
+            }
+            __syncthreads();
+            const float inv_n = 1.0f / (float)nfr;
+            for (int k = warp; k < p.n_mfcc; k += kThreads / 32) {
+                float* row = outc + (size_t)k * nfr;
+                float s = 0.f;
+                for (int t = lane; t < nfr; t += 32) s += row[t];
+                const float mean = warp_sum(s) * inv_n;
+                float ss = 0.f;
+                for (int t = lane; t < nfr; t += 32) { const float d = row[t] - mean; ss = fmaf(d, d, ss); }
+                const float sd = sqrtf(warp_sum(ss) * inv_n) + 1e-8f;
+                for (int t = lane; t < nfr; t += 32) row[t] = __fdiv_rn(row[t] - mean, sd);
+            }
+        }
+        __syncthreads();     // s_red / s_pow reuse by the next clip
+    }
+}
+
+template <int LOG2NC, bool I16, int KIND>
+static cudaError_t launch_one(const FrontParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto k = front_kernel<LOG2NC, I16, KIND>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+template <int LOG2NC>
+static cudaError_t launch_l(const FrontParams& p, bool i16, int kind, int grid, size_t smem, cudaStream_t st) {
+    if (kind == 0) return i16 ? launch_one<LOG2NC, true, 0>(p, grid, smem, st) : launch_one<LOG2NC, false, 0>(p, grid, smem, st);
+    return i16 ? launch_one<LOG2NC, true, 1>(p, grid, smem, st) : launch_one<LOG2NC, false, 1>(p, grid, smem, st);
+}
+
+int front_ctas_per_sm(int log2nc) { return log2nc <= 8 ? 2 : 1; }
+
+cudaError_t launch_front(const FrontParams& p, int log2nc, bool i16, int kind, int grid, cudaStream_t st) {
+    const size_t smem = front_smem_bytes(log2nc, p.hop, p.n_mels, p.mel_nnz);
+    switch (log2nc) {
+        case 7: return launch_l<7>(p, i16, kind, grid, smem, st);
+        case 8: return launch_l<8>(p, i16, kind, grid, smem, st);
+        case 9: return launch_l<9>(p, i16, kind, grid, smem, st);
+        case 10: return launch_l<10>(p, i16, kind, grid, smem, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace b2a

@@ -1,0 +1,131 @@
+/* b2a.h — C ABI of the B200-native Stage-2 audio feature-extraction path.
+ *
+ * Drop-in boundary for ONE hot path of gcpgarcias/audio-edge-ml-pipeline: the arithmetic behind
+ * the `audio_mel_spec`, `audio_mfcc_seq` and `audio_cqt` extractors
+ * (reference: src/preprocessing/feature_extraction/audio/deep.py:75-134, 196-260, 268-328),
+ * i.e. everything those classes delegate to librosa 0.11.0 between "decoded, padded/trimmed
+ * mono clip" and "normalised float32 feature matrix".
+ *
+ * Nothing in the reference calls C on this path (it is pure Python over librosa); the reference
+ * FFI a maintainer would add is the ctypes stub shown in INTEGRATION.md, binding exactly the
+ * symbols below.  Plain C symbols, plain pointers and sizes, no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative B2A_E* code on failure;
+ *     b2a_last_error() returns a thread-local, NUL-terminated description of the last failure.
+ *   - one handle = one (device, configuration); one host thread uses a handle at a time;
+ *     different handles / devices are independent.
+ *   - the caller owns all sample and feature buffers; the library owns its constant tables
+ *     (window, twiddles, banded mel weights, DCT matrix, CQT bases, decimator taps), all built on
+ *     the host in double precision inside b2a_create().
+ *   - clips are fixed length within a call: `n_samples` per clip, already padded/trimmed by the
+ *     caller exactly as deep.py:52-53,58-61 does (right zero-pad / truncate).
+ *   - input layout:  [n_clips][n_samples]  int16 PCM (value/32768 is applied on device,
+ *                    deep.py:44-50 via librosa.load; model_to_c.py:577) or float32.
+ *   - output layout: [n_clips][rows][frames] float32, C-contiguous — the `(N, rows, T)` layout
+ *                    FeaturePipeline.save writes to features.npy (pipeline.py:125-170).
+ */
+#ifndef B2A_H_
+#define B2A_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2A_ABI_VERSION 1
+
+/* error codes */
+#define B2A_OK            0
+#define B2A_EINVAL       -1   /* bad argument / unsupported configuration            */
+#define B2A_ECUDA        -2   /* CUDA runtime error (message in b2a_last_error)      */
+#define B2A_ENOMEM       -3   /* host or device allocation failed                    */
+#define B2A_ENODEVICE    -4   /* no usable CUDA device: there is NO CPU fallback     */
+
+/* b2a_config.kind — which extractor's arithmetic (deep.py class in parentheses) */
+#define B2A_KIND_MEL      0   /* AudioMelSpectrogram.extract  deep.py:112-134 */
+#define B2A_KIND_MFCC     1   /* AudioMFCCSequence.extract    deep.py:304-328 */
+#define B2A_KIND_CQT      2   /* AudioCQT.extract             deep.py:235-260 */
+
+/* b2a_config.input_dtype */
+#define B2A_IN_I16        0
+#define B2A_IN_F32        1
+
+/* b2a_config.pad_mode — librosa.stft(center=True, pad_mode=...) */
+#define B2A_PAD_CONSTANT  0   /* librosa >= 0.10 default: zeros (CLAUDE.md:90-91)   */
+#define B2A_PAD_REFLECT   1   /* selectable, never the default                      */
+
+typedef struct b2a_config {
+    int32_t kind;             /* B2A_KIND_*                                                   */
+    int32_t input_dtype;      /* B2A_IN_*                                                     */
+    int32_t sample_rate;      /* Hz                                   (all kinds)             */
+    int32_t n_samples;        /* samples per clip, = int(duration*sr) (all kinds)             */
+    int32_t n_fft;            /* 256|512|1024|2048                    (mel, mfcc)             */
+    int32_t hop_length;       /*                                      (all kinds)             */
+    int32_t n_mels;           /* mel bands (mfcc: librosa default 128)(mel, mfcc)             */
+    int32_t n_mfcc;           /* DCT rows kept                        (mfcc)                  */
+    int32_t n_bins;           /* CQT bins                             (cqt)                   */
+    int32_t bins_per_octave;  /*                                      (cqt)                   */
+    double  fmin;             /* CQT lowest frequency; <=0 -> C1 = 32.7032 Hz   (cqt)         */
+    int32_t pad_mode;         /* B2A_PAD_*                            (mel, mfcc)             */
+    float   top_db;           /* dB floor below the peak; reference uses librosa's 80.0       */
+    int32_t reserved[8];      /* must be zero                                                 */
+} b2a_config;
+
+typedef struct b2a_handle b2a_handle;
+
+/* Fills *cfg with the reference defaults of `kind` (deep.py:98-105, 219-227, 290-297 plus
+ * librosa's n_mels=128 for mfcc) and n_samples = 0; the caller then overrides fields. */
+int b2a_default_config(int32_t kind, b2a_config* cfg);
+
+/* Builds tables in double precision on the host, uploads them to `device`, allocates scratch.
+ * Fails with B2A_ENODEVICE when no CUDA device is present — there is no CPU path. */
+int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out);
+int b2a_destroy(b2a_handle* h);
+
+/* rows = n_mels | n_mfcc | n_bins; frames = 1 + n_samples / hop_length  (CLAUDE.md:90) */
+int b2a_out_shape(const b2a_handle* h, int32_t* rows, int32_t* frames);
+
+/* Device-resident path: d_clips and d_out are device pointers on the handle's device; the work
+ * is enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and the call returns
+ * without synchronising.  d_clips: [n_clips][n_samples] of input_dtype; d_out:
+ * [n_clips][rows][frames] float32. */
+int b2a_run_device(b2a_handle* h, const void* d_clips, int64_t n_clips, float* d_out,
+                   void* stream);
+
+/* Host path: clips/out are HOST pointers (pinned or pageable).  The library chunks the batch,
+ * overlaps H2D / kernels / D2H on its own streams and returns when `out` is complete. */
+int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out);
+
+/* Number of CUDA kernel launches the last b2a_run_* call on this handle enqueued. */
+int64_t b2a_last_launch_count(const b2a_handle* h);
+
+/* Pinned host memory for run_host callers (so H2D/D2H are true async DMA). */
+int b2a_alloc_pinned(size_t bytes, void** out);
+int b2a_free_pinned(void* p);
+
+/* Introspection of the constant tables, for tests and integrators (float32 copies).
+ *   which: B2A_TABLE_*; on entry *count = capacity of `dst` in floats (dst may be NULL to query),
+ *   on exit *count = number of floats the table holds. */
+#define B2A_TABLE_WINDOW      0   /* [n_fft]                     periodic Hann               */
+#define B2A_TABLE_MEL_DENSE   1   /* [n_mels][1+n_fft/2]         Slaney filterbank, dense    */
+#define B2A_TABLE_DCT         2   /* [n_mfcc][n_mels]            orthonormal DCT-II          */
+#define B2A_TABLE_DECIM_TAPS  3   /* [383]                       2:1 decimator (cqt)         */
+#define B2A_TABLE_CQT_LENGTHS 4   /* [n_bins]                    wavelet lengths (cqt)       */
+#define B2A_TABLE_CQT_BASIS   5   /* [n_octaves][n_filters][1+n_fft_o/2][2] re,im; dense     */
+int b2a_get_table(const b2a_handle* h, int32_t which, float* dst, int64_t* count);
+
+/* CQT geometry: per-octave FFT size / hop / signal length (cqt handles only). */
+int b2a_cqt_geometry(const b2a_handle* h, int32_t* n_octaves, int32_t* n_filters,
+                     int32_t* n_fft /*[n_octaves]*/, int32_t* hop /*[n_octaves]*/,
+                     int32_t* sig_len /*[n_octaves]*/);
+
+const char* b2a_last_error(void);
+int b2a_abi_version(void);
+int b2a_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2A_H_ */

@@ -1,0 +1,159 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Tolerances (BASELINE.json north_star):
+  audio_mel_spec  max-abs <= 1e-4 in [0,1] space
+  audio_mfcc_seq  max-abs <= 1e-3 in z-score units
+  audio_cqt       max-abs <= 1e-4 in [0,1] space (oracle and kernel share decimator taps)
+Shapes and frame counts bit-exact everywhere.
+"""
+import numpy as np
+import pytest
+
+from audio_edge_ml_pipeline_b200 import _lib as B
+from audio_edge_ml_pipeline_b200 import synth
+from oracle import librosa_restated as L
+
+pytestmark = pytest.mark.gpu
+
+MEL_TOL = 1e-4
+MFCC_TOL = 1e-3
+CQT_TOL = 1e-4
+
+
+def _engine(kind, n_samples, dtype=B.IN_I16, **kw):
+    cfg = B.default_config(kind)
+    cfg.n_samples = n_samples
+    cfg.input_dtype = dtype
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return B.Engine(cfg, 0)
+
+
+def _mel_oracle(pcm, **kw):
+    return np.stack([L.audio_mel_spec(L.pcm16_to_float(c), **kw) for c in pcm])
+
+
+@pytest.mark.parametrize("dtype", [B.IN_I16, B.IN_F32])
+def test_mel_fsc22_shape_suite(dtype):
+    """config 1 (subset): 5 s @ 16 kHz, n_fft 512, hop 160, 40 mels -> (40, 501)."""
+    pcm = synth.make_suite(70, 16000, 80000, seed=1234)
+    with _engine(B.KIND_MEL, 80000, dtype) as e:
+        assert (e.rows, e.frames) == (40, 501)
+        x = pcm if dtype == B.IN_I16 else L.pcm16_to_float(pcm)
+        got = e.run_host(x)
+        assert e.last_launch_count >= 1
+    ref = _mel_oracle(pcm, duration=5.0)
+    assert got.shape == ref.shape == (70, 40, 501) and got.dtype == np.float32
+    err = np.abs(got - ref).reshape(70, -1).max(axis=1)
+    assert err.max() <= MEL_TOL, f"per-clip max-abs: {err}"
+    assert got.min() >= 0.0 and got.max() <= 1.0
+
+
+@pytest.mark.parametrize("n_fft,hop,n_mels,sr,n", [
+    (256, 64, 20, 8000, 8000),
+    (512, 160, 40, 16000, 16000),
+    (1024, 512, 128, 22050, 110250),
+    (2048, 512, 128, 22050, 44100),
+    (512, 161, 40, 16000, 20011),       # odd hop, ragged length
+    (1024, 256, 64, 16000, 1024),       # shortest legal clip (== n_fft)
+])
+def test_mel_other_shapes(n_fft, hop, n_mels, sr, n):
+    pcm = synth.make_suite(14, sr, n, seed=7)
+    with _engine(B.KIND_MEL, n, n_fft=n_fft, hop_length=hop, n_mels=n_mels, sample_rate=sr) as e:
+        assert (e.rows, e.frames) == (n_mels, 1 + n // hop)
+        got = e.run_host(pcm)
+    ref = _mel_oracle(pcm, sample_rate=sr, n_fft=n_fft, hop_length=hop, n_mels=n_mels)
+    assert np.abs(got - ref).max() <= MEL_TOL
+
+
+def test_mel_reflect_padding_option():
+    pcm = synth.make_suite(7, 16000, 16000, seed=3)
+    with _engine(B.KIND_MEL, 16000, pad_mode=B.PAD_REFLECT) as e:
+        got = e.run_host(pcm)
+    ref = _mel_oracle(pcm, pad_mode="reflect")
+    assert np.abs(got - ref).max() <= MEL_TOL
+
+
+def test_mel_silence_is_all_zero_and_finite():
+    pcm = np.zeros((3, 80000), np.int16)
+    with _engine(B.KIND_MEL, 80000) as e:
+        got = e.run_host(pcm)
+    assert np.isfinite(got).all() and (got == 0).all()
+
+
+def test_mel_device_resident_matches_host_path():
+    import torch
+    pcm = synth.make_noise_batch(300, 80000, seed=5)
+    with _engine(B.KIND_MEL, 80000) as e:
+        host = e.run_host(pcm)
+        d_in = torch.from_numpy(pcm).cuda()
+        d_out = torch.empty((300, 40, 501), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        e.run_device(d_in.data_ptr(), 300, d_out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(d_out.cpu().numpy(), host)     # deterministic: bit-identical
+    ref = _mel_oracle(pcm[:8], duration=5.0)
+    assert np.abs(host[:8] - ref).max() <= MEL_TOL
+
+
+def test_mel_size_independent_properties_at_scale():
+    """Full-size batch (larger than one wave of CTAs): range, idempotence of re-runs, and
+    invariance of each clip's features to where it sits in the batch."""
+    pcm = synth.make_noise_batch(2025, 80000, seed=11)
+    with _engine(B.KIND_MEL, 80000) as e:
+        a = e.run_host(pcm)
+        b = e.run_host(pcm[::-1].copy())
+    assert a.min() >= 0 and a.max() <= 1 and np.isfinite(a).all()
+    assert np.array_equal(a, b[::-1])
+    assert np.all(a.reshape(2025, -1).max(axis=1) == 1.0)     # ref=np.max -> each clip peaks at 1
+
+
+@pytest.mark.parametrize("args", [
+    dict(sample_rate=16000, n_fft=512, hop_length=160, n_mels=40, n_mfcc=13, n=80000),   # config 2
+    dict(sample_rate=22050, n_fft=1024, hop_length=512, n_mels=128, n_mfcc=40, n=110250),  # defaults
+])
+def test_mfcc_seq(args):
+    n = args.pop("n")
+    pcm = synth.make_suite(21, args["sample_rate"], n, seed=99)
+    # an all-zero clip has zero variance: (0)/(0+1e-8) = 0 in both paths
+    with _engine(B.KIND_MFCC, n, **args) as e:
+        assert (e.rows, e.frames) == (args["n_mfcc"], 1 + n // args["hop_length"])
+        got = e.run_host(pcm)
+    ref = np.stack([L.audio_mfcc_seq(L.pcm16_to_float(c), args["sample_rate"], args["n_mfcc"], args["n_fft"],
+                                     args["hop_length"], None, n_mels=args["n_mels"]) for c in pcm])
+    err = np.abs(got - ref).reshape(len(pcm), -1).max(axis=1)
+    assert err.max() <= MFCC_TOL, f"per-clip max-abs: {err}"
+
+
+@pytest.mark.parametrize("dtype", [B.IN_F32, B.IN_I16])
+def test_cqt_config3(dtype):
+    """config 3: 5 s @ 22.05 kHz, hop 512, 84 bins, 12/octave -> (84, 216)."""
+    pcm = synth.make_suite(14, 22050, 110250, seed=21)
+    with _engine(B.KIND_CQT, 110250, dtype) as e:
+        assert (e.rows, e.frames) == (84, 216)
+        x = pcm if dtype == B.IN_I16 else L.pcm16_to_float(pcm)
+        got = e.run_host(x)
+    ref = np.stack([L.audio_cqt(L.pcm16_to_float(c), duration=5.0) for c in pcm])
+    err = np.abs(got - ref).reshape(len(pcm), -1).max(axis=1)
+    assert err.max() <= CQT_TOL, f"per-clip max-abs: {err}"
+
+
+def test_tables_match_oracle():
+    with _engine(B.KIND_MEL, 80000) as e:
+        w = e.table(B.TABLE_MEL_DENSE).reshape(40, 257)
+        assert np.array_equal(w, L.mel_filterbank(16000, 512, 40))
+        import scipy.signal
+        assert np.array_equal(e.table(B.TABLE_WINDOW),
+                              scipy.signal.get_window("hann", 512, fftbins=True).astype(np.float32))
+    with _engine(B.KIND_CQT, 110250) as e:
+        taps = e.table(B.TABLE_DECIM_TAPS)
+        assert np.abs(taps - L.halfband_taps().astype(np.float32)).max() <= 1e-9
+        plan = L.cqt_plan(22050.0, 512, 84, 12, None)
+        geo = e.cqt_geometry()
+        assert list(geo["n_fft"]) == [o["n_fft"] for o in plan["octaves"]]
+        assert list(geo["hop"]) == [o["hop"] for o in plan["octaves"]]
+        basis = e.table(B.TABLE_CQT_BASIS).reshape(7, 12, 129, 2)
+        ob = np.stack([o["basis"] for o in plan["octaves"]])
+        gb = basis[..., 0] + 1j * basis[..., 1]
+        assert np.array_equal(gb != 0, ob != 0), "sparsified support differs"
+        assert np.abs(gb - ob).max() <= 2e-6 * np.abs(ob).max()
