@@ -300,15 +300,18 @@ __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel
                 }
             }
             __syncthreads();
-            const float inv_n = 1.0f / (float)nfr;
+            const float fn = (float)nfr;
             for (int k = warp; k < p.n_mfcc; k += kThreads / 32) {
                 float* row = outc + (size_t)k * nfr;
+                // mean about the first sample: exact for a constant row (silence -> z == 0, as the
+                // reference gives) and better conditioned otherwise
+                const float x0 = row[0];
                 float s = 0.f;
-                for (int t = lane; t < nfr; t += 32) s += row[t];
-                const float mean = warp_sum(s) * inv_n;
+                for (int t = lane; t < nfr; t += 32) s += row[t] - x0;
+                const float mean = x0 + __fdiv_rn(warp_sum(s), fn);
                 float ss = 0.f;
                 for (int t = lane; t < nfr; t += 32) { const float d = row[t] - mean; ss = fmaf(d, d, ss); }
-                const float sd = sqrtf(warp_sum(ss) * inv_n) + 1e-8f;
+                const float sd = sqrtf(__fdiv_rn(warp_sum(ss), fn)) + 1e-8f;
                 for (int t = lane; t < nfr; t += 32) row[t] = __fdiv_rn(row[t] - mean, sd);
             }
         }

@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the Stage-2 audio hot path on B200.
+
+Metric (BASELINE.json): log-mel clips/sec, 5 s @ 16 kHz clips, n_fft 512 / hop 160 / 40 mels,
+device-resident int16 batches (BASELINE config 4: "100k synthetic 5 s clips"), plus
+audio-seconds/sec, achieved HBM GB/s against the measured roofline, and the CPU path beside it.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (one rank per GPU; torchrun for N>1)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm on host cores
+
+A "step" is one pass of the hot path over one resident batch (`--clips` per GPU, default
+100 000 = BASELINE config 4).  Clips are independent, so ranks shard them with no collective:
+weak scaling (per-GPU batch fixed).  `value` is timed with CUDA events on the launching stream,
+max over ranks; `e2e` is the same metric through the public host API (`Engine.run_host`, i.e.
+`b2a_run_host`) with pinned HOST buffers, H2D and D2H inside the timed region.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+SR, N_SAMPLES, N_FFT, HOP, N_MELS = 16000, 80000, 512, 160, 40
+N_FRAMES = 1 + N_SAMPLES // HOP
+BYTES_PER_CLIP = N_SAMPLES * 2 + N_MELS * N_FRAMES * 4        # 240 160 B
+CLIP_SECONDS = N_SAMPLES / SR
+METRIC = "log-mel clips/sec (5 s @16 kHz, n_fft 512, hop 160, 40 mels)"
+WORKLOAD = "BASELINE config 4: synthetic 5 s 16 kHz int16 clips, device-resident, audio_mel_spec (40,501)"
+
+
+def _peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def _ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:
+        return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu: int):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0: float, t1: float):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons, power = [], None, set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                clk, mx = float(parts[1]), float(parts[2])
+            except ValueError:
+                continue
+            smax = mx
+            if t0 - 0.05 <= ts <= t1 + 0.15:
+                sm.append(clk)
+                try:
+                    power.append(float(parts[3]))
+                except ValueError:
+                    pass
+                for nm, val in zip(names, parts[4:8]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+        if not sm:      # region shorter than the sampling period: take the nearest samples
+            sm = [float(r[1].split(",")[1]) for r in self.rows[-3:]] if self.rows else []
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(power) if power else None}
+
+
+def _oracle_worker(args):
+    """CPU leg: restated librosa path over a slice of clips (numpy/scipy, one process)."""
+    seed, n = args
+    from threadpoolctl import threadpool_limits
+    from oracle import librosa_restated as L
+    from audio_edge_ml_pipeline_b200 import synth
+    pcm = synth.make_noise_batch(n, N_SAMPLES, seed=seed)
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        for c in pcm:
+            L.audio_mel_spec(L.pcm16_to_float(c), sample_rate=SR, n_mels=N_MELS, n_fft=N_FFT,
+                             hop_length=HOP, duration=CLIP_SECONDS)
+        return time.perf_counter() - t0
+
+
+def cpu_baseline_serial(n_clips: int = 384):
+    """The reference's behaviour: one process, serial per-clip loop (base.py:199-214)."""
+    dt = _oracle_worker((1234, n_clips))
+    return {"value": n_clips / dt, "unit": "clips/s", "cores": 1, "kind": "port",
+            "sample": f"{n_clips} clips of the bench workload through oracle/librosa_restated.py "
+                      f"(numpy/scipy restatement of librosa 0.11.0; librosa itself is not installable here), "
+                      f"serial loop as base.py:199-214, {dt:.1f} s",
+            "audio_seconds_per_s": n_clips * CLIP_SECONDS / dt}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm on all host cores (oracle port)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    per_worker = 32
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        def step(seed):
+            t0 = time.perf_counter()
+            pool.map(_oracle_worker, [(seed * 1000 + w, per_worker) for w in range(cores)])
+            return time.perf_counter() - t0
+        for w in range(args.warmup):
+            step(w)
+        times = [step(100 + k) for k in range(args.steps)]
+    total = sum(times)
+    clips = per_worker * cores * args.steps
+    val = clips / total
+    line = {
+        "metric": METRIC, "value": val, "unit": "clips/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 FFT / f32 elsewhere (librosa semantics)",
+        "data": "synthetic", "impl": "reference",
+        "config": {"workload": WORKLOAD, "sample_per_step": f"{per_worker * cores} clips ({per_worker} per worker)",
+                   "n_fft": N_FFT, "hop_length": HOP, "n_mels": N_MELS, "sample_rate": SR},
+        "audio_seconds_per_s": val * CLIP_SECONDS,
+        "cpu_baseline": {"value": val, "unit": "clips/s", "cores": cores, "kind": "port",
+                         "sample": f"{per_worker * cores} clips/step x {args.steps} steps through "
+                                   "oracle/librosa_restated.py in a multiprocessing pool (librosa not installable)"},
+        "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from audio_edge_ml_pipeline_b200 import _lib as B
+    from audio_edge_ml_pipeline_b200.build import build_lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this package has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    if rank == 0:
+        build_lib()
+    if world > 1:
+        dist.barrier()
+
+    cfg = B.default_config(B.KIND_MEL)
+    cfg.n_samples = N_SAMPLES
+    eng = B.Engine(cfg, local)
+    assert (eng.rows, eng.frames) == (N_MELS, N_FRAMES)
+
+    # ---- resident synthetic batch (white noise sigma 0.1 -> int16), generated on device ------
+    n = args.clips
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    d_in = torch.empty((n, N_SAMPLES), dtype=torch.int16, device=dev)
+    for a in range(0, n, 4096):
+        b = min(n, a + 4096)
+        x = torch.randn((b - a, N_SAMPLES), generator=g, device=dev, dtype=torch.float32)
+        d_in[a:b] = (x * (0.1 * 32768.0)).round_().clamp_(-32768, 32767).to(torch.int16)
+        del x
+    d_out = torch.empty((n, N_MELS, N_FRAMES), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        eng.run_device(d_in.data_ptr(), n, d_out.data_ptr(), stream)
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    fence()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.25)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fence()
+    t_wall0 = time.time()
+    ev0.record()
+    launches = 0
+    for _ in range(args.steps):
+        step()
+        launches += eng.last_launch_count
+    ev1.record()
+    fence()
+    t_wall1 = time.time()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+
+    # ---- end to end through the host API: pinned host buffers, H2D + kernel + D2H timed --------
+    ne = args.e2e_clips
+    pin_in = B.PinnedArray((ne, N_SAMPLES), np.int16)
+    pin_out = B.PinnedArray((ne, N_MELS, N_FRAMES), np.float32)
+    torch.from_numpy(pin_in.array).copy_(d_in[:ne] if ne <= n else d_in[:1].expand(ne, -1))
+    torch.cuda.synchronize()
+    for _ in range(2):
+        eng.run_host(pin_in.array, pin_out.array)
+    fence()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        eng.run_host(pin_in.array, pin_out.array)      # returns when the features are on the host
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = world * ne * e2e_steps / float(e2e_s.item())
+    checksum = float(pin_out.array[0].sum())
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        total_clips = world * n * args.steps
+        value = total_clips / (ms * 1e-3)
+        launch_s = ms * 1e-3 / args.steps                       # one launch per step per GPU
+        achieved = n * BYTES_PER_CLIP / launch_s / 1e9           # per GPU
+        traffic = _ncu_traffic()
+        line = {
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "clips_per_gpu": n, "global_clips": world * n,
+                       "n_fft": N_FFT, "hop_length": HOP, "n_mels": N_MELS, "sample_rate": SR,
+                       "input": "int16", "parallelism": f"clip-sharded x{world}, no collective",
+                       "l2": f"inputs {n * N_SAMPLES * 2 / 1e9:.1f} GB + outputs {n * N_MELS * N_FRAMES * 4 / 1e9:.1f} GB per GPU per step, >> 126 MB L2 (no flush needed)"},
+            "audio_seconds_per_s": value * CLIP_SECONDS,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "peak_source": peak_src,
+                         "bytes_per_clip": BYTES_PER_CLIP, "kernel": "front_kernel<8,true,0>",
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None,
+                         "traffic_note": (traffic or {}).get("note") if traffic else "no ncu capture committed yet",
+                         "frac_of_nominal_8TBs": achieved / 8000.0},
+            "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": ne * N_SAMPLES * 2,
+                    "d2h_bytes_per_step": ne * N_MELS * N_FRAMES * 4, "clips_per_step": ne,
+                    "steps": e2e_steps, "api": "Engine.run_host -> b2a_run_host (pinned host buffers)",
+                    "checksum": checksum},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_serial(args.cpu_clips)
+        print(json.dumps(line), flush=True)
+    pin_in.close()
+    pin_out.close()
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clips", type=int, default=100000, help="resident clips per GPU per step")
+    ap.add_argument("--e2e-clips", type=int, default=16384, help="clips per end-to-end step (host buffers)")
+    ap.add_argument("--cpu-clips", type=int, default=384, help="clips in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
