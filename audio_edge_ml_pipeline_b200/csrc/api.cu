@@ -73,6 +73,12 @@ struct b2a_handle {
     int* d_cnt = nullptr;
     int* d_off = nullptr;
     float* d_w = nullptr;
+    float* d_wq = nullptr;      // 4-padded, 0.25-prescaled weights (logmel512)
+    int* d_cnt4 = nullptr;
+    int* d_off4 = nullptr;
+    int* d_order = nullptr;
+    int mel_wpad = 0;
+    bool use512 = false;
     float* d_dct = nullptr;
     float* d_inter = nullptr;
     int grid_cap = 0;
@@ -125,6 +131,7 @@ int b2a_destroy(b2a_handle* h) {
     }
     cudaFree(h->d_window); cudaFree(h->d_tw); cudaFree(h->d_tw2);
     cudaFree(h->d_k0); cudaFree(h->d_cnt); cudaFree(h->d_off); cudaFree(h->d_w);
+    cudaFree(h->d_wq); cudaFree(h->d_cnt4); cudaFree(h->d_off4); cudaFree(h->d_order);
     cudaFree(h->d_dct); cudaFree(h->d_inter);
     b2a::cqt_device_free(&h->cqtdev);
     delete h;
@@ -203,6 +210,47 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
         if (h->mel.w.empty()) h->mel.w.push_back(0.f);
         CU_TRY_H(upload(h->mel.w, &h->d_w));
         h->grid_cap = h->sm_count * b2a::front_ctas_per_sm(h->log2nc);
+        if (n_fft == 512 && (cfg->hop_length % 2) == 0) {
+            // tables of the specialised kernel: bands padded to float4 groups, |X|^2 -> 4|X|^2 folded
+            // into the weights (x0.25 is exact), bands dealt to the 8 warps in snake order by size
+            std::vector<float> wq;
+            std::vector<int> cnt4(cfg->n_mels), off4(cfg->n_mels), order;
+            for (int m = 0; m < cfg->n_mels; ++m) {
+                off4[m] = (int)wq.size();
+                cnt4[m] = (h->mel.cnt[m] + 3) / 4;
+                for (int q = 0; q < cnt4[m] * 4; ++q)
+                    wq.push_back(q < h->mel.cnt[m] ? 0.25f * h->mel.w[h->mel.off[m] + q] : 0.f);
+            }
+            if (wq.empty()) wq.assign(4, 0.f);
+            std::vector<int> idx(cfg->n_mels);
+            for (int m = 0; m < cfg->n_mels; ++m) idx[m] = m;
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cnt4[a] > cnt4[b]; });
+            order.assign(cfg->n_mels, 0);
+            for (int i = 0; i < cfg->n_mels; ++i) {           // position i is served by warp i % 8
+                const int rnd = i / 8, w = i % 8;
+                const int src = rnd * 8 + ((rnd & 1) ? 7 - w : w);
+                order[i] = idx[std::min(src, cfg->n_mels - 1)];
+            }
+            {   // the snake can alias at the ragged end; fall back to identity if not a permutation
+                std::vector<int> seen(cfg->n_mels, 0);
+                bool perm = true;
+                for (int v : order) { if (seen[v]++) perm = false; }
+                if (!perm) order = idx;
+            }
+            h->mel_wpad = (int)wq.size();
+            const size_t smem512 = b2a::logmel512_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad,
+                                                             cfg->input_dtype == B2A_IN_I16);
+            const bool fits = smem512 <= (size_t)prop.sharedMemPerBlockOptin &&
+                              (!mfcc || (size_t)cfg->n_mels * 32 <= 260u * 34u);
+            if (fits) {
+                CU_TRY_H(upload(wq, &h->d_wq));
+                CU_TRY_H(upload(cnt4, &h->d_cnt4));
+                CU_TRY_H(upload(off4, &h->d_off4));
+                CU_TRY_H(upload(order, &h->d_order));
+                h->use512 = true;
+                h->grid_cap = h->sm_count * (smem512 * 2 <= (size_t)prop.sharedMemPerMultiprocessor - 2048 ? 2 : 1);
+            }
+        }
         if (mfcc) {
             CU_TRY_H(upload(h->dct, &h->d_dct));
             CU_TRY_H(cudaMalloc((void**)&h->d_inter, (size_t)h->grid_cap * cfg->n_mels * h->frames * sizeof(float)));
@@ -254,9 +302,13 @@ static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, 
     p.n_clips = n_clips; p.n_samples = h->cfg.n_samples; p.hop = h->cfg.hop_length;
     p.n_frames = h->frames; p.n_mels = h->cfg.n_mels; p.mel_nnz = (int)h->mel.w.size();
     p.n_mfcc = h->cfg.n_mfcc; p.pad_mode = h->cfg.pad_mode; p.top_db = h->cfg.top_db;
+    p.mel_wq = h->d_wq; p.mel_cnt4 = h->d_cnt4; p.mel_off4 = h->d_off4; p.mel_order = h->d_order;
+    p.mel_wpad = h->mel_wpad;
     const int grid = (int)std::min<int64_t>(n_clips, h->grid_cap);
-    CU_TRY(b2a::launch_front(p, h->log2nc, h->cfg.input_dtype == B2A_IN_I16,
-                             h->cfg.kind == B2A_KIND_MFCC ? 1 : 0, grid, st));
+    const bool i16 = h->cfg.input_dtype == B2A_IN_I16;
+    const int kind = h->cfg.kind == B2A_KIND_MFCC ? 1 : 0;
+    if (h->use512) CU_TRY(b2a::launch_logmel512(p, i16, kind, grid, st));
+    else CU_TRY(b2a::launch_front(p, h->log2nc, i16, kind, grid, st));
     *launches += 1;
     return B2A_OK;
 }

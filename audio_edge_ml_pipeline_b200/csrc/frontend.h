@@ -16,6 +16,12 @@ struct FrontParams {
     const int* mel_cnt;
     const int* mel_off;
     const float* mel_w;
+    // 4-padded, 0.25-prescaled banded weights + balanced band order (logmel512 kernel)
+    const float* mel_wq;
+    const int* mel_cnt4;     // per band: number of float4 groups
+    const int* mel_off4;     // per band: float offset into mel_wq (multiple of 4)
+    const int* mel_order;    // band processed at position i (position i belongs to warp i % 8)
+    int mel_wpad;            // floats in mel_wq
     const float* dct;        // mfcc only: [n_mfcc][n_mels]
     long long n_clips;
     int n_samples, hop, n_frames, n_mels, mel_nnz, n_mfcc, pad_mode;
@@ -26,5 +32,9 @@ size_t front_smem_bytes(int log2nc, int hop, int n_mels, int mel_nnz);
 int front_ctas_per_sm(int log2nc);
 // kind: 0 = mel, 1 = mfcc
 cudaError_t launch_front(const FrontParams& p, int log2nc, bool i16, int kind, int grid, cudaStream_t st);
+
+// specialised n_fft = 512 kernel (logmel512.cu); requires an even hop
+size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16);
+cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st);
 
 }  // namespace b2a

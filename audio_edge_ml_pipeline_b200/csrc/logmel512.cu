@@ -1,0 +1,435 @@
+// logmel512.cu — the headline kernel: n_fft = 512 fused log-mel / MFCC front end, sm_100a only.
+//
+// Same arithmetic as frontend.cu (the generic n_fft kernel) but laid out for the 16 x 16
+// decomposition of the 256-point packed FFT:
+//   * one half-warp per frame, 16 complex points per lane in registers for both radix-16 passes;
+//     pass-2 results never leave registers — only the 8 rows the mirror lane needs go through
+//     shared memory (X[k] needs Z[k] and Z[256-k], which lives in lane 16-j);
+//   * the next tile's raw PCM is fetched by one cp.async.bulk (TMA bulk copy, mbarrier
+//     completion) while the current tile is being transformed, then widened int16 -> fp32 once
+//     per sample in shared memory (frames overlap 3.2x, so per-frame conversion would cost 3.2x);
+//   * power tile is [bin][frame] with a 34-word row so the two frames of a warp write disjoint
+//     banks and the mel phase (lane = frame, weights warp-uniform, 128-bit broadcast loads)
+//     reads conflict-free;
+//   * raw dB goes to the output buffer (L2-resident), per-clip max/min stay in registers, and
+//     the same CTA normalises the clip in place a few microseconds later.
+//
+// Reference arithmetic: deep.py:126-134 (mel), :318-328 (mfcc) via librosa 0.11.0.
+#include "frontend.h"
+#include "fft_core.cuh"
+
+#include <cstdint>
+
+namespace b2a {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int NC = 256, NFFT = 512, F = 32;     // complex points, frame length, frames per tile
+constexpr int XSLOT = 16 * 17 + 2;              // float2 per frame slot (pad 1 per 16, +2 slack)
+constexpr int PROW = 34;                        // power-tile row stride in words (32 frames + 2)
+constexpr int PROWS = 260;                      // bins 0..256 plus 3 zero rows for padded bands
+
+__device__ __forceinline__ float db10(float s) {
+    return 3.01029995663981195f * __log2f(fmaxf(s, 1e-10f));
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <bool I16>
+__device__ __forceinline__ float load_sample(const void* clip, int s, int n, int pad_mode) {
+    if (s < 0 || s >= n) {
+        if (pad_mode == 0) return 0.f;
+        s = (s < 0) ? -s : 2 * (n - 1) - s;
+        if (s < 0 || s >= n) return 0.f;
+    }
+    if (I16) return (float)((const int16_t*)clip)[s] * (1.0f / 32768.0f);
+    return ((const float*)clip)[s];
+}
+
+struct Layout {
+    int chunk;          // samples staged per tile, multiple of 8
+    int off_raw, off_raw2, off_audio, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, total;
+};
+
+__host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16) {
+    Layout L;
+    L.chunk = (hop * (F - 1) + NFFT + 7) & ~7;
+    int o = 0;
+    auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
+    if (i16) {
+        L.off_raw = take(L.chunk * 2);
+        L.off_raw2 = L.off_raw;
+        L.off_audio = take(L.chunk * 4);
+    } else {
+        L.off_raw = take(L.chunk * 4);          // two fp32 buffers, transformed in place
+        L.off_raw2 = take(L.chunk * 4);
+        L.off_audio = L.off_raw;
+    }
+    L.off_xch = take(16 * XSLOT * 8);
+    L.off_pow = take(PROWS * PROW * 4);
+    L.off_tw2 = take(8 * 16 * 8);
+    L.off_melw = take(mel_wpad * 4);
+    L.off_melk = take(n_mels * 3 * 4);
+    L.off_red = take(64 * 4);
+    L.off_bar = take(16);
+    L.total = o;
+    return L;
+}
+
+template <bool I16, int KIND>
+__global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16);
+    float2* const s_xch = reinterpret_cast<float2*>(smem + L.off_xch);
+    float* const s_pow = reinterpret_cast<float*>(smem + L.off_pow);
+    float2* const s_tw2 = reinterpret_cast<float2*>(smem + L.off_tw2);
+    float* const s_melw = reinterpret_cast<float*>(smem + L.off_melw);
+    int* const s_k0 = reinterpret_cast<int*>(smem + L.off_melk);
+    int* const s_cnt = s_k0 + p.n_mels;
+    int* const s_off = s_cnt + p.n_mels;
+    float* const s_red = reinterpret_cast<float*>(smem + L.off_red);
+    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int j = lane & 15, h = lane >> 4;
+    const int hop = p.hop, n = p.n_samples, nfr = p.n_frames, n_mels = p.n_mels, chunk = L.chunk;
+
+    // ---- per-CTA tables --------------------------------------------------------------------
+    for (int i = tid; i < 128; i += kThreads) {          // s_tw2[r][j] = exp(-i pi (j+16r)/256)
+        const int r = i >> 4, jj = i & 15;
+        s_tw2[i] = p.tw2[jj + 16 * r];
+    }
+    for (int i = tid; i < p.mel_wpad; i += kThreads) s_melw[i] = p.mel_wq[i];
+    for (int i = tid; i < n_mels; i += kThreads) { s_k0[i] = p.mel_k0[i]; s_cnt[i] = p.mel_cnt4[i]; s_off[i] = p.mel_off4[i]; }
+    for (int i = tid; i < (PROWS - 257) * PROW; i += kThreads) s_pow[257 * PROW + i] = 0.f;
+    if (tid == 0) {
+        mbar_init(s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+
+    // ---- per-thread constants ----------------------------------------------------------------
+    float2 win[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const int q = j + 16 * t;
+        win[t] = make_float2(__ldg(p.window + 2 * q), __ldg(p.window + 2 * q + 1));
+    }
+    float2 tw1[15];
+#pragma unroll
+    for (int t = 1; t < 16; ++t) tw1[t - 1] = p.tw[t * j];
+    float2* const xs = s_xch + (2 * warp + h) * XSLOT;       // this frame's exchange slot
+    float2* const x1 = xs + 17 * j;                          // pass-1 store base
+    float2* const x2 = xs + j;                               // pass-2 load base (stride 17)
+    float2* const mst = xs + j;                              // mirror store base: M[(row-8)*16 + j]
+    const float2* const mld = xs + (j ? 16 - j : 16);        // mirror load base:  M[(7-r)*16 + ...]
+    const float2* const t2 = s_tw2 + j;
+    __syncthreads();
+
+    const size_t esz = I16 ? 2 : 4;
+    constexpr int V = I16 ? 8 : 4;                           // samples per 16 bytes
+    const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
+    uint32_t bar_parity = 0;
+    int buf = 0;                                             // fp32 input: which raw buffer holds this tile
+
+    // Issue (or perform) the staging of one tile into `dst_raw`.  Returns true when a bulk copy is
+    // in flight on s_bar (every thread computes the same answer).
+    // true when tile (clip, t0) can be staged by a bulk copy (uniform over the CTA)
+    auto can_bulk = [&](long long clip, int t0) -> bool {
+        const long long e0 = clip * (long long)n;
+        const int c0 = t0 * hop - NFFT / 2;
+        const int lo = c0 < 0 ? 0 : c0;
+        const int hi = (c0 + chunk < n) ? c0 + chunk : n;
+        return p.pad_mode == 0 && base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
+               (((lo - c0) & (V - 1)) == 0);
+    };
+    auto stage_issue = [&](long long clip, int t0, unsigned char* dst_raw, bool ok) -> bool {
+        const long long e0 = clip * (long long)n;
+        const unsigned char* cptr = (const unsigned char*)p.clips + (size_t)e0 * esz;
+        const int c0 = t0 * hop - NFFT / 2;
+        const int lo = c0 < 0 ? 0 : c0;
+        const int hi = (c0 + chunk < n) ? c0 + chunk : n;
+        if (ok) {
+            const int nb = ((hi - lo) / V) * V;             // bulk part, whole 16-byte units
+            for (int i = tid; i < chunk; i += kThreads) {   // zero what the bulk copy will not write
+                const int s = c0 + i;
+                if (s < lo || s >= lo + nb) {
+                    float v = 0.f;
+                    if (s >= lo + nb && s < hi) v = load_sample<I16>(cptr, s, n, 0);   // < V tail samples
+                    if (I16) reinterpret_cast<int16_t*>(dst_raw)[i] = (int16_t)__float2int_rn(v * 32768.0f);
+                    else reinterpret_cast<float*>(dst_raw)[i] = v;
+                }
+            }
+            if (tid == 0 && nb > 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads -> async write
+                mbar_expect_tx(s_bar, (uint32_t)(nb * esz));
+                bulk_g2s(dst_raw + (size_t)(lo - c0) * esz, cptr + (size_t)lo * esz, (uint32_t)(nb * esz), s_bar);
+            }
+            return nb > 0;
+        }
+        // generic path (reflect padding, unaligned clips): plain loads, already widened
+        for (int i = tid; i < chunk; i += kThreads) {
+            const float v = load_sample<I16>(cptr, c0 + i, n, p.pad_mode);
+            if (I16) reinterpret_cast<float*>(smem + L.off_audio)[i] = v;   // written after the tile's FFT
+            else reinterpret_cast<float*>(dst_raw)[i] = v;
+        }
+        return false;
+    };
+    // The generic path writes the fp32 samples directly, so it runs at the start of its own tile
+    // (where the bulk path's conversion runs), never as a prefetch: `deferred` carries that.
+
+    const int tiles = (nfr + F - 1) / F;
+    long long clip = blockIdx.x;
+    if (clip >= p.n_clips) return;
+    // prologue: stage the first tile of the first clip
+    unsigned char* raw0 = smem + L.off_raw;
+    unsigned char* raw1 = smem + L.off_raw2;
+    bool inflight = false, deferred = false;
+    if (can_bulk(clip, 0)) inflight = stage_issue(clip, 0, raw0, true);
+    else deferred = true;
+
+    for (; clip < p.n_clips; clip += gridDim.x) {
+        float* inter = (KIND == 0) ? p.out + (size_t)clip * n_mels * nfr
+                                   : p.inter + (size_t)blockIdx.x * n_mels * nfr;
+        float vmax = -3.0e38f, vmin = 3.0e38f;
+
+        for (int tile = 0; tile < tiles; ++tile) {
+            const int t0 = tile * F;
+            unsigned char* cur_raw = (I16 || buf == 0) ? raw0 : raw1;
+            // (A) this tile's samples have landed
+            if (inflight) { mbar_wait(s_bar, bar_parity); bar_parity ^= 1; }
+            float* audio;
+            if (I16) {
+                audio = reinterpret_cast<float*>(smem + L.off_audio);
+                if (deferred) {
+                    stage_issue(clip, t0, cur_raw, false);         // generic path: writes s_audio itself
+                } else {
+                    __syncthreads();                               // zero-fill / tail stores visible
+                    // (B) widen int16 -> fp32 once per sample: 4 samples per thread per step
+                    const uint2* r2 = reinterpret_cast<const uint2*>(cur_raw);
+                    float4* a4 = reinterpret_cast<float4*>(audio);
+                    for (int g = tid; g < chunk / 4; g += kThreads) {
+                        const uint2 u = r2[g];
+                        float4 f;
+                        f.x = (float)(int)(short)(u.x & 0xffffu) * (1.0f / 32768.0f);
+                        f.y = (float)((int)u.x >> 16) * (1.0f / 32768.0f);
+                        f.z = (float)(int)(short)(u.y & 0xffffu) * (1.0f / 32768.0f);
+                        f.w = (float)((int)u.y >> 16) * (1.0f / 32768.0f);
+                        a4[g] = f;
+                    }
+                }
+            } else {
+                audio = reinterpret_cast<float*>(cur_raw);
+                if (deferred) stage_issue(clip, t0, cur_raw, false);
+            }
+            __syncthreads();                                       // (C) audio ready, raw buffer free
+
+            // (D) prefetch the next tile (possibly the next clip's first tile)
+            {
+                long long nclip = clip;
+                int nt0 = t0 + F;
+                if (tile + 1 == tiles) { nclip = clip + gridDim.x; nt0 = 0; }
+                inflight = false; deferred = false;
+                if (nclip < p.n_clips) {
+                    unsigned char* nxt = (I16 || buf == 1) ? raw0 : raw1;
+                    if (can_bulk(nclip, nt0)) inflight = stage_issue(nclip, nt0, nxt, true);
+                    else deferred = true;
+                }
+                buf ^= 1;
+            }
+
+            // (E) two rounds of 16 frames: window, radix-16, exchange, radix-16, mirror, |X|^2
+#pragma unroll 1
+            for (int r = 0; r < 2; ++r) {
+                const int f = 16 * r + 2 * warp + h;
+                float2 v[16];
+                {
+                    const float* a = audio + f * hop + 2 * j;
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const float2 x = *reinterpret_cast<const float2*>(a + 32 * t);
+                        v[t] = make_float2(x.x * win[t].x, x.y * win[t].y);
+                    }
+                }
+                Dft<16>::run(v);
+#pragma unroll
+                for (int t = 0; t < 16; ++t) x1[t] = v[t];
+                __syncwarp();
+                v[0] = x2[0];
+#pragma unroll
+                for (int t = 1; t < 16; ++t) v[t] = cmul(x2[17 * t], tw1[t - 1]);
+                Dft<16>::run(v);                                   // v[t] = Z[j + 16 t]
+                __syncwarp();
+#pragma unroll
+                for (int t = 8; t < 16; ++t) mst[(t - 8) * 16] = v[t];
+                mst[8 * 16] = v[0];                                // "row 16": Z[256] == Z[0] for lane 0
+                __syncwarp();
+                float* pk = s_pow + j * PROW + f;                  // bin j + 16 r2
+                float* pn = s_pow + (NC - j) * PROW + f;           // bin 256 - j - 16 r2
+#pragma unroll
+                for (int r2 = 0; r2 < 8; ++r2) {
+                    const float2 B = mld[(7 - r2) * 16];
+                    float2 xk, xnk;
+                    rfft_split(v[r2], B, t2[16 * r2], xk, xnk);    // 2 X[k], 2 X[256-k]
+                    pk[16 * r2 * PROW] = xk.x * xk.x + xk.y * xk.y;        // 4|X|^2: the 1/4 lives
+                    pn[-16 * r2 * PROW] = xnk.x * xnk.x + xnk.y * xnk.y;   // in the mel weights
+                }
+                if (j == 0) s_pow[(NC / 2) * PROW + f] = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
+                __syncwarp();
+            }
+            __syncthreads();                                       // (F) power tile complete
+
+            // (G) mel bands: lane = frame, warp-uniform band, 128-bit broadcast weight loads
+            {
+                const int t = t0 + lane;
+                const float* pl = s_pow + lane;
+                for (int i = warp; i < n_mels; i += kWarps) {
+                    const int m = p.mel_order ? __ldg(p.mel_order + i) : i;
+                    const float* pr = pl + s_k0[m] * PROW;
+                    const float4* wq = reinterpret_cast<const float4*>(s_melw + s_off[m]);
+                    const int c4 = s_cnt[m];
+                    float a0 = 0.f, a1 = 0.f;
+                    for (int q4 = 0; q4 < c4; ++q4) {
+                        const float4 w = wq[q4];
+                        a0 = fmaf(w.x, pr[0], a0);
+                        a1 = fmaf(w.y, pr[PROW], a1);
+                        a0 = fmaf(w.z, pr[2 * PROW], a0);
+                        a1 = fmaf(w.w, pr[3 * PROW], a1);
+                        pr += 4 * PROW;
+                    }
+                    if (t < nfr) {
+                        const float vv = db10(a0 + a1);
+                        inter[(size_t)m * nfr + t] = vv;
+                        vmax = fmaxf(vmax, vv);
+                        vmin = fminf(vmin, vv);
+                    }
+                }
+            }
+        }
+
+        // ---- per-clip reductions ---------------------------------------------------------------
+        vmax = warp_max(vmax); vmin = warp_min(vmin);
+        if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
+        __syncthreads();
+        {
+            const float a = (lane < kWarps) ? s_red[lane] : -3.0e38f;
+            const float b = (lane < kWarps) ? s_red[32 + lane] : 3.0e38f;
+            vmax = warp_max(a); vmin = warp_min(b);
+        }
+        if constexpr (KIND == 0) {
+            const float lo = fmaxf(vmin - vmax, -p.top_db);
+            const float range = (0.0f - lo) + 1e-8f;
+            const int total = n_mels * nfr;
+            if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(inter) & 15) == 0)) {
+                float4* o4 = reinterpret_cast<float4*>(inter);
+                for (int i = tid; i < total / 4; i += kThreads) {
+                    float4 x = o4[i];
+                    x.x = __fdiv_rn(fmaxf(x.x - vmax, -p.top_db) - lo, range);
+                    x.y = __fdiv_rn(fmaxf(x.y - vmax, -p.top_db) - lo, range);
+                    x.z = __fdiv_rn(fmaxf(x.z - vmax, -p.top_db) - lo, range);
+                    x.w = __fdiv_rn(fmaxf(x.w - vmax, -p.top_db) - lo, range);
+                    o4[i] = x;
+                }
+            } else {
+                for (int i = tid; i < total; i += kThreads)
+                    inter[i] = __fdiv_rn(fmaxf(inter[i] - vmax, -p.top_db) - lo, range);
+            }
+        } else {
+            float* outc = p.out + (size_t)clip * p.n_mfcc * nfr;
+            const float thr = vmax - p.top_db;
+            float* s_l = s_pow;                                   // [n_mels][32] clipped dB tile
+            for (int t0 = 0; t0 < nfr; t0 += 32) {
+                __syncthreads();
+                for (int i = tid; i < n_mels * 32; i += kThreads) {
+                    const int m = i >> 5, f = i & 31, t = t0 + f;
+                    s_l[i] = (t < nfr) ? fmaxf(inter[(size_t)m * nfr + t], thr) : 0.f;
+                }
+                __syncthreads();
+                for (int i = tid; i < p.n_mfcc * 32; i += kThreads) {
+                    const int k = i >> 5, f = i & 31, t = t0 + f;
+                    const float* d = p.dct + (size_t)k * n_mels;
+                    float acc = 0.f;
+#pragma unroll 4
+                    for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(d + m), s_l[m * 32 + f], acc);
+                    if (t < nfr) outc[(size_t)k * nfr + t] = acc;
+                }
+            }
+            __syncthreads();
+            for (int i = tid; i < (PROWS - 257) * PROW; i += kThreads) s_pow[257 * PROW + i] = 0.f;   // s_l reuse
+            const float fn = (float)nfr;
+            for (int k = warp; k < p.n_mfcc; k += kWarps) {
+                float* row = outc + (size_t)k * nfr;
+                const float x0 = row[0];
+                float s = 0.f;
+                for (int t = lane; t < nfr; t += 32) s += row[t] - x0;
+                const float mean = x0 + __fdiv_rn(warp_sum(s), fn);
+                float ss = 0.f;
+                for (int t = lane; t < nfr; t += 32) { const float d = row[t] - mean; ss = fmaf(d, d, ss); }
+                const float sd = sqrtf(__fdiv_rn(warp_sum(ss), fn)) + 1e-8f;
+                for (int t = lane; t < nfr; t += 32) row[t] = __fdiv_rn(row[t] - mean, sd);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace
+
+size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16) {
+    return (size_t)make_layout(hop, n_mels, mel_wpad, i16).total + 128;
+}
+
+template <bool I16, int KIND>
+static cudaError_t launch_k(const FrontParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto k = logmel512_kernel<I16, KIND>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st) {
+    const size_t smem = logmel512_smem_bytes(p.hop, p.n_mels, p.mel_wpad, i16);
+    if (kind == 0) return i16 ? launch_k<true, 0>(p, grid, smem, st) : launch_k<false, 0>(p, grid, smem, st);
+    return i16 ? launch_k<true, 1>(p, grid, smem, st) : launch_k<false, 1>(p, grid, smem, st);
+}
+
+}  // namespace b2a

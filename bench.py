@@ -318,7 +318,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clips", type=int, default=100000, help="resident clips per GPU per step")
     ap.add_argument("--e2e-clips", type=int, default=16384, help="clips per end-to-end step (host buffers)")
-    ap.add_argument("--cpu-clips", type=int, default=384, help="clips in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-clips", type=int, default=6000, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

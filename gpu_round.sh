@@ -9,6 +9,6 @@ python bench.py --steps 3 --warmup 3 --clips 20000 --e2e-clips 2048 --no-cpu > g
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_$TAG.csv \
     python bench.py --steps 3 --warmup 3 --clips 20000 --e2e-clips 2048 --no-cpu > gpurun_out/ncu_l_$TAG.log 2>&1
 python bench.py --steps 3 --warmup 3 --clips 20000 --e2e-clips 2048 --no-cpu > gpurun_out/plain2_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:front_kernel -s 3 -c 2 -f -o gpurun_out/prof_$TAG \
+ncu --set full --clock-control none --import-source on -k regex:logmel512_kernel -s 3 -c 2 -f -o gpurun_out/prof_$TAG \
     python bench.py --steps 3 --warmup 3 --clips 20000 --e2e-clips 2048 --no-cpu > gpurun_out/ncu_f_$TAG.log 2>&1
 ls -la gpurun_out/
