@@ -74,6 +74,7 @@ struct b2a_handle {
     int* d_off = nullptr;
     float* d_w = nullptr;
     float* d_wq = nullptr;      // 4-padded, 0.25-prescaled weights (logmel512)
+    int* d_k0e = nullptr;
     int* d_cnt4 = nullptr;
     int* d_off4 = nullptr;
     int* d_order = nullptr;
@@ -131,7 +132,7 @@ int b2a_destroy(b2a_handle* h) {
     }
     cudaFree(h->d_window); cudaFree(h->d_tw); cudaFree(h->d_tw2);
     cudaFree(h->d_k0); cudaFree(h->d_cnt); cudaFree(h->d_off); cudaFree(h->d_w);
-    cudaFree(h->d_wq); cudaFree(h->d_cnt4); cudaFree(h->d_off4); cudaFree(h->d_order);
+    cudaFree(h->d_wq); cudaFree(h->d_k0e); cudaFree(h->d_cnt4); cudaFree(h->d_off4); cudaFree(h->d_order);
     cudaFree(h->d_dct); cudaFree(h->d_inter);
     b2a::cqt_device_free(&h->cqtdev);
     delete h;
@@ -214,12 +215,16 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
             // tables of the specialised kernel: bands padded to float4 groups, |X|^2 -> 4|X|^2 folded
             // into the weights (x0.25 is exact), bands dealt to the 8 warps in snake order by size
             std::vector<float> wq;
-            std::vector<int> cnt4(cfg->n_mels), off4(cfg->n_mels), order;
+            std::vector<int> k0e(cfg->n_mels), cnt4(cfg->n_mels), off4(cfg->n_mels), order;
             for (int m = 0; m < cfg->n_mels; ++m) {
                 off4[m] = (int)wq.size();
-                cnt4[m] = (h->mel.cnt[m] + 3) / 4;
-                for (int q = 0; q < cnt4[m] * 4; ++q)
-                    wq.push_back(q < h->mel.cnt[m] ? 0.25f * h->mel.w[h->mel.off[m] + q] : 0.f);
+                k0e[m] = h->mel.k0[m] & ~1;                       // bands start on an even bin
+                const int lead = h->mel.k0[m] - k0e[m];
+                cnt4[m] = h->mel.cnt[m] ? (lead + h->mel.cnt[m] + 3) / 4 : 0;
+                for (int q = 0; q < cnt4[m] * 4; ++q) {
+                    const int src = q - lead;
+                    wq.push_back(src >= 0 && src < h->mel.cnt[m] ? 0.25f * h->mel.w[h->mel.off[m] + src] : 0.f);
+                }
             }
             if (wq.empty()) wq.assign(4, 0.f);
             std::vector<int> idx(cfg->n_mels);
@@ -241,9 +246,10 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
             const size_t smem512 = b2a::logmel512_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad,
                                                              cfg->input_dtype == B2A_IN_I16);
             const bool fits = smem512 <= (size_t)prop.sharedMemPerBlockOptin &&
-                              (!mfcc || (size_t)cfg->n_mels * 32 <= 260u * 34u);
+                              (!mfcc || (size_t)cfg->n_mels * 32 <= 130u * 68u);
             if (fits) {
                 CU_TRY_H(upload(wq, &h->d_wq));
+                CU_TRY_H(upload(k0e, &h->d_k0e));
                 CU_TRY_H(upload(cnt4, &h->d_cnt4));
                 CU_TRY_H(upload(off4, &h->d_off4));
                 CU_TRY_H(upload(order, &h->d_order));
@@ -302,7 +308,7 @@ static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, 
     p.n_clips = n_clips; p.n_samples = h->cfg.n_samples; p.hop = h->cfg.hop_length;
     p.n_frames = h->frames; p.n_mels = h->cfg.n_mels; p.mel_nnz = (int)h->mel.w.size();
     p.n_mfcc = h->cfg.n_mfcc; p.pad_mode = h->cfg.pad_mode; p.top_db = h->cfg.top_db;
-    p.mel_wq = h->d_wq; p.mel_cnt4 = h->d_cnt4; p.mel_off4 = h->d_off4; p.mel_order = h->d_order;
+    p.mel_wq = h->d_wq; p.mel_k0e = h->d_k0e; p.mel_cnt4 = h->d_cnt4; p.mel_off4 = h->d_off4; p.mel_order = h->d_order;
     p.mel_wpad = h->mel_wpad;
     const int grid = (int)std::min<int64_t>(n_clips, h->grid_cap);
     const bool i16 = h->cfg.input_dtype == B2A_IN_I16;

@@ -28,8 +28,8 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int NC = 256, NFFT = 512, F = 32;     // complex points, frame length, frames per tile
 constexpr int XSLOT = 16 * 17 + 2;              // float2 per frame slot (pad 1 per 16, +2 slack)
-constexpr int PROW = 34;                        // power-tile row stride in words (32 frames + 2)
-constexpr int PROWS = 260;                      // bins 0..256 plus 3 zero rows for padded bands
+constexpr int PROW = 68;                        // power tile: row = 2 adjacent bins x (32 frames + 2 pad)
+constexpr int PROWS = 130;                      // bin pairs (0,1)..(256,257),(258,259): tail is zero padding
 
 __device__ __forceinline__ float db10(float s) {
     return 3.01029995663981195f * __log2f(fmaxf(s, 1e-10f));
@@ -108,7 +108,7 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.off_pow = take(PROWS * PROW * 4);
     L.off_tw2 = take(8 * 16 * 8);
     L.off_melw = take(mel_wpad * 4);
-    L.off_melk = take(n_mels * 3 * 4);
+    L.off_melk = take(n_mels * 16);
     L.off_red = take(64 * 4);
     L.off_bar = take(16);
     L.total = o;
@@ -123,9 +123,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     float* const s_pow = reinterpret_cast<float*>(smem + L.off_pow);
     float2* const s_tw2 = reinterpret_cast<float2*>(smem + L.off_tw2);
     float* const s_melw = reinterpret_cast<float*>(smem + L.off_melw);
-    int* const s_k0 = reinterpret_cast<int*>(smem + L.off_melk);
-    int* const s_cnt = s_k0 + p.n_mels;
-    int* const s_off = s_cnt + p.n_mels;
+    int4* const s_desc = reinterpret_cast<int4*>(smem + L.off_melk);
     float* const s_red = reinterpret_cast<float*>(smem + L.off_red);
     uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
 
@@ -139,8 +137,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
         s_tw2[i] = p.tw2[jj + 16 * r];
     }
     for (int i = tid; i < p.mel_wpad; i += kThreads) s_melw[i] = p.mel_wq[i];
-    for (int i = tid; i < n_mels; i += kThreads) { s_k0[i] = p.mel_k0[i]; s_cnt[i] = p.mel_cnt4[i]; s_off[i] = p.mel_off4[i]; }
-    for (int i = tid; i < (PROWS - 257) * PROW; i += kThreads) s_pow[257 * PROW + i] = 0.f;
+    for (int i = tid; i < n_mels; i += kThreads) {
+        const int m = p.mel_order[i];                        // position i is served by warp i % 8
+        s_desc[i] = make_int4((p.mel_k0e[m] >> 1) * (PROW / 2), p.mel_cnt4[m], p.mel_off4[m], m * nfr);
+    }
+    for (int i = tid; i < 2 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // bins 256..259
     if (tid == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -151,7 +152,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
 #pragma unroll
     for (int t = 0; t < 16; ++t) {
         const int q = j + 16 * t;
-        win[t] = make_float2(__ldg(p.window + 2 * q), __ldg(p.window + 2 * q + 1));
+        // int16 path: the exact power-of-two 1/32768 of librosa.load rides on the window
+        const float sc = I16 ? (1.0f / 32768.0f) : 1.0f;
+        win[t] = make_float2(__ldg(p.window + 2 * q) * sc, __ldg(p.window + 2 * q + 1) * sc);
     }
     float2 tw1[15];
 #pragma unroll
@@ -189,15 +192,16 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
         const int hi = (c0 + chunk < n) ? c0 + chunk : n;
         if (ok) {
             const int nb = ((hi - lo) / V) * V;             // bulk part, whole 16-byte units
-            for (int i = tid; i < chunk; i += kThreads) {   // zero what the bulk copy will not write
+            const int head = lo - c0;                        // [0, head) and [head+nb, chunk) are not
+            auto fill = [&](int i) {                         // written by the bulk copy
                 const int s = c0 + i;
-                if (s < lo || s >= lo + nb) {
-                    float v = 0.f;
-                    if (s >= lo + nb && s < hi) v = load_sample<I16>(cptr, s, n, 0);   // < V tail samples
-                    if (I16) reinterpret_cast<int16_t*>(dst_raw)[i] = (int16_t)__float2int_rn(v * 32768.0f);
-                    else reinterpret_cast<float*>(dst_raw)[i] = v;
-                }
-            }
+                float v = 0.f;
+                if (s >= lo + nb && s < hi) v = load_sample<I16>(cptr, s, n, 0);   // < V tail samples
+                if (I16) reinterpret_cast<int16_t*>(dst_raw)[i] = (int16_t)__float2int_rn(v * 32768.0f);
+                else reinterpret_cast<float*>(dst_raw)[i] = v;
+            };
+            for (int i = tid; i < head; i += kThreads) fill(i);
+            for (int i = head + nb + tid; i < chunk; i += kThreads) fill(i);
             if (tid == 0 && nb > 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads -> async write
                 mbar_expect_tx(s_bar, (uint32_t)(nb * esz));
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
         // generic path (reflect padding, unaligned clips): plain loads, already widened
         for (int i = tid; i < chunk; i += kThreads) {
             const float v = load_sample<I16>(cptr, c0 + i, n, p.pad_mode);
-            if (I16) reinterpret_cast<float*>(smem + L.off_audio)[i] = v;   // written after the tile's FFT
+            if (I16) reinterpret_cast<float*>(smem + L.off_audio)[i] = v * 32768.0f;   // integer-valued, see win[]
             else reinterpret_cast<float*>(dst_raw)[i] = v;
         }
         return false;
@@ -249,10 +253,10 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                     for (int g = tid; g < chunk / 4; g += kThreads) {
                         const uint2 u = r2[g];
                         float4 f;
-                        f.x = (float)(int)(short)(u.x & 0xffffu) * (1.0f / 32768.0f);
-                        f.y = (float)((int)u.x >> 16) * (1.0f / 32768.0f);
-                        f.z = (float)(int)(short)(u.y & 0xffffu) * (1.0f / 32768.0f);
-                        f.w = (float)((int)u.y >> 16) * (1.0f / 32768.0f);
+                        f.x = (float)((int)(u.x << 16) >> 16);      // integer-valued; scaled by the window
+                        f.y = (float)((int)u.x >> 16);
+                        f.z = (float)((int)(u.y << 16) >> 16);
+                        f.w = (float)((int)u.y >> 16);
                         a4[g] = f;
                     }
                 }
@@ -302,42 +306,45 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                 for (int t = 8; t < 16; ++t) mst[(t - 8) * 16] = v[t];
                 mst[8 * 16] = v[0];                                // "row 16": Z[256] == Z[0] for lane 0
                 __syncwarp();
-                float* pk = s_pow + j * PROW + f;                  // bin j + 16 r2
-                float* pn = s_pow + (NC - j) * PROW + f;           // bin 256 - j - 16 r2
+                // element (bin k, frame f) lives at word (k>>1)*PROW + 2f + (k&1)
+                float* pk = s_pow + (j >> 1) * PROW + 2 * f + (j & 1);                 // bin j + 16 r2
+                float* pn = s_pow + ((NC - j) >> 1) * PROW + 2 * f + (j & 1);          // bin 256 - j - 16 r2
 #pragma unroll
                 for (int r2 = 0; r2 < 8; ++r2) {
                     const float2 B = mld[(7 - r2) * 16];
                     float2 xk, xnk;
                     rfft_split(v[r2], B, t2[16 * r2], xk, xnk);    // 2 X[k], 2 X[256-k]
-                    pk[16 * r2 * PROW] = xk.x * xk.x + xk.y * xk.y;        // 4|X|^2: the 1/4 lives
-                    pn[-16 * r2 * PROW] = xnk.x * xnk.x + xnk.y * xnk.y;   // in the mel weights
+                    pk[8 * r2 * PROW] = xk.x * xk.x + xk.y * xk.y;         // 4|X|^2: the 1/4 lives
+                    pn[-8 * r2 * PROW] = xnk.x * xnk.x + xnk.y * xnk.y;    // in the mel weights
                 }
-                if (j == 0) s_pow[(NC / 2) * PROW + f] = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
+                if (j == 0) s_pow[(NC / 4) * PROW + 2 * f] = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
                 __syncwarp();
             }
             __syncthreads();                                       // (F) power tile complete
 
-            // (G) mel bands: lane = frame, warp-uniform band, 128-bit broadcast weight loads
+            // (G) mel bands: lane = frame, warp-uniform band; one descriptor, 128-bit broadcast
+            //     weight loads and 64-bit power loads (two adjacent bins) per step
             {
                 const int t = t0 + lane;
-                const float* pl = s_pow + lane;
+                const float2* pl = reinterpret_cast<const float2*>(s_pow) + lane;
                 for (int i = warp; i < n_mels; i += kWarps) {
-                    const int m = p.mel_order ? __ldg(p.mel_order + i) : i;
-                    const float* pr = pl + s_k0[m] * PROW;
-                    const float4* wq = reinterpret_cast<const float4*>(s_melw + s_off[m]);
-                    const int c4 = s_cnt[m];
+                    const int4 d = s_desc[i];          // {pair-row offset (float2), n float4 groups, weight offset, m*nfr}
+                    const float2* pr = pl + d.x;
+                    const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
                     float a0 = 0.f, a1 = 0.f;
-                    for (int q4 = 0; q4 < c4; ++q4) {
+#pragma unroll 2
+                    for (int q4 = 0; q4 < d.y; ++q4) {
                         const float4 w = wq[q4];
-                        a0 = fmaf(w.x, pr[0], a0);
-                        a1 = fmaf(w.y, pr[PROW], a1);
-                        a0 = fmaf(w.z, pr[2 * PROW], a0);
-                        a1 = fmaf(w.w, pr[3 * PROW], a1);
-                        pr += 4 * PROW;
+                        const float2 p0 = pr[0], p1 = pr[PROW / 2];
+                        a0 = fmaf(w.x, p0.x, a0);
+                        a1 = fmaf(w.y, p0.y, a1);
+                        a0 = fmaf(w.z, p1.x, a0);
+                        a1 = fmaf(w.w, p1.y, a1);
+                        pr += PROW;
                     }
                     if (t < nfr) {
                         const float vv = db10(a0 + a1);
-                        inter[(size_t)m * nfr + t] = vv;
+                        inter[d.w + t] = vv;
                         vmax = fmaxf(vmax, vv);
                         vmin = fminf(vmin, vv);
                     }
@@ -357,20 +364,21 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
         if constexpr (KIND == 0) {
             const float lo = fmaxf(vmin - vmax, -p.top_db);
             const float range = (0.0f - lo) + 1e-8f;
+            const float inv = __frcp_rn(range);               // x * (1/range): <= 1.5 ulp from x / range
             const int total = n_mels * nfr;
             if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(inter) & 15) == 0)) {
                 float4* o4 = reinterpret_cast<float4*>(inter);
                 for (int i = tid; i < total / 4; i += kThreads) {
                     float4 x = o4[i];
-                    x.x = __fdiv_rn(fmaxf(x.x - vmax, -p.top_db) - lo, range);
-                    x.y = __fdiv_rn(fmaxf(x.y - vmax, -p.top_db) - lo, range);
-                    x.z = __fdiv_rn(fmaxf(x.z - vmax, -p.top_db) - lo, range);
-                    x.w = __fdiv_rn(fmaxf(x.w - vmax, -p.top_db) - lo, range);
+                    x.x = (fmaxf(x.x - vmax, -p.top_db) - lo) * inv;
+                    x.y = (fmaxf(x.y - vmax, -p.top_db) - lo) * inv;
+                    x.z = (fmaxf(x.z - vmax, -p.top_db) - lo) * inv;
+                    x.w = (fmaxf(x.w - vmax, -p.top_db) - lo) * inv;
                     o4[i] = x;
                 }
             } else {
                 for (int i = tid; i < total; i += kThreads)
-                    inter[i] = __fdiv_rn(fmaxf(inter[i] - vmax, -p.top_db) - lo, range);
+                    inter[i] = (fmaxf(inter[i] - vmax, -p.top_db) - lo) * inv;
             }
         } else {
             float* outc = p.out + (size_t)clip * p.n_mfcc * nfr;
@@ -393,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                 }
             }
             __syncthreads();
-            for (int i = tid; i < (PROWS - 257) * PROW; i += kThreads) s_pow[257 * PROW + i] = 0.f;   // s_l reuse
+            for (int i = tid; i < 2 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // s_l reuse
             const float fn = (float)nfr;
             for (int k = warp; k < p.n_mfcc; k += kWarps) {
                 float* row = outc + (size_t)k * nfr;
