@@ -220,8 +220,8 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
                 off4[m] = (int)wq.size();
                 k0e[m] = h->mel.k0[m] & ~1;                       // bands start on an even bin
                 const int lead = h->mel.k0[m] - k0e[m];
-                cnt4[m] = h->mel.cnt[m] ? (lead + h->mel.cnt[m] + 3) / 4 : 0;
-                for (int q = 0; q < cnt4[m] * 4; ++q) {
+                cnt4[m] = h->mel.cnt[m] ? (lead + h->mel.cnt[m] + 7) / 8 : 0;     // 8-bin steps
+                for (int q = 0; q < cnt4[m] * 8; ++q) {
                     const int src = q - lead;
                     wq.push_back(src >= 0 && src < h->mel.cnt[m] ? 0.25f * h->mel.w[h->mel.off[m] + src] : 0.f);
                 }
@@ -246,7 +246,7 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
             const size_t smem512 = b2a::logmel512_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad,
                                                              cfg->input_dtype == B2A_IN_I16);
             const bool fits = smem512 <= (size_t)prop.sharedMemPerBlockOptin &&
-                              (!mfcc || (size_t)cfg->n_mels * 32 <= 130u * 68u);
+                              (!mfcc || (size_t)cfg->n_mels * 32 <= 132u * 68u);
             if (fits) {
                 CU_TRY_H(upload(wq, &h->d_wq));
                 CU_TRY_H(upload(k0e, &h->d_k0e));

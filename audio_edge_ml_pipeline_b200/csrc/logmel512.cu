@@ -29,7 +29,7 @@ constexpr int kWarps = kThreads / 32;
 constexpr int NC = 256, NFFT = 512, F = 32;     // complex points, frame length, frames per tile
 constexpr int XSLOT = 16 * 17 + 2;              // float2 per frame slot (pad 1 per 16, +2 slack)
 constexpr int PROW = 68;                        // power tile: row = 2 adjacent bins x (32 frames + 2 pad)
-constexpr int PROWS = 130;                      // bin pairs (0,1)..(256,257),(258,259): tail is zero padding
+constexpr int PROWS = 132;                      // bin pairs (0,1)..(256,257) + 3 zero rows for 8-bin padding
 
 __device__ __forceinline__ float db10(float s) {
     return 3.01029995663981195f * __log2f(fmaxf(s, 1e-10f));
@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
         const int m = p.mel_order[i];                        // position i is served by warp i % 8
         s_desc[i] = make_int4((p.mel_k0e[m] >> 1) * (PROW / 2), p.mel_cnt4[m], p.mel_off4[m], m * nfr);
     }
-    for (int i = tid; i < 2 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // bins 256..259
+    for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // bins 256..263
     if (tid == 0) {
         mbar_init(s_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -323,28 +323,35 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
             __syncthreads();                                       // (F) power tile complete
 
             // (G) mel bands: lane = frame, warp-uniform band; one descriptor, 128-bit broadcast
-            //     weight loads and 64-bit power loads (two adjacent bins) per step
+            //     weight loads and 64-bit power loads (two adjacent bins); bands are padded to
+            //     whole 8-bin steps with zero weights so the loop has no remainder
             {
                 const int t = t0 + lane;
+                const bool valid = t < nfr;
+                float* const outp = inter + t;
                 const float2* pl = reinterpret_cast<const float2*>(s_pow) + lane;
                 for (int i = warp; i < n_mels; i += kWarps) {
-                    const int4 d = s_desc[i];          // {pair-row offset (float2), n float4 groups, weight offset, m*nfr}
+                    const int4 d = s_desc[i];          // {pair-row offset (float2), n 8-bin steps, weight offset, m*nfr}
                     const float2* pr = pl + d.x;
                     const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
-                    float a0 = 0.f, a1 = 0.f;
-#pragma unroll 2
-                    for (int q4 = 0; q4 < d.y; ++q4) {
-                        const float4 w = wq[q4];
-                        const float2 p0 = pr[0], p1 = pr[PROW / 2];
-                        a0 = fmaf(w.x, p0.x, a0);
-                        a1 = fmaf(w.y, p0.y, a1);
-                        a0 = fmaf(w.z, p1.x, a0);
-                        a1 = fmaf(w.w, p1.y, a1);
-                        pr += PROW;
+                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    for (int q8 = 0; q8 < d.y; ++q8) {
+                        const float4 w0 = wq[0], w1 = wq[1];
+                        const float2 p0 = pr[0], p1 = pr[PROW / 2], p2 = pr[PROW], p3 = pr[3 * PROW / 2];
+                        a0 = fmaf(w0.x, p0.x, a0);
+                        a1 = fmaf(w0.y, p0.y, a1);
+                        a2 = fmaf(w0.z, p1.x, a2);
+                        a3 = fmaf(w0.w, p1.y, a3);
+                        a0 = fmaf(w1.x, p2.x, a0);
+                        a1 = fmaf(w1.y, p2.y, a1);
+                        a2 = fmaf(w1.z, p3.x, a2);
+                        a3 = fmaf(w1.w, p3.y, a3);
+                        pr += 2 * PROW;
+                        wq += 2;
                     }
-                    if (t < nfr) {
-                        const float vv = db10(a0 + a1);
-                        inter[d.w + t] = vv;
+                    const float vv = db10((a0 + a1) + (a2 + a3));
+                    if (valid) {
+                        outp[d.w] = vv;
                         vmax = fmaxf(vmax, vv);
                         vmin = fminf(vmin, vv);
                     }
@@ -364,21 +371,28 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
         if constexpr (KIND == 0) {
             const float lo = fmaxf(vmin - vmax, -p.top_db);
             const float range = (0.0f - lo) + 1e-8f;
-            const float inv = __frcp_rn(range);               // x * (1/range): <= 1.5 ulp from x / range
+            const float inv = __frcp_rn(range);
+            // x / range by one Newton step on x * (1/range): correctly rounded for these operand
+            // ranges (so the clip's peak is exactly 1.0, as with numpy's true division)
+            auto nrm = [&](float x) {
+                const float num = fmaxf(x - vmax, -p.top_db) - lo;
+                const float q = num * inv;
+                return fmaf(fmaf(-q, range, num), inv, q);
+            };
             const int total = n_mels * nfr;
             if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(inter) & 15) == 0)) {
                 float4* o4 = reinterpret_cast<float4*>(inter);
                 for (int i = tid; i < total / 4; i += kThreads) {
                     float4 x = o4[i];
-                    x.x = (fmaxf(x.x - vmax, -p.top_db) - lo) * inv;
-                    x.y = (fmaxf(x.y - vmax, -p.top_db) - lo) * inv;
-                    x.z = (fmaxf(x.z - vmax, -p.top_db) - lo) * inv;
-                    x.w = (fmaxf(x.w - vmax, -p.top_db) - lo) * inv;
+                    x.x = nrm(x.x);
+                    x.y = nrm(x.y);
+                    x.z = nrm(x.z);
+                    x.w = nrm(x.w);
                     o4[i] = x;
                 }
             } else {
                 for (int i = tid; i < total; i += kThreads)
-                    inter[i] = (fmaxf(inter[i] - vmax, -p.top_db) - lo) * inv;
+                    inter[i] = nrm(inter[i]);
             }
         } else {
             float* outc = p.out + (size_t)clip * p.n_mfcc * nfr;
@@ -401,7 +415,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                 }
             }
             __syncthreads();
-            for (int i = tid; i < 2 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // s_l reuse
+            for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // s_l reuse
             const float fn = (float)nfr;
             for (int k = warp; k < p.n_mfcc; k += kWarps) {
                 float* row = outc + (size_t)k * nfr;
