@@ -1,0 +1,295 @@
+"""The three registered extractors, B200-backed.
+
+Drop-in for ``AudioMelSpectrogram`` / ``AudioCQT`` / ``AudioMFCCSequence`` of the reference
+(``src/preprocessing/feature_extraction/audio/deep.py:75-134, 196-260, 268-328``): same ``name``,
+``feature_type``, ``modality``, constructor keywords and defaults, ``extract`` signature (unknown
+loader metadata swallowed), output dtype/shape/layout and skip-on-error behaviour.  The librosa
+calls are replaced by hand-written sm_100a kernels reached through the C ABI (``_lib.Engine``);
+there is no CPU path: without the library or a CUDA device every extract call raises.
+
+``extract_dataset`` is overridden to batch clips through the GPU(s) while reproducing the
+reference loop's observable behaviour (base.py:176-234): iteration order, ``max_samples`` by
+enumeration index, per-sample skip with a warning, label index by first *successful*
+occurrence, int32 labels, ``RuntimeError`` when nothing was extracted.
+
+Documented extensions (defaults preserve the reference): ``n_mels`` on ``audio_mfcc_seq``
+(librosa's 128), ``pad_mode`` on mel/mfcc (``"constant"`` = librosa >= 0.10), ``devices``.
+"""
+
+from __future__ import annotations
+
+import logging
+import os
+import threading
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as B
+from . import wavio
+from .base import BaseFeatureExtractor, FeatureSet, assemble_feature_set
+from .registry import register
+
+logger = logging.getLogger(__name__)
+
+HOST_BATCH_CLIPS = 4096          # clips decoded and shipped per GPU round in extract_dataset
+
+
+def _make_engine(cfg: B.B2AConfig, device: int):
+    """Engine factory (a seam: host-logic tests substitute an oracle-backed stand-in)."""
+    return B.Engine(cfg, device)
+
+
+def _resolve_devices(devices) -> list:
+    if devices is None:
+        env = os.environ.get("B2A_DEVICES", "").strip()
+        if not env:
+            return [0]
+        devices = env
+    if isinstance(devices, str):
+        if devices.lower() == "all":
+            n = B.device_count()
+            if n <= 0:
+                raise RuntimeError("no CUDA device visible: audio_edge_ml_pipeline_b200 has no CPU path")
+            return list(range(n))
+        return [int(x) for x in devices.split(",") if x.strip() != ""]
+    return [int(d) for d in devices]
+
+
+class _GpuAudioExtractor(BaseFeatureExtractor):
+    feature_type = "deep"
+    modality = "audio"
+    _kind: int = -1
+
+    sample_rate: int
+    duration: Optional[float]
+
+    def _init_common(self, devices) -> None:
+        self._devices_arg = devices
+        self._engines: dict = {}
+        self._lock = threading.Lock()
+
+    # ---- per-extractor hooks -----------------------------------------------------------
+    def _min_samples(self) -> int:
+        raise NotImplementedError
+
+    def _fill_config(self, cfg: B.B2AConfig) -> None:
+        raise NotImplementedError
+
+    # ---- engines -----------------------------------------------------------------------
+    @property
+    def devices(self) -> list:
+        return _resolve_devices(self._devices_arg)
+
+    def _engine(self, n_samples: int, in_dtype, device: int):
+        key = (int(n_samples), np.dtype(in_dtype).str, int(device))
+        with self._lock:
+            eng = self._engines.get(key)
+            if eng is None:
+                cfg = B.default_config(self._kind)
+                cfg.n_samples = int(n_samples)
+                cfg.input_dtype = B.IN_I16 if np.dtype(in_dtype) == np.int16 else B.IN_F32
+                cfg.sample_rate = int(self.sample_rate)
+                self._fill_config(cfg)
+                eng = _make_engine(cfg, device)
+                self._engines[key] = eng
+            return eng
+
+    def close(self) -> None:
+        for e in self._engines.values():
+            e.close()
+        self._engines.clear()
+
+    # ---- host-side front end (deep.py:30-61) ---------------------------------------------
+    def _prepare(self, sample_path, start_time, end_time) -> np.ndarray:
+        audio = wavio.load_segment(sample_path, self.sample_rate, start_time, end_time,
+                                   min_samples=self._min_samples())
+        if self.duration is not None:
+            audio = wavio.pad_or_trim(audio, int(self.duration * self.sample_rate))
+        return audio
+
+    # ---- compute ---------------------------------------------------------------------------
+    def extract_batch(self, clips: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """(N, n_samples) int16/float32 clips, already padded/trimmed -> (N, rows, T) float32.
+        Clips are sharded in contiguous blocks over ``devices`` (no collective)."""
+        clips = np.asarray(clips)
+        if clips.dtype != np.int16:
+            clips = clips.astype(np.float32, copy=False)
+        if clips.ndim != 2:
+            raise ValueError("clips must be (N, n_samples)")
+        n, ns = clips.shape
+        devs = self.devices
+        engines = [self._engine(ns, clips.dtype, d) for d in devs[:max(1, min(len(devs), n))]]
+        rows, frames = engines[0].rows, engines[0].frames
+        if out is None:
+            out = np.empty((n, rows, frames), dtype=np.float32)
+        if len(engines) == 1:
+            engines[0].run_host(clips, out)
+            return out
+        bounds = [n * g // len(engines) for g in range(len(engines) + 1)]
+        errs: list = []
+
+        def work(g):
+            try:
+                a, b = bounds[g], bounds[g + 1]
+                if b > a:
+                    engines[g].run_host(clips[a:b], out[a:b])
+            except Exception as exc:  # noqa: BLE001
+                errs.append(exc)
+
+        threads = [threading.Thread(target=work, args=(g,)) for g in range(len(engines))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+        return out
+
+    def extract_array(self, audio: np.ndarray) -> np.ndarray:
+        """One decoded clip (int16 or float32, any length) -> (rows, T): the body of
+        ``extract`` after ``librosa.load`` (pad to min_samples, pad/trim to duration)."""
+        audio = np.asarray(audio)
+        if audio.dtype != np.int16:
+            audio = audio.astype(np.float32, copy=False)
+        if len(audio) < self._min_samples():
+            audio = np.pad(audio, (0, self._min_samples() - len(audio)))
+        if self.duration is not None:
+            audio = wavio.pad_or_trim(audio, int(self.duration * self.sample_rate))
+        return self.extract_batch(audio[None, :])[0]
+
+    def extract(self, sample_path: Path, start_time: Optional[float] = None,
+                end_time: Optional[float] = None, **_kwargs) -> np.ndarray:
+        audio = self._prepare(sample_path, start_time, end_time)
+        return self.extract_batch(audio[None, :])[0]
+
+    def extract_dataset(self, loader, max_samples: Optional[int] = None) -> FeatureSet:
+        feats: list = []
+        labels: list = []
+        metas: list = []
+        label_to_idx: dict = {}
+        pending: list = []           # (audio, label, meta, path)
+
+        def flush():
+            if not pending:
+                return
+            # group by (length, dtype) keeping loader order inside the batch
+            results: list = [None] * len(pending)
+            groups: dict = {}
+            for idx, (audio, _l, _m, _p) in enumerate(pending):
+                groups.setdefault((len(audio), audio.dtype.str), []).append(idx)
+            for (_n, _dt), idxs in groups.items():
+                try:
+                    block = np.stack([pending[i][0] for i in idxs])
+                    got = self.extract_batch(block)
+                    for k, i in enumerate(idxs):
+                        results[i] = got[k]
+                except Exception as exc:  # noqa: BLE001 — same policy as a failing extract()
+                    for i in idxs:
+                        logger.warning("Skipping %s: %s", pending[i][3], exc)
+            for i, (_a, label, meta, _p) in enumerate(pending):
+                if results[i] is None:
+                    continue
+                feats.append(results[i])
+                metas.append(meta)
+                if label is not None:
+                    if label not in label_to_idx:
+                        label_to_idx[label] = len(label_to_idx)
+                    labels.append(label_to_idx[label])
+            pending.clear()
+
+        for i, (sample_path, label, meta) in enumerate(loader):
+            if max_samples is not None and i >= max_samples:
+                break
+            try:
+                audio = self._prepare(sample_path, meta.get("start_time"), meta.get("end_time"))
+            except Exception as exc:  # noqa: BLE001
+                logger.warning("Skipping %s: %s", sample_path, exc)
+                continue
+            pending.append((audio, label, meta, sample_path))
+            if len(pending) >= HOST_BATCH_CLIPS:
+                flush()
+        flush()
+        return assemble_feature_set(self, feats, labels, metas, label_to_idx)
+
+
+@register
+class AudioMelSpectrogram(_GpuAudioExtractor):
+    """Log-mel spectrogram in [0, 1], shape ``(n_mels, T)`` — deep.py:75-134."""
+
+    name = "audio_mel_spec"
+    _kind = B.KIND_MEL
+
+    def __init__(self, sample_rate: int = 16000, n_mels: int = 40, n_fft: int = 512,
+                 hop_length: int = 160, duration: Optional[float] = None, *,
+                 pad_mode: str = "constant", devices: Optional[Sequence[int]] = None) -> None:
+        self.sample_rate = sample_rate
+        self.n_mels = n_mels
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.duration = duration
+        self.pad_mode = pad_mode
+        self._init_common(devices)
+
+    def _min_samples(self) -> int:
+        return self.n_fft                      # deep.py:119-120
+
+    def _fill_config(self, cfg) -> None:
+        cfg.n_fft, cfg.hop_length, cfg.n_mels = int(self.n_fft), int(self.hop_length), int(self.n_mels)
+        cfg.pad_mode = {"constant": B.PAD_CONSTANT, "reflect": B.PAD_REFLECT}[self.pad_mode]
+
+
+@register
+class AudioCQT(_GpuAudioExtractor):
+    """Log-magnitude constant-Q transform in [0, 1], shape ``(n_bins, T)`` — deep.py:196-260."""
+
+    name = "audio_cqt"
+    _kind = B.KIND_CQT
+
+    def __init__(self, sample_rate: int = 22050, hop_length: int = 512, n_bins: int = 84,
+                 bins_per_octave: int = 12, fmin: Optional[float] = None,
+                 duration: Optional[float] = None, *, devices: Optional[Sequence[int]] = None) -> None:
+        self.sample_rate = sample_rate
+        self.hop_length = hop_length
+        self.n_bins = n_bins
+        self.bins_per_octave = bins_per_octave
+        self.fmin = fmin
+        self.duration = duration
+        self._init_common(devices)
+
+    def _min_samples(self) -> int:
+        return self.hop_length * 2             # deep.py:242-243
+
+    def _fill_config(self, cfg) -> None:
+        cfg.hop_length, cfg.n_bins = int(self.hop_length), int(self.n_bins)
+        cfg.bins_per_octave = int(self.bins_per_octave)
+        cfg.fmin = float(self.fmin) if self.fmin is not None else 0.0
+
+
+@register
+class AudioMFCCSequence(_GpuAudioExtractor):
+    """Per-coefficient z-scored MFCC sequence, shape ``(n_mfcc, T)`` — deep.py:268-328."""
+
+    name = "audio_mfcc_seq"
+    _kind = B.KIND_MFCC
+
+    def __init__(self, sample_rate: int = 22050, n_mfcc: int = 40, n_fft: int = 1024,
+                 hop_length: int = 512, duration: Optional[float] = None, *, n_mels: int = 128,
+                 pad_mode: str = "constant", devices: Optional[Sequence[int]] = None) -> None:
+        self.sample_rate = sample_rate
+        self.n_mfcc = n_mfcc
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.duration = duration
+        self.n_mels = n_mels
+        self.pad_mode = pad_mode
+        self._init_common(devices)
+
+    def _min_samples(self) -> int:
+        return self.n_fft                      # deep.py:311-312
+
+    def _fill_config(self, cfg) -> None:
+        cfg.n_fft, cfg.hop_length = int(self.n_fft), int(self.hop_length)
+        cfg.n_mels, cfg.n_mfcc = int(self.n_mels), int(self.n_mfcc)
+        cfg.pad_mode = {"constant": B.PAD_CONSTANT, "reflect": B.PAD_REFLECT}[self.pad_mode]

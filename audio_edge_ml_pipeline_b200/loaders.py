@@ -1,0 +1,67 @@
+"""Class-per-folder audio loader with the iteration contract of the reference's
+``AudioFolderLoader`` (``src/preprocessing/dataset_loaders/audio_folder_loader.py:106-232``):
+sorted class folders, sorted clips, per-sample metadata ``filename / class_dir / duration /
+sample_rate / n_channels`` (header probe, zeros on failure), optional split sub-directory and
+``split_manifest.json`` filter.  Inside the reference tree the reference's own loaders are used
+unchanged; this one lets the package run stand-alone."""
+
+from __future__ import annotations
+
+import json
+import logging
+from pathlib import Path
+from typing import Iterator, Optional
+
+from .base import BaseDatasetLoader
+from .wavio import wav_info
+
+logger = logging.getLogger(__name__)
+
+_AUDIO_SUFFIXES = frozenset({".wav", ".flac", ".ogg", ".mp3", ".aac", ".m4a", ".opus", ".aiff", ".aif"})
+
+
+class AudioFolderLoader(BaseDatasetLoader):
+    def __init__(self, root, split: Optional[str] = None, extensions=None, class_names=None,
+                 manifest=None, manifest_split: Optional[str] = None) -> None:
+        eff = Path(root) / split if split else Path(root)
+        if not eff.is_dir():
+            raise NotADirectoryError(f"Dataset root not found: {eff}")
+        exts = frozenset(e.lower() for e in extensions) if extensions is not None else _AUDIO_SUFFIXES
+        if class_names is not None:
+            self._class_names = list(class_names)
+            class_dirs = [eff / c for c in class_names]
+        else:
+            class_dirs = sorted(p for p in eff.iterdir() if p.is_dir())
+            self._class_names = [d.name for d in class_dirs]
+        self._samples: list = []
+        for class_dir, label in zip(class_dirs, self._class_names):
+            if not class_dir.is_dir():
+                logger.warning("Class directory not found: %s (skipping)", class_dir)
+                continue
+            clips = sorted(p for p in class_dir.iterdir() if p.is_file() and p.suffix.lower() in exts)
+            if not clips:
+                logger.warning("No audio files found in: %s", class_dir)
+            for clip in clips:
+                self._samples.append((clip, label, {"filename": clip.name, "class_dir": class_dir.name,
+                                                    **wav_info(clip)}))
+        if manifest is not None:
+            if manifest_split is None:
+                raise ValueError("manifest_split must be set when manifest is given")
+            allowed = set(json.loads(Path(manifest).read_text()).get(manifest_split, []))
+            rr = Path(root)
+            self._samples = [s for s in self._samples if str(s[0].relative_to(rr)) in allowed]
+        logger.info("AudioFolderLoader: %d clips across %d classes.", len(self._samples), len(self._class_names))
+
+    def __len__(self) -> int:
+        return len(self._samples)
+
+    def __iter__(self) -> Iterator[tuple]:
+        yield from self._samples
+
+    @property
+    def class_names(self) -> list:
+        return list(self._class_names)
+
+    @property
+    def n_classes(self) -> int:
+        return len(self._class_names)

@@ -1,0 +1,269 @@
+"""Host-side mirror of the reference's plugin interface: registry, extractor constructors,
+extract / extract_dataset semantics, WAV decode, persistence layout, YAML config.  The compute
+engine is replaced by tests/fake_engine.py (oracle-backed) — these tests run without a GPU."""
+import inspect
+import json
+import logging
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import audio_edge_ml_pipeline_b200 as P
+from audio_edge_ml_pipeline_b200 import extractors, pipeline, registry, synth, wavio
+from audio_edge_ml_pipeline_b200.base import BaseFeatureExtractor
+from fake_engine import FakeEngine
+from oracle import librosa_restated as L
+
+REF = Path("/root/reference")
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    FakeEngine.calls = []
+    monkeypatch.setattr(extractors, "_make_engine", lambda cfg, dev: FakeEngine(cfg, dev))
+    return FakeEngine
+
+
+def _make_dataset(root: Path, sr=16000, n=8000, classes=("bird", "axe", "rain"), per=3, seed=0, broken=()):
+    rng = np.random.default_rng(seed)
+    clips = {}
+    for c in classes:
+        (root / c).mkdir(parents=True)
+        for i in range(per):
+            pcm = synth.to_pcm16(rng.standard_normal(int(n * rng.uniform(0.7, 1.2))) * 0.1)
+            p = root / c / f"clip_{i}.wav"
+            if (c, i) in broken:
+                p.write_bytes(b"not a wav file")
+            else:
+                wavio.write_wav_pcm16(p, pcm, sr)
+            clips[(c, i)] = pcm
+    return clips
+
+
+# ---- registry / constructors -------------------------------------------------------------------
+
+def test_registry_semantics_match_reference():
+    assert P.list_extractors() == ["audio_cqt", "audio_mel_spec", "audio_mfcc_seq"]
+    assert P.get("audio_mel_spec") is P.AudioMelSpectrogram
+    with pytest.raises(KeyError):
+        P.get("nope")
+    with pytest.raises(ValueError):
+        registry.register(P.AudioMelSpectrogram)          # duplicate name
+
+    class NoName(BaseFeatureExtractor):
+        def extract(self, sample_path, **kw):
+            return np.zeros(1)
+    with pytest.raises(TypeError):
+        registry.register(NoName)
+
+
+def test_constructor_signatures_are_the_reference_ones():
+    def pos(cls):
+        return [(n, p.default) for n, p in inspect.signature(cls.__init__).parameters.items()
+                if n != "self" and p.kind == p.POSITIONAL_OR_KEYWORD]
+    assert pos(P.AudioMelSpectrogram) == [("sample_rate", 16000), ("n_mels", 40), ("n_fft", 512),
+                                          ("hop_length", 160), ("duration", None)]          # deep.py:98-105
+    assert pos(P.AudioMFCCSequence) == [("sample_rate", 22050), ("n_mfcc", 40), ("n_fft", 1024),
+                                        ("hop_length", 512), ("duration", None)]            # deep.py:290-297
+    assert pos(P.AudioCQT) == [("sample_rate", 22050), ("hop_length", 512), ("n_bins", 84),
+                               ("bins_per_octave", 12), ("fmin", None), ("duration", None)]  # deep.py:219-227
+    for cls, nm in ((P.AudioMelSpectrogram, "audio_mel_spec"), (P.AudioMFCCSequence, "audio_mfcc_seq"),
+                    (P.AudioCQT, "audio_cqt")):
+        assert (cls.name, cls.feature_type, cls.modality) == (nm, "deep", "audio")
+    with pytest.raises(TypeError):                          # pipeline.py:524 splat: unknown key fails
+        P.AudioMelSpectrogram(bogus=1)
+    # the YAML keys of config/feature_extraction.yaml:65-70
+    P.AudioMelSpectrogram(duration=5.0, n_mels=40, sample_rate=16000, n_fft=512, hop_length=160)
+
+
+@pytest.mark.skipif(not REF.exists(), reason="authoring container only")
+def test_constructor_signatures_against_reference_source():
+    import ast
+    tree = ast.parse((REF / "src/preprocessing/feature_extraction/audio/deep.py").read_text())
+    want = {}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef):
+            for f in node.body:
+                if isinstance(f, ast.FunctionDef) and f.name == "__init__":
+                    args = [a.arg for a in f.args.args[1:]]
+                    defs = [ast.literal_eval(d) for d in f.args.defaults]
+                    want[node.name] = list(zip(args, defs))
+    for cls in (P.AudioMelSpectrogram, P.AudioMFCCSequence, P.AudioCQT):
+        got = [(n, p.default) for n, p in inspect.signature(cls.__init__).parameters.items()
+               if n != "self" and p.kind == p.POSITIONAL_OR_KEYWORD]
+        assert got == want[cls.__name__]
+
+
+# ---- extract / extract_dataset -------------------------------------------------------------------
+
+def test_extract_swallows_loader_metadata_and_matches_oracle(tmp_path, fake):
+    pcm = synth.to_pcm16(np.random.default_rng(1).standard_normal(20000) * 0.1)
+    wavio.write_wav_pcm16(tmp_path / "a.wav", pcm, 16000)
+    ex = P.AudioMelSpectrogram(duration=1.0)
+    got = ex.extract(tmp_path / "a.wav", filename="a.wav", class_dir="x", duration=1.25, sample_rate=16000,
+                     n_channels=1)                        # audio_folder_loader.py:181-185 metadata
+    ref = L.audio_mel_spec(L.pcm16_to_float(pcm), duration=1.0)
+    assert got.shape == (40, 101) and got.dtype == np.float32 and got.flags.c_contiguous
+    assert np.array_equal(got, ref)
+    seg = ex.extract(tmp_path / "a.wav", start_time=0.25, end_time=0.75)
+    ref = L.audio_mel_spec(L.pcm16_to_float(pcm[4000:12000]), duration=1.0)
+    assert np.array_equal(seg, ref)
+
+
+def test_short_clip_is_padded_to_min_samples(tmp_path, fake):
+    wavio.write_wav_pcm16(tmp_path / "s.wav", np.arange(100, dtype=np.int16), 16000)
+    assert P.AudioMelSpectrogram().extract(tmp_path / "s.wav").shape == (40, 1 + 512 // 160)      # n_fft
+    assert P.AudioCQT(sample_rate=16000, n_bins=24).extract(tmp_path / "s.wav").shape == (24, 3)  # 2*hop
+
+
+def test_extract_dataset_reproduces_reference_loop(tmp_path, fake, caplog):
+    clips = _make_dataset(tmp_path / "ds", broken={("axe", 1)})
+    loader = P.loaders.AudioFolderLoader(tmp_path / "ds") if hasattr(P, "loaders") else None
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    loader = AudioFolderLoader(tmp_path / "ds")
+    ex = P.AudioMelSpectrogram(duration=0.5)
+    with caplog.at_level(logging.WARNING):
+        fs = ex.extract_dataset(loader)
+    serial = BaseFeatureExtractor.extract_dataset(ex, loader)        # the reference's loop, verbatim semantics
+    assert np.array_equal(fs.features, serial.features) and fs.features.shape == (8, 40, 51)
+    assert np.array_equal(fs.labels, serial.labels) and fs.labels.dtype == np.int32
+    assert fs.label_names == serial.label_names == ["axe", "bird", "rain"]     # sorted dirs, first-seen order
+    assert fs.metadata == serial.metadata and len(fs.metadata) == 8
+    assert any("Skipping" in r.message for r in caplog.records)
+    assert fs.features.flags.c_contiguous and fs.features.dtype == np.float32
+    # max_samples cuts by enumeration index, failed samples included (base.py:199-201)
+    fs4 = ex.extract_dataset(loader, max_samples=5)
+    assert fs4.n_samples == 4 and fs4.label_names == ["axe", "bird"]
+
+
+def test_extract_dataset_first_class_all_broken_shifts_label_indices(tmp_path, fake):
+    _make_dataset(tmp_path / "ds", classes=("a", "b"), per=2, broken={("a", 0), ("a", 1)})
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    fs = P.AudioMelSpectrogram(duration=0.5).extract_dataset(AudioFolderLoader(tmp_path / "ds"))
+    assert fs.label_names == ["b"] and fs.labels.tolist() == [0, 0]
+
+
+def test_extract_dataset_nothing_extracted_raises(tmp_path, fake):
+    _make_dataset(tmp_path / "ds", classes=("a",), per=2, broken={("a", 0), ("a", 1)})
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    with pytest.raises(RuntimeError, match="No features were successfully extracted."):
+        P.AudioMelSpectrogram().extract_dataset(AudioFolderLoader(tmp_path / "ds"))
+
+
+def test_rate_mismatch_is_a_per_sample_skip(tmp_path, fake):
+    (tmp_path / "ds" / "a").mkdir(parents=True)
+    wavio.write_wav_pcm16(tmp_path / "ds" / "a" / "x.wav", np.zeros(4000, np.int16), 8000)
+    wavio.write_wav_pcm16(tmp_path / "ds" / "a" / "y.wav", np.zeros(4000, np.int16), 16000)
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    fs = P.AudioMelSpectrogram(duration=0.25).extract_dataset(AudioFolderLoader(tmp_path / "ds"))
+    assert fs.n_samples == 1 and fs.metadata[0]["filename"] == "y.wav"
+
+
+def test_multi_device_sharding_is_contiguous_and_ordered(fake):
+    pcm = synth.make_suite(10, 16000, 4000, seed=3)
+    one = P.AudioMelSpectrogram(devices=[0]).extract_batch(pcm)
+    FakeEngine.calls = []
+    four = P.AudioMelSpectrogram(devices=[0, 1, 2, 3]).extract_batch(pcm)
+    assert np.array_equal(one, four)
+    assert sorted(FakeEngine.calls) == [(0, 2), (1, 3), (2, 2), (3, 3)]
+
+
+def test_mfcc_and_cqt_extractors_match_oracle(tmp_path, fake):
+    pcm = synth.to_pcm16(np.random.default_rng(5).standard_normal(22050) * 0.1)
+    wavio.write_wav_pcm16(tmp_path / "a.wav", pcm, 22050)
+    y = L.pcm16_to_float(pcm)
+    assert np.array_equal(P.AudioMFCCSequence(duration=1.0).extract(tmp_path / "a.wav"),
+                          L.audio_mfcc_seq(y, duration=1.0))
+    assert np.array_equal(P.AudioMFCCSequence(sample_rate=22050, n_mfcc=13, n_fft=512, hop_length=160, n_mels=40)
+                          .extract(tmp_path / "a.wav"), L.audio_mfcc_seq(y, 22050, 13, 512, 160, None, n_mels=40))
+    assert np.array_equal(P.AudioCQT(duration=1.0).extract(tmp_path / "a.wav"), L.audio_cqt(y, duration=1.0))
+
+
+# ---- WAV decode ------------------------------------------------------------------------------------
+
+def test_wav_decode_variants(tmp_path):
+    import scipy.io.wavfile as wf
+    rng = np.random.default_rng(7)
+    x16 = synth.to_pcm16(rng.standard_normal(3000) * 0.2)
+    wavio.write_wav_pcm16(tmp_path / "m16.wav", x16, 16000)
+    a, sr = wavio.decode_wav(tmp_path / "m16.wav")
+    assert sr == 16000 and a.dtype == np.int16 and np.array_equal(a, x16)
+    assert np.array_equal(wf.read(tmp_path / "m16.wav")[1], x16)           # our writer is a valid WAV
+    st = np.stack([x16, x16[::-1]], axis=1)
+    wf.write(tmp_path / "s16.wav", 16000, st)
+    a, _ = wavio.decode_wav(tmp_path / "s16.wav")
+    assert a.dtype == np.float32 and np.allclose(a, (st.astype(np.float32) / 32768).mean(axis=1))
+    f32 = (rng.standard_normal(3000) * 0.1).astype(np.float32)
+    wf.write(tmp_path / "f32.wav", 22050, f32)
+    a, sr = wavio.decode_wav(tmp_path / "f32.wav")
+    assert sr == 22050 and np.array_equal(a, f32)
+    i32 = (rng.integers(-2**31, 2**31 - 1, 1000)).astype(np.int32)
+    wf.write(tmp_path / "i32.wav", 8000, i32)
+    a, _ = wavio.decode_wav(tmp_path / "i32.wav")
+    assert np.allclose(a, i32 / 2147483648.0, atol=1e-7)
+    a, _ = wavio.decode_wav(tmp_path / "m16.wav", offset=0.05, duration=0.1)
+    assert np.array_equal(a, x16[800:2400])
+    info = wavio.wav_info(tmp_path / "s16.wav")
+    assert info == {"duration": 3000 / 16000, "sample_rate": 16000, "n_channels": 2}
+    assert wavio.wav_info(tmp_path / "missing.wav") == {"duration": 0.0, "sample_rate": 0, "n_channels": 0}
+    with pytest.raises(wavio.AudioDecodeError):
+        (tmp_path / "bad.wav").write_bytes(b"garbage")
+        wavio.decode_wav(tmp_path / "bad.wav")
+
+
+# ---- persistence + config ---------------------------------------------------------------------------
+
+def test_save_layout_and_roundtrip(tmp_path, fake):
+    _make_dataset(tmp_path / "ds")
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    fs = P.FeaturePipeline(AudioFolderLoader(tmp_path / "ds"), P.AudioMelSpectrogram(duration=0.5)).run()
+    P.FeaturePipeline.save(fs, tmp_path / "out")
+    assert sorted(p.name for p in (tmp_path / "out").iterdir()) == ["features.npy", "info.json", "label_names.json",
+                                                                   "labels.npy", "metadata.json"]
+    f = np.load(tmp_path / "out" / "features.npy")
+    assert f.shape == (9, 40, 51) and f.dtype == np.float32 and f.flags.c_contiguous
+    assert np.load(tmp_path / "out" / "labels.npy").dtype == np.int32
+    info = json.loads((tmp_path / "out" / "info.json").read_text())
+    assert info == {"feature_type": "deep", "modality": "audio", "n_samples": 9, "feature_shape": [40, 51],
+                    "n_classes": 3, "is_supervised": True}
+    back = P.FeaturePipeline.load(tmp_path / "out")
+    assert np.array_equal(back.features, fs.features) and back.label_names == fs.label_names
+    with pytest.raises(FileNotFoundError):
+        P.FeaturePipeline.load(tmp_path / "nowhere")
+
+
+def test_reference_yaml_runs_unchanged(tmp_path, fake, monkeypatch):
+    """config/feature_extraction.yaml:60-70, copied verbatim (keys + extractor_params)."""
+    cfg = """
+dataset: DS
+experiments:
+  - name:           fsc22_device_augmented_melspec_train
+    extractor:      audio_mel_spec
+    loader:         audio_folder
+    dataset:        DS
+    split:          ""
+    unknown_key:    ignored
+    extractor_params:
+      duration:    5.0
+      n_mels:      40
+      sample_rate: 16000
+      n_fft:       512
+      hop_length:  160
+""".replace("DS", str(tmp_path / "ds"))
+    _make_dataset(tmp_path / "ds", n=80000, classes=("a", "b"), per=2)
+    (tmp_path / "c.yaml").write_text(cfg)
+    monkeypatch.chdir(tmp_path)
+    (fs,) = pipeline.run_config(tmp_path / "c.yaml")
+    out = tmp_path / "data/processed/fsc22_device_augmented_melspec_train"
+    assert np.load(out / "features.npy").shape == (4, 40, 501)
+    assert (out / "config.yaml").read_text() == cfg
+    if REF.exists():
+        import yaml
+        ref_cfg = yaml.safe_load((REF / "config/feature_extraction.yaml").read_text())
+        exps = pipeline.resolve_experiments(ref_cfg)
+        assert exps[0]["extractor"] == "audio_mel_spec" and exps[0]["loader"] == "audio_folder"
+        assert exps[0]["extractor_params"] == {"duration": 5.0, "n_mels": 40, "sample_rate": 16000,
+                                               "n_fft": 512, "hop_length": 160}
+        P.get(exps[0]["extractor"])(**exps[0]["extractor_params"])
