@@ -290,7 +290,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
                          "bytes_per_clip": BYTES_PER_CLIP, "kernel": "front_kernel<8,true,0>",
-                         "traffic": (traffic or {}).get("dram_bytes_per_launch") if traffic else None,
+                         "traffic": (traffic["dram_bytes_per_clip"] * n) if traffic else None,
                          "traffic_note": (traffic or {}).get("note") if traffic else "no ncu capture committed yet",
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": ne * N_SAMPLES * 2,
