@@ -220,8 +220,8 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
                 off4[m] = (int)wq.size();
                 k0e[m] = h->mel.k0[m] & ~1;                       // bands start on an even bin
                 const int lead = h->mel.k0[m] - k0e[m];
-                cnt4[m] = h->mel.cnt[m] ? (lead + h->mel.cnt[m] + 7) / 8 : 0;     // 8-bin steps
-                for (int q = 0; q < cnt4[m] * 8; ++q) {
+                cnt4[m] = h->mel.cnt[m] ? (lead + h->mel.cnt[m] + 3) / 4 : 0;     // 4-bin steps
+                for (int q = 0; q < cnt4[m] * 4; ++q) {
                     const int src = q - lead;
                     wq.push_back(src >= 0 && src < h->mel.cnt[m] ? 0.25f * h->mel.w[h->mel.off[m] + src] : 0.f);
                 }

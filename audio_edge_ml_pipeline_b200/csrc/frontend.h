@@ -19,7 +19,7 @@ struct FrontParams {
     // 4-padded, 0.25-prescaled banded weights + balanced band order (logmel512 kernel)
     const float* mel_wq;
     const int* mel_k0e;      // per band: first bin rounded down to even
-    const int* mel_cnt4;     // per band: number of 8-bin steps (from mel_k0e)
+    const int* mel_cnt4;     // per band: number of 4-bin steps (from mel_k0e)
     const int* mel_off4;     // per band: float offset into mel_wq (multiple of 4)
     const int* mel_order;    // band processed at position i (position i belongs to warp i % 8)
     int mel_wpad;            // floats in mel_wq

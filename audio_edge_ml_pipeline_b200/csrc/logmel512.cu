@@ -19,6 +19,7 @@
 #include "fft_core.cuh"
 
 #include <cstdint>
+#include <type_traits>
 
 namespace b2a {
 
@@ -27,12 +28,23 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int NC = 256, NFFT = 512, F = 32;     // complex points, frame length, frames per tile
-constexpr int XSLOT = 16 * 17 + 2;              // float2 per frame slot (pad 1 per 16, +2 slack)
+constexpr int XS = 18;                          // exchange row stride (float2): 128-bit pass-1 stores and
+constexpr int XSLOT = 16 * XS + 2;              // 64-bit pass-2 loads are both conflict-free
 constexpr int PROW = 68;                        // power tile: row = 2 adjacent bins x (32 frames + 2 pad)
 constexpr int PROWS = 132;                      // bin pairs (0,1)..(256,257) + 3 zero rows for 8-bin padding
 
 __device__ __forceinline__ float db10(float s) {
-    return 3.01029995663981195f * __log2f(fmaxf(s, 1e-10f));
+    // 10*log10(max(amin, s)); the argument is >= 1e-10, never denormal -> lg2.approx.ftz
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(s, 1e-10f)));
+    return 3.01029995663981195f * l;
+}
+// two packed int16 PCM samples -> two integer-valued floats (the 1/32768 rides on the window)
+__device__ __forceinline__ float2 cvt_pcm2(uint32_t u) {
+    float lo, hi;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.rn.f32.s16 %0, l;\n\tcvt.rn.f32.s16 %1, h;\n\t}"
+        : "=f"(lo), "=f"(hi) : "r"(u));
+    return make_float2(lo, hi);
 }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -74,15 +86,15 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <bool I16>
-__device__ __forceinline__ float load_sample(const void* clip, int s, int n, int pad_mode) {
+// sample s of a clip in its storage type; zero (or the reflected sample) outside [0, n)
+template <typename E>
+__device__ __forceinline__ E raw_sample(const E* clip, int s, int n, int pad_mode) {
     if (s < 0 || s >= n) {
-        if (pad_mode == 0) return 0.f;
-        s = (s < 0) ? -s : 2 * (n - 1) - s;
-        if (s < 0 || s >= n) return 0.f;
+        if (pad_mode == 0) return (E)0;
+        s = (s < 0) ? -s : 2 * (n - 1) - s;          // np.pad(mode="reflect")
+        if (s < 0 || s >= n) return (E)0;
     }
-    if (I16) return (float)((const int16_t*)clip)[s] * (1.0f / 32768.0f);
-    return ((const float*)clip)[s];
+    return clip[s];
 }
 
 struct Layout {
@@ -95,15 +107,10 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.chunk = (hop * (F - 1) + NFFT + 7) & ~7;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
-    if (i16) {
-        L.off_raw = take(L.chunk * 2);
-        L.off_raw2 = L.off_raw;
-        L.off_audio = take(L.chunk * 4);
-    } else {
-        L.off_raw = take(L.chunk * 4);          // two fp32 buffers, transformed in place
-        L.off_raw2 = take(L.chunk * 4);
-        L.off_audio = L.off_raw;
-    }
+    const int esz = i16 ? 2 : 4;                // two raw buffers (ping-pong), read directly by pass 1
+    L.off_raw = take(L.chunk * esz);
+    L.off_raw2 = take(L.chunk * esz);
+    L.off_audio = L.off_raw;
     L.off_xch = take(16 * XSLOT * 8);
     L.off_pow = take(PROWS * PROW * 4);
     L.off_tw2 = take(8 * 16 * 8);
@@ -160,75 +167,52 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
 #pragma unroll
     for (int t = 1; t < 16; ++t) tw1[t - 1] = p.tw[t * j];
     float2* const xs = s_xch + (2 * warp + h) * XSLOT;       // this frame's exchange slot
-    float2* const x1 = xs + 17 * j;                          // pass-1 store base
-    float2* const x2 = xs + j;                               // pass-2 load base (stride 17)
+    float4* const x1 = reinterpret_cast<float4*>(xs + XS * j);   // pass-1 store base (row j, 2 points per store)
+    float2* const x2 = xs + j;                               // pass-2 load base (column j, stride XS)
     float2* const mst = xs + j;                              // mirror store base: M[(row-8)*16 + j]
     const float2* const mld = xs + (j ? 16 - j : 16);        // mirror load base:  M[(7-r)*16 + ...]
     const float2* const t2 = s_tw2 + j;
     __syncthreads();
 
-    const size_t esz = I16 ? 2 : 4;
-    constexpr int V = I16 ? 8 : 4;                           // samples per 16 bytes
+    using E = typename std::conditional<I16, int16_t, float>::type;
+    constexpr int V = 16 / (int)sizeof(E);                   // samples per 16 bytes
     const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
     uint32_t bar_parity = 0;
-    int buf = 0;                                             // fp32 input: which raw buffer holds this tile
+    int buf = 0;                                             // which raw buffer holds the current tile
 
-    // Issue (or perform) the staging of one tile into `dst_raw`.  Returns true when a bulk copy is
-    // in flight on s_bar (every thread computes the same answer).
-    // true when tile (clip, t0) can be staged by a bulk copy (uniform over the CTA)
-    auto can_bulk = [&](long long clip, int t0) -> bool {
+    // Stage tile (clip, t0) into dst.  Aligned zero-padded clips go by one TMA bulk copy (returns
+    // true: completion arrives on s_bar) with the clip's head/tail zero-filled by plain stores;
+    // reflect padding or unaligned clips use plain loads.  Every thread computes the same answer.
+    auto stage_issue = [&](long long clip, int t0, E* dst) -> bool {
         const long long e0 = clip * (long long)n;
+        const E* cptr = reinterpret_cast<const E*>(p.clips) + e0;
         const int c0 = t0 * hop - NFFT / 2;
         const int lo = c0 < 0 ? 0 : c0;
         const int hi = (c0 + chunk < n) ? c0 + chunk : n;
-        return p.pad_mode == 0 && base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
-               (((lo - c0) & (V - 1)) == 0);
-    };
-    auto stage_issue = [&](long long clip, int t0, unsigned char* dst_raw, bool ok) -> bool {
-        const long long e0 = clip * (long long)n;
-        const unsigned char* cptr = (const unsigned char*)p.clips + (size_t)e0 * esz;
-        const int c0 = t0 * hop - NFFT / 2;
-        const int lo = c0 < 0 ? 0 : c0;
-        const int hi = (c0 + chunk < n) ? c0 + chunk : n;
-        if (ok) {
-            const int nb = ((hi - lo) / V) * V;             // bulk part, whole 16-byte units
-            const int head = lo - c0;                        // [0, head) and [head+nb, chunk) are not
-            auto fill = [&](int i) {                         // written by the bulk copy
-                const int s = c0 + i;
-                float v = 0.f;
-                if (s >= lo + nb && s < hi) v = load_sample<I16>(cptr, s, n, 0);   // < V tail samples
-                if (I16) reinterpret_cast<int16_t*>(dst_raw)[i] = (int16_t)__float2int_rn(v * 32768.0f);
-                else reinterpret_cast<float*>(dst_raw)[i] = v;
-            };
-            for (int i = tid; i < head; i += kThreads) fill(i);
-            for (int i = head + nb + tid; i < chunk; i += kThreads) fill(i);
-            if (tid == 0 && nb > 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic reads -> async write
-                mbar_expect_tx(s_bar, (uint32_t)(nb * esz));
-                bulk_g2s(dst_raw + (size_t)(lo - c0) * esz, cptr + (size_t)lo * esz, (uint32_t)(nb * esz), s_bar);
-            }
-            return nb > 0;
+        const bool ok = p.pad_mode == 0 && base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
+                        (((lo - c0) & (V - 1)) == 0);
+        if (!ok) {
+            for (int i = tid; i < chunk; i += kThreads) dst[i] = raw_sample<E>(cptr, c0 + i, n, p.pad_mode);
+            return false;
         }
-        // generic path (reflect padding, unaligned clips): plain loads, already widened
-        for (int i = tid; i < chunk; i += kThreads) {
-            const float v = load_sample<I16>(cptr, c0 + i, n, p.pad_mode);
-            if (I16) reinterpret_cast<float*>(smem + L.off_audio)[i] = v * 32768.0f;   // integer-valued, see win[]
-            else reinterpret_cast<float*>(dst_raw)[i] = v;
+        const int nb = ((hi - lo) / V) * V;                  // bulk part, whole 16-byte units
+        const int head = lo - c0;                            // [0, head) and [head+nb, chunk) are not
+        for (int i = tid; i < head; i += kThreads) dst[i] = (E)0;                 // written by the bulk copy
+        for (int i = head + nb + tid; i < chunk; i += kThreads) dst[i] = raw_sample<E>(cptr, c0 + i, n, 0);
+        if (tid == 0 && nb > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic reads -> async write
+            mbar_expect_tx(s_bar, (uint32_t)(nb * sizeof(E)));
+            bulk_g2s(dst + head, cptr + lo, (uint32_t)(nb * sizeof(E)), s_bar);
         }
-        return false;
+        return nb > 0;
     };
-    // The generic path writes the fp32 samples directly, so it runs at the start of its own tile
-    // (where the bulk path's conversion runs), never as a prefetch: `deferred` carries that.
 
     const int tiles = (nfr + F - 1) / F;
     long long clip = blockIdx.x;
     if (clip >= p.n_clips) return;
-    // prologue: stage the first tile of the first clip
-    unsigned char* raw0 = smem + L.off_raw;
-    unsigned char* raw1 = smem + L.off_raw2;
-    bool inflight = false, deferred = false;
-    if (can_bulk(clip, 0)) inflight = stage_issue(clip, 0, raw0, true);
-    else deferred = true;
+    E* const raw0 = reinterpret_cast<E*>(smem + L.off_raw);
+    E* const raw1 = reinterpret_cast<E*>(smem + L.off_raw2);
+    bool inflight = stage_issue(clip, 0, raw0);            // prologue: first tile of the first clip
 
     for (; clip < p.n_clips; clip += gridDim.x) {
         float* inter = (KIND == 0) ? p.out + (size_t)clip * n_mels * nfr
@@ -237,56 +221,36 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
 
         for (int tile = 0; tile < tiles; ++tile) {
             const int t0 = tile * F;
-            unsigned char* cur_raw = (I16 || buf == 0) ? raw0 : raw1;
-            // (A) this tile's samples have landed
+            const E* const cur = buf ? raw1 : raw0;
+            // (A) this tile's samples have landed (bulk copy) / are visible (plain stores)
             if (inflight) { mbar_wait(s_bar, bar_parity); bar_parity ^= 1; }
-            float* audio;
-            if (I16) {
-                audio = reinterpret_cast<float*>(smem + L.off_audio);
-                if (deferred) {
-                    stage_issue(clip, t0, cur_raw, false);         // generic path: writes s_audio itself
-                } else {
-                    __syncthreads();                               // zero-fill / tail stores visible
-                    // (B) widen int16 -> fp32 once per sample: 4 samples per thread per step
-                    const uint2* r2 = reinterpret_cast<const uint2*>(cur_raw);
-                    float4* a4 = reinterpret_cast<float4*>(audio);
-                    for (int g = tid; g < chunk / 4; g += kThreads) {
-                        const uint2 u = r2[g];
-                        float4 f;
-                        f.x = (float)((int)(u.x << 16) >> 16);      // integer-valued; scaled by the window
-                        f.y = (float)((int)u.x >> 16);
-                        f.z = (float)((int)(u.y << 16) >> 16);
-                        f.w = (float)((int)u.y >> 16);
-                        a4[g] = f;
-                    }
-                }
-            } else {
-                audio = reinterpret_cast<float*>(cur_raw);
-                if (deferred) stage_issue(clip, t0, cur_raw, false);
-            }
-            __syncthreads();                                       // (C) audio ready, raw buffer free
+            __syncthreads();
 
-            // (D) prefetch the next tile (possibly the next clip's first tile)
+            // (D) prefetch the next tile (possibly the next clip's first tile) into the other buffer
             {
                 long long nclip = clip;
                 int nt0 = t0 + F;
                 if (tile + 1 == tiles) { nclip = clip + gridDim.x; nt0 = 0; }
-                inflight = false; deferred = false;
-                if (nclip < p.n_clips) {
-                    unsigned char* nxt = (I16 || buf == 1) ? raw0 : raw1;
-                    if (can_bulk(nclip, nt0)) inflight = stage_issue(nclip, nt0, nxt, true);
-                    else deferred = true;
-                }
+                inflight = (nclip < p.n_clips) ? stage_issue(nclip, nt0, buf ? raw0 : raw1) : false;
                 buf ^= 1;
             }
 
             // (E) two rounds of 16 frames: window, radix-16, exchange, radix-16, mirror, |X|^2
 #pragma unroll 1
             for (int r = 0; r < 2; ++r) {
+                if (t0 + 16 * r + 2 * warp >= nfr) continue;        // both frames past the clip's end
                 const int f = 16 * r + 2 * warp + h;
                 float2 v[16];
-                {
-                    const float* a = audio + f * hop + 2 * j;
+                if constexpr (I16) {
+                    // one 32-bit word = one packed complex point (two int16 samples)
+                    const uint32_t* a = reinterpret_cast<const uint32_t*>(cur) + ((f * hop) >> 1) + j;
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) {
+                        const float2 x = cvt_pcm2(a[16 * t]);
+                        v[t] = make_float2(x.x * win[t].x, x.y * win[t].y);
+                    }
+                } else {
+                    const float* a = cur + f * hop + 2 * j;
 #pragma unroll
                     for (int t = 0; t < 16; ++t) {
                         const float2 x = *reinterpret_cast<const float2*>(a + 32 * t);
@@ -295,11 +259,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                 }
                 Dft<16>::run(v);
 #pragma unroll
-                for (int t = 0; t < 16; ++t) x1[t] = v[t];
+                for (int t = 0; t < 16; t += 2) x1[t >> 1] = make_float4(v[t].x, v[t].y, v[t + 1].x, v[t + 1].y);
                 __syncwarp();
                 v[0] = x2[0];
 #pragma unroll
-                for (int t = 1; t < 16; ++t) v[t] = cmul(x2[17 * t], tw1[t - 1]);
+                for (int t = 1; t < 16; ++t) v[t] = cmul(x2[XS * t], tw1[t - 1]);
                 Dft<16>::run(v);                                   // v[t] = Z[j + 16 t]
                 __syncwarp();
 #pragma unroll
@@ -322,32 +286,27 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
             }
             __syncthreads();                                       // (F) power tile complete
 
-            // (G) mel bands: lane = frame, warp-uniform band; one descriptor, 128-bit broadcast
-            //     weight loads and 64-bit power loads (two adjacent bins); bands are padded to
-            //     whole 8-bin steps with zero weights so the loop has no remainder
+            // (G) mel bands: lane = frame, warp-uniform band; per 4-bin step one 128-bit broadcast
+            //     weight load and two 64-bit power loads (bands padded with zero weights)
             {
                 const int t = t0 + lane;
                 const bool valid = t < nfr;
                 float* const outp = inter + t;
                 const float2* pl = reinterpret_cast<const float2*>(s_pow) + lane;
                 for (int i = warp; i < n_mels; i += kWarps) {
-                    const int4 d = s_desc[i];          // {pair-row offset (float2), n 8-bin steps, weight offset, m*nfr}
+                    const int4 d = s_desc[i];          // {pair-row offset (float2), n 4-bin steps, weight offset, m*nfr}
                     const float2* pr = pl + d.x;
                     const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
                     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    for (int q8 = 0; q8 < d.y; ++q8) {
-                        const float4 w0 = wq[0], w1 = wq[1];
-                        const float2 p0 = pr[0], p1 = pr[PROW / 2], p2 = pr[PROW], p3 = pr[3 * PROW / 2];
-                        a0 = fmaf(w0.x, p0.x, a0);
-                        a1 = fmaf(w0.y, p0.y, a1);
-                        a2 = fmaf(w0.z, p1.x, a2);
-                        a3 = fmaf(w0.w, p1.y, a3);
-                        a0 = fmaf(w1.x, p2.x, a0);
-                        a1 = fmaf(w1.y, p2.y, a1);
-                        a2 = fmaf(w1.z, p3.x, a2);
-                        a3 = fmaf(w1.w, p3.y, a3);
-                        pr += 2 * PROW;
-                        wq += 2;
+#pragma unroll 1
+                    for (int q4 = 0; q4 < d.y; ++q4) {
+                        const float4 w = *wq++;
+                        const float2 p0 = pr[0], p1 = pr[PROW / 2];
+                        a0 = fmaf(w.x, p0.x, a0);
+                        a1 = fmaf(w.y, p0.y, a1);
+                        a2 = fmaf(w.z, p1.x, a2);
+                        a3 = fmaf(w.w, p1.y, a3);
+                        pr += PROW;
                     }
                     const float vv = db10((a0 + a1) + (a2 + a3));
                     if (valid) {
