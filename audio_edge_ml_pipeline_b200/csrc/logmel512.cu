@@ -39,12 +39,13 @@ __device__ __forceinline__ float db10(float s) {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(s, 1e-10f)));
     return 3.01029995663981195f * l;
 }
-// two packed int16 PCM samples -> two integer-valued floats (the 1/32768 rides on the window)
+// two packed int16 PCM samples -> two integer-valued floats (the 1/32768 rides on the window).
+// Sign-extend on the ALU (PRMT / SHF) then I2FP.F32.S32: cvt.f32.s16 (I2F.S16) runs on the
+// quarter-rate XU pipe and cost 4.5x an FADD per instruction in the ncu source view.
 __device__ __forceinline__ float2 cvt_pcm2(uint32_t u) {
-    float lo, hi;
-    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.rn.f32.s16 %0, l;\n\tcvt.rn.f32.s16 %1, h;\n\t}"
-        : "=f"(lo), "=f"(hi) : "r"(u));
-    return make_float2(lo, hi);
+    const int lo = (int)__byte_perm(u, 0u, 0x9910);          // bytes {b0, b1, sign(b1), sign(b1)}
+    const int hi = (int)u >> 16;
+    return make_float2(__int2float_rn(lo), __int2float_rn(hi));
 }
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
