@@ -31,7 +31,7 @@ def _nvcc() -> str:
 
 def _fingerprint() -> str:
     h = hashlib.sha256()
-    for p in sorted(list(CSRC.glob("*")) + [PKG.parent / "include" / "b2a.h", Path(__file__)]):
+    for p in sorted([q for q in CSRC.glob("*") if q.is_file()] + [PKG.parent / "include" / "b2a.h", Path(__file__)]):
         if p.is_file():
             h.update(p.name.encode())
             h.update(p.read_bytes())
@@ -47,6 +47,15 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     objdir = PKG / "build"
     objdir.mkdir(exist_ok=True)
+    # build-time code generation: straight-line mel code for the headline configuration
+    gen = objdir / "gen_mel"
+    subprocess.run(["g++", "-O2", "-std=c++17", str(CSRC / "gen_mel.cpp"), str(CSRC / "tables.cpp"), "-o", str(gen)],
+                   check=True)
+    inc = subprocess.run([str(gen), "16000", "512", "40"], check=True, capture_output=True, text=True).stdout
+    (CSRC / "gen").mkdir(exist_ok=True)
+    tgt = CSRC / "gen" / "mel_special.inc"
+    if not tgt.exists() or tgt.read_text() != inc:
+        tgt.write_text(inc)
     flags = list(NVCC_FLAGS)
     procs = []
     objs = []

@@ -310,6 +310,7 @@ static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, 
     p.n_mfcc = h->cfg.n_mfcc; p.pad_mode = h->cfg.pad_mode; p.top_db = h->cfg.top_db;
     p.mel_wq = h->d_wq; p.mel_k0e = h->d_k0e; p.mel_cnt4 = h->d_cnt4; p.mel_off4 = h->d_off4; p.mel_order = h->d_order;
     p.mel_wpad = h->mel_wpad;
+    p.mel_special = (h->use512 && !h->cfg.reserved[0] && b2a::logmel512_has_special(h->cfg.sample_rate, h->cfg.n_mels)) ? 1 : 0;
     const int grid = (int)std::min<int64_t>(n_clips, h->grid_cap);
     const bool i16 = h->cfg.input_dtype == B2A_IN_I16;
     const int kind = h->cfg.kind == B2A_KIND_MFCC ? 1 : 0;

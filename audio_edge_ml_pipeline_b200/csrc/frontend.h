@@ -23,6 +23,7 @@ struct FrontParams {
     const int* mel_off4;     // per band: float offset into mel_wq (multiple of 4)
     const int* mel_order;    // band processed at position i (position i belongs to warp i % 8)
     int mel_wpad;            // floats in mel_wq
+    int mel_special;         // 1: the generated straight-line mel code matches this configuration
     const float* dct;        // mfcc only: [n_mfcc][n_mels]
     long long n_clips;
     int n_samples, hop, n_frames, n_mels, mel_nnz, n_mfcc, pad_mode;
@@ -36,6 +37,7 @@ cudaError_t launch_front(const FrontParams& p, int log2nc, bool i16, int kind, i
 
 // specialised n_fft = 512 kernel (logmel512.cu); requires an even hop
 size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16);
+bool logmel512_has_special(int sample_rate, int n_mels);
 cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st);
 
 }  // namespace b2a

@@ -17,6 +17,7 @@
 // Reference arithmetic: deep.py:126-134 (mel), :318-328 (mfcc) via librosa 0.11.0.
 #include "frontend.h"
 #include "fft_core.cuh"
+#include "gen/mel_special.inc"   // build-time generated straight-line mel code (gen_mel.cpp)
 
 #include <cstdint>
 #include <type_traits>
@@ -123,7 +124,7 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     return L;
 }
 
-template <bool I16, int KIND>
+template <bool I16, int KIND, bool SPEC>
 __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16);
@@ -294,26 +295,46 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                 const bool valid = t < nfr;
                 float* const outp = inter + t;
                 const float2* pl = reinterpret_cast<const float2*>(s_pow) + lane;
-                for (int i = warp; i < n_mels; i += kWarps) {
-                    const int4 d = s_desc[i];          // {pair-row offset (float2), n 4-bin steps, weight offset, m*nfr}
-                    const float2* pr = pl + d.x;
-                    const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 1
-                    for (int q4 = 0; q4 < d.y; ++q4) {
-                        const float4 w = *wq++;
-                        const float2 p0 = pr[0], p1 = pr[PROW / 2];
-                        a0 = fmaf(w.x, p0.x, a0);
-                        a1 = fmaf(w.y, p0.y, a1);
-                        a2 = fmaf(w.z, p1.x, a2);
-                        a3 = fmaf(w.w, p1.y, a3);
-                        pr += PROW;
+                if constexpr (SPEC) {
+                    // headline configuration: every band unrolled, weights are FFMA immediates
+#define B2A_EMIT(M, VAL)                                                            \
+    {                                                                               \
+        const float vv = db10(VAL);                                                 \
+        if (valid) { outp[(M) * nfr] = vv; vmax = fmaxf(vmax, vv); vmin = fminf(vmin, vv); } \
+    }
+                    switch (warp) {
+                        case 0: B2A_MEL_WARP0(pl, B2A_EMIT) break;
+                        case 1: B2A_MEL_WARP1(pl, B2A_EMIT) break;
+                        case 2: B2A_MEL_WARP2(pl, B2A_EMIT) break;
+                        case 3: B2A_MEL_WARP3(pl, B2A_EMIT) break;
+                        case 4: B2A_MEL_WARP4(pl, B2A_EMIT) break;
+                        case 5: B2A_MEL_WARP5(pl, B2A_EMIT) break;
+                        case 6: B2A_MEL_WARP6(pl, B2A_EMIT) break;
+                        default: B2A_MEL_WARP7(pl, B2A_EMIT) break;
                     }
-                    const float vv = db10((a0 + a1) + (a2 + a3));
-                    if (valid) {
-                        outp[d.w] = vv;
-                        vmax = fmaxf(vmax, vv);
-                        vmin = fminf(vmin, vv);
+#undef B2A_EMIT
+                } else {
+                    for (int i = warp; i < n_mels; i += kWarps) {
+                        const int4 d = s_desc[i];      // {pair-row offset (float2), n 4-bin steps, weight offset, m*nfr}
+                        const float2* pr = pl + d.x;
+                        const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 1
+                        for (int q4 = 0; q4 < d.y; ++q4) {
+                            const float4 w = *wq++;
+                            const float2 p0 = pr[0], p1 = pr[PROW / 2];
+                            a0 = fmaf(w.x, p0.x, a0);
+                            a1 = fmaf(w.y, p0.y, a1);
+                            a2 = fmaf(w.z, p1.x, a2);
+                            a3 = fmaf(w.w, p1.y, a3);
+                            pr += PROW;
+                        }
+                        const float vv = db10((a0 + a1) + (a2 + a3));
+                        if (valid) {
+                            outp[d.w] = vv;
+                            vmax = fmaxf(vmax, vv);
+                            vmin = fminf(vmin, vv);
+                        }
                     }
                 }
             }
@@ -399,19 +420,28 @@ size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16) {
     return (size_t)make_layout(hop, n_mels, mel_wpad, i16).total + 128;
 }
 
-template <bool I16, int KIND>
+bool logmel512_has_special(int sample_rate, int n_mels) {
+    return sample_rate == B2A_MELSPEC_SR && n_mels == B2A_MELSPEC_NMELS && B2A_MELSPEC_NFFT == NFFT;
+}
+
+template <bool I16, int KIND, bool SPEC>
 static cudaError_t launch_k(const FrontParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto k = logmel512_kernel<I16, KIND>;
+    auto k = logmel512_kernel<I16, KIND, SPEC>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, kThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
+template <bool SPEC>
+static cudaError_t launch_s(const FrontParams& p, bool i16, int kind, int grid, size_t smem, cudaStream_t st) {
+    if (kind == 0) return i16 ? launch_k<true, 0, SPEC>(p, grid, smem, st) : launch_k<false, 0, SPEC>(p, grid, smem, st);
+    return i16 ? launch_k<true, 1, SPEC>(p, grid, smem, st) : launch_k<false, 1, SPEC>(p, grid, smem, st);
+}
+
 cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st) {
     const size_t smem = logmel512_smem_bytes(p.hop, p.n_mels, p.mel_wpad, i16);
-    if (kind == 0) return i16 ? launch_k<true, 0>(p, grid, smem, st) : launch_k<false, 0>(p, grid, smem, st);
-    return i16 ? launch_k<true, 1>(p, grid, smem, st) : launch_k<false, 1>(p, grid, smem, st);
+    return p.mel_special ? launch_s<true>(p, i16, kind, grid, smem, st) : launch_s<false>(p, i16, kind, grid, smem, st);
 }
 
 }  // namespace b2a

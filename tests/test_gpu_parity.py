@@ -54,6 +54,8 @@ def test_mel_fsc22_shape_suite(dtype):
     (512, 160, 40, 16000, 16000),
     (1024, 512, 128, 22050, 110250),
     (2048, 512, 128, 22050, 44100),
+    (512, 160, 64, 22050, 33075),       # n_fft 512 kernel, generic (not generated) mel loop
+    (512, 128, 40, 16000, 16000),       # n_fft 512 kernel, generated mel code, other hop
     (512, 161, 40, 16000, 20011),       # odd hop, ragged length
     (1024, 256, 64, 16000, 1024),       # shortest legal clip (== n_fft)
 ])
