@@ -44,7 +44,9 @@ __device__ __forceinline__ float db10(float s) {
 // Sign-extend on the ALU (PRMT / SHF) then I2FP.F32.S32: cvt.f32.s16 (I2F.S16) runs on the
 // quarter-rate XU pipe and cost 4.5x an FADD per instruction in the ncu source view.
 __device__ __forceinline__ float2 cvt_pcm2(uint32_t u) {
-    const int lo = (int)__byte_perm(u, 0u, 0x9910);          // bytes {b0, b1, sign(b1), sign(b1)}
+    int lo;                                                  // bytes {b0, b1, sign(b1), sign(b1)}: selector
+    asm("prmt.b32 %0, %1, 0, 0x9910;" : "=r"(lo) : "r"(u));   // msb = replicate sign (PTX prmt; the
+                                                             // __byte_perm intrinsic ignores that bit)
     const int hi = (int)u >> 16;
     return make_float2(__int2float_rn(lo), __int2float_rn(hi));
 }
