@@ -38,6 +38,20 @@ CLIP_SECONDS = N_SAMPLES / SR
 METRIC = "log-mel clips/sec (5 s @16 kHz, n_fft 512, hop 160, 40 mels)"
 WORKLOAD = "BASELINE config 4: synthetic 5 s 16 kHz int16 clips, device-resident, audio_mel_spec (40,501)"
 
+# Secondary workloads (--extractor mfcc|cqt): BASELINE configs 2 and 3 at throughput scale.  The
+# default (mel) is the headline metric; these fill the other rows of BASELINE.md section 5.
+EXTRA = {
+    "mfcc": dict(kind=1, sr=16000, n=80000, rows=13, hop=160, bytes=80000 * 2 + 13 * 501 * 4,
+                 metric="mfcc_seq clips/sec (5 s @16 kHz, n_fft 512, hop 160, 40 mels -> 13 mfcc)",
+                 workload="BASELINE config 2 at scale: audio_mfcc_seq (13,501), int16, device-resident",
+                 name="audio_mfcc_seq", params=dict(sample_rate=16000, n_mfcc=13, n_fft=512, hop_length=160,
+                                                    duration=5.0, n_mels=40)),
+    "cqt": dict(kind=2, sr=22050, n=110250, rows=84, hop=512, bytes=110250 * 2 + 84 * 216 * 4,
+                metric="cqt clips/sec (5 s @22.05 kHz, hop 512, 84 bins, 12/octave)",
+                workload="BASELINE config 3 at scale: audio_cqt (84,216), int16, device-resident",
+                name="audio_cqt", params=dict(duration=5.0)),
+}
+
 
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
@@ -197,9 +211,19 @@ def run_ours(args):
         build_lib()
     D.barrier()
 
-    cfg = B.default_config(B.KIND_MEL)
-    cfg.n_samples = N_SAMPLES
-    eng = B.Engine(cfg, local)
+    global SR, N_SAMPLES, HOP, N_MELS, N_FRAMES, BYTES_PER_CLIP, CLIP_SECONDS, METRIC, WORKLOAD
+    ext_name, ext_params = "audio_mel_spec", dict(duration=5.0, n_mels=N_MELS, sample_rate=SR, n_fft=N_FFT,
+                                                   hop_length=HOP)
+    kernel_name = "logmel512_kernel<int16, mel, generated-mel>"
+    if args.extractor != "mel":
+        x = EXTRA[args.extractor]
+        SR, N_SAMPLES, HOP, N_MELS = x["sr"], x["n"], x["hop"], x["rows"]
+        N_FRAMES, BYTES_PER_CLIP, CLIP_SECONDS = 1 + N_SAMPLES // HOP, x["bytes"], N_SAMPLES / SR
+        METRIC, WORKLOAD, ext_name, ext_params = x["metric"], x["workload"], x["name"], x["params"]
+        kernel_name = "logmel512_kernel<int16, mfcc>" if args.extractor == "mfcc" else \
+            "cqt_decimate_kernel x6 + cqt_octave_kernel x7 + cqt_finalize_kernel"
+    ext = P.get(ext_name)(**ext_params, devices=[local])
+    eng = ext._engine(N_SAMPLES, np.int16, local)
     assert (eng.rows, eng.frames) == (N_MELS, N_FRAMES)
 
     # ---- resident synthetic batch (white noise sigma 0.1 -> int16), generated on device ------
@@ -255,8 +279,6 @@ def run_ours(args):
     torch.from_numpy(pin_in.array).copy_(d_in[:ne] if ne <= n else d_in[:1].expand(ne, -1))
     torch.cuda.synchronize()
     # the call a user makes: the registered extractor's batch API (-> Engine.run_host -> b2a_run_host)
-    ext = P.get("audio_mel_spec")(duration=CLIP_SECONDS, n_mels=N_MELS, sample_rate=SR, n_fft=N_FFT,
-                                  hop_length=HOP, devices=[local])
     for _ in range(2):
         ext.extract_batch(pin_in.array, pin_out.array)
     fence()
@@ -275,7 +297,7 @@ def run_ours(args):
         peak, peak_src = _peaks()
         total_clips = world * n * args.steps
         value = total_clips / (ms * 1e-3)
-        launch_s = ms * 1e-3 / args.steps                       # one launch per step per GPU
+        launch_s = ms * 1e-3 / args.steps                       # one step per GPU (mel/mfcc: one launch)
         achieved = n * BYTES_PER_CLIP / launch_s / 1e9           # per GPU
         traffic = _ncu_traffic()
         line = {
@@ -289,24 +311,23 @@ def run_ours(args):
             "audio_seconds_per_s": value * CLIP_SECONDS,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "peak_source": peak_src,
-                         "bytes_per_clip": BYTES_PER_CLIP, "kernel": "front_kernel<8,true,0>",
-                         "traffic": (traffic["dram_bytes_per_clip"] * n) if traffic else None,
+                         "bytes_per_clip": BYTES_PER_CLIP, "kernel": kernel_name,
+                         "traffic": (traffic["dram_bytes_per_clip"] * n) if (traffic and args.extractor == "mel") else None,
                          "traffic_note": (traffic or {}).get("note") if traffic else "no ncu capture committed yet",
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": ne * N_SAMPLES * 2,
                     "d2h_bytes_per_step": ne * N_MELS * N_FRAMES * 4, "clips_per_step": ne,
-                    "steps": e2e_steps, "api": "get('audio_mel_spec')(...).extract_batch -> b2a_run_host (pinned host buffers)",
+                    "steps": e2e_steps, "api": f"get('{ext_name}')(...).extract_batch -> b2a_run_host (pinned host buffers)",
                     "checksum": checksum},
             "gpu_launches": launches,
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu:
+        if world == 1 and not args.no_cpu and args.extractor == "mel":
             line["cpu_baseline"] = cpu_baseline_serial(args.cpu_clips)
         print(json.dumps(line), flush=True)
-    ext.close()
     pin_in.close()
     pin_out.close()
-    eng.close()
+    ext.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -323,6 +344,8 @@ def main():
     ap.add_argument("--e2e-clips", type=int, default=16384, help="clips per end-to-end step (host buffers)")
     ap.add_argument("--cpu-clips", type=int, default=6000, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--extractor", default="mel", choices=["mel", "mfcc", "cqt"],
+                    help="mel = the headline metric; mfcc / cqt = BASELINE configs 2 / 3 at scale")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
