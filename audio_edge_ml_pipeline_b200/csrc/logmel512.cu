@@ -101,44 +101,6 @@ __device__ __forceinline__ E raw_sample(const E* clip, int s, int n, int pad_mod
     return clip[s];
 }
 
-struct StageArgs {
-    const void* clips; uint64_t* bar; int n, hop, chunk, pad_mode, base_aligned;
-};
-
-// Stage tile (clip, t0) into dst.  Aligned zero-padded clips go by one TMA bulk copy (returns
-// true: completion arrives on the mbarrier) with the clip's head/tail zero-filled by plain stores;
-// reflect padding or unaligned clips use plain loads.  Every thread computes the same answer.
-// Kept out of line: it runs once per 32-frame tile and would otherwise be inlined twice.
-template <typename E>
-__device__ __noinline__ bool stage_tile(const StageArgs a, long long clip, int t0, E* dst) {
-    constexpr int V = 16 / (int)sizeof(E);                   // samples per 16 bytes
-    const int tid = threadIdx.x, n = a.n, chunk = a.chunk;
-    const long long e0 = clip * (long long)n;
-    const E* cptr = reinterpret_cast<const E*>(a.clips) + e0;
-    const int c0 = t0 * a.hop - NFFT / 2;
-    const int lo = c0 < 0 ? 0 : c0;
-    const int hi = (c0 + chunk < n) ? c0 + chunk : n;
-    const bool ok = a.pad_mode == 0 && a.base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
-                    (((lo - c0) & (V - 1)) == 0);
-    if (!ok) {
-#pragma unroll 1
-        for (int i = tid; i < chunk; i += kThreads) dst[i] = raw_sample<E>(cptr, c0 + i, n, a.pad_mode);
-        return false;
-    }
-    const int nb = ((hi - lo) / V) * V;                      // bulk part, whole 16-byte units
-    const int head = lo - c0;                                // [0, head) and [head+nb, chunk) are not
-#pragma unroll 1
-    for (int i = tid; i < head; i += kThreads) dst[i] = (E)0;                 // written by the bulk copy
-#pragma unroll 1
-    for (int i = head + nb + tid; i < chunk; i += kThreads) dst[i] = raw_sample<E>(cptr, c0 + i, n, 0);
-    if (tid == 0 && nb > 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic reads -> async write
-        mbar_expect_tx(a.bar, (uint32_t)(nb * sizeof(E)));
-        bulk_g2s(dst + head, cptr + lo, (uint32_t)(nb * sizeof(E)), a.bar);
-    }
-    return nb > 0;
-}
-
 struct Layout {
     int chunk;          // samples staged per tile, multiple of 8
     int off_raw, off_raw2, off_audio, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, total;
@@ -217,17 +179,44 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     __syncthreads();
 
     using E = typename std::conditional<I16, int16_t, float>::type;
+    constexpr int V = 16 / (int)sizeof(E);                   // samples per 16 bytes
     const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
     uint32_t bar_parity = 0;
     int buf = 0;                                             // which raw buffer holds the current tile
 
-    const StageArgs sa{p.clips, s_bar, n, hop, chunk, p.pad_mode, base_aligned ? 1 : 0};
+    // Stage tile (clip, t0) into dst.  Aligned zero-padded clips go by one TMA bulk copy (returns
+    // true: completion arrives on s_bar) with the clip's head/tail zero-filled by plain stores;
+    // reflect padding or unaligned clips use plain loads.  Every thread computes the same answer.
+    auto stage_issue = [&](long long clip, int t0, E* dst) -> bool {
+        const long long e0 = clip * (long long)n;
+        const E* cptr = reinterpret_cast<const E*>(p.clips) + e0;
+        const int c0 = t0 * hop - NFFT / 2;
+        const int lo = c0 < 0 ? 0 : c0;
+        const int hi = (c0 + chunk < n) ? c0 + chunk : n;
+        const bool ok = p.pad_mode == 0 && base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
+                        (((lo - c0) & (V - 1)) == 0);
+        if (!ok) {
+            for (int i = tid; i < chunk; i += kThreads) dst[i] = raw_sample<E>(cptr, c0 + i, n, p.pad_mode);
+            return false;
+        }
+        const int nb = ((hi - lo) / V) * V;                  // bulk part, whole 16-byte units
+        const int head = lo - c0;                            // [0, head) and [head+nb, chunk) are not
+        for (int i = tid; i < head; i += kThreads) dst[i] = (E)0;                 // written by the bulk copy
+        for (int i = head + nb + tid; i < chunk; i += kThreads) dst[i] = raw_sample<E>(cptr, c0 + i, n, 0);
+        if (tid == 0 && nb > 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic reads -> async write
+            mbar_expect_tx(s_bar, (uint32_t)(nb * sizeof(E)));
+            bulk_g2s(dst + head, cptr + lo, (uint32_t)(nb * sizeof(E)), s_bar);
+        }
+        return nb > 0;
+    };
+
     const int tiles = (nfr + F - 1) / F;
     long long clip = blockIdx.x;
     if (clip >= p.n_clips) return;
     E* const raw0 = reinterpret_cast<E*>(smem + L.off_raw);
     E* const raw1 = reinterpret_cast<E*>(smem + L.off_raw2);
-    bool inflight = stage_tile<E>(sa, clip, 0, raw0);            // prologue: first tile of the first clip
+    bool inflight = stage_issue(clip, 0, raw0);            // prologue: first tile of the first clip
 
     for (; clip < p.n_clips; clip += gridDim.x) {
         float* inter = (KIND == 0) ? p.out + (size_t)clip * n_mels * nfr
@@ -246,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                 long long nclip = clip;
                 int nt0 = t0 + F;
                 if (tile + 1 == tiles) { nclip = clip + gridDim.x; nt0 = 0; }
-                inflight = (nclip < p.n_clips) ? stage_tile<E>(sa, nclip, nt0, buf ? raw0 : raw1) : false;
+                inflight = (nclip < p.n_clips) ? stage_issue(nclip, nt0, buf ? raw0 : raw1) : false;
                 buf ^= 1;
             }
 
@@ -376,18 +365,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
             const int total = n_mels * nfr;
             if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(inter) & 15) == 0)) {
                 float4* o4 = reinterpret_cast<float4*>(inter);
-                const int n4 = total / 4;
-                for (int i0 = tid; i0 < n4; i0 += 4 * kThreads) {     // 4 independent L2 loads in flight
-                    float4 x[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (i0 + u * kThreads < n4) x[u] = o4[i0 + u * kThreads];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (i0 + u * kThreads < n4) {
-                            x[u].x = nrm(x[u].x); x[u].y = nrm(x[u].y); x[u].z = nrm(x[u].z); x[u].w = nrm(x[u].w);
-                            o4[i0 + u * kThreads] = x[u];
-                        }
+                for (int i = tid; i < total / 4; i += kThreads) {
+                    float4 x = o4[i];
+                    x.x = nrm(x.x);
+                    x.y = nrm(x.y);
+                    x.z = nrm(x.z);
+                    x.w = nrm(x.w);
+                    o4[i] = x;
                 }
             } else {
                 for (int i = tid; i < total; i += kThreads)
