@@ -34,6 +34,7 @@ from .registry import register
 logger = logging.getLogger(__name__)
 
 HOST_BATCH_CLIPS = 4096          # clips decoded and shipped per GPU round in extract_dataset
+DECODE_WORKERS = min(16, os.cpu_count() or 1)   # file reads release the GIL; order is preserved
 
 
 def _make_engine(cfg: B.B2AConfig, device: int):
@@ -199,16 +200,34 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
                     labels.append(label_to_idx[label])
             pending.clear()
 
-        for i, (sample_path, label, meta) in enumerate(loader):
-            if max_samples is not None and i >= max_samples:
-                break
+        def decode(item):
+            sample_path, _label, meta = item
             try:
-                audio = self._prepare(sample_path, meta.get("start_time"), meta.get("end_time"))
-            except Exception as exc:  # noqa: BLE001
-                logger.warning("Skipping %s: %s", sample_path, exc)
-                continue
-            pending.append((audio, label, meta, sample_path))
-            if len(pending) >= HOST_BATCH_CLIPS:
+                return self._prepare(sample_path, meta.get("start_time"), meta.get("end_time"))
+            except Exception as exc:  # noqa: BLE001 — reference semantics: warn and skip (base.py:204-206)
+                return exc
+
+        def window():
+            buf = []
+            for i, item in enumerate(loader):
+                if max_samples is not None and i >= max_samples:
+                    break
+                buf.append(item)
+                if len(buf) >= HOST_BATCH_CLIPS:
+                    yield buf
+                    buf = []
+            if buf:
+                yield buf
+
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=DECODE_WORKERS) as pool:
+            for items in window():
+                decoded = list(pool.map(decode, items)) if DECODE_WORKERS > 1 else [decode(it) for it in items]
+                for (sample_path, label, meta), audio in zip(items, decoded):
+                    if isinstance(audio, Exception):
+                        logger.warning("Skipping %s: %s", sample_path, audio)
+                        continue
+                    pending.append((audio, label, meta, sample_path))
                 flush()
         flush()
         return assemble_feature_set(self, feats, labels, metas, label_to_idx)

@@ -1,0 +1,86 @@
+#!/usr/bin/env python
+"""End-to-end Stage-2 run (BASELINE config 5): an fsc22-shaped, augmentation-expanded set of
+PCM16 WAV files -> loader scan -> decode -> pinned H2D -> log-mel on every visible GPU -> D2H ->
+features.npy, through the reference-facing API (registered extractor + FeaturePipeline).
+
+    python bench_stage2.py [--classes 27 --per-class 260] [--devices all] [--dir /dev/shm/b2a_stage2]
+
+27 x 260 = 7020 clips = the reference's train split (52/class) x (1 + n_augments=4)
+(config/augmentation.yaml:18-19,25).  The WAVs are synthetic (the reference ships no audio).
+Prints one JSON line; host-bound by design (decode + np.save), reported beside the kernel bench.
+"""
+import argparse
+import json
+import os
+import shutil
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--classes", type=int, default=27)
+    ap.add_argument("--per-class", type=int, default=260)
+    ap.add_argument("--devices", default="all")
+    ap.add_argument("--dir", default="/dev/shm/b2a_stage2")
+    ap.add_argument("--repeat", type=int, default=3)
+    args = ap.parse_args()
+
+    import audio_edge_ml_pipeline_b200 as P
+    from audio_edge_ml_pipeline_b200 import _lib as B
+    from audio_edge_ml_pipeline_b200 import synth, wavio
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+
+    root = Path(args.dir)
+    if root.exists():
+        shutil.rmtree(root)
+    ds = root / "fsc22_device_augmented"
+    rng = np.random.default_rng(2026)
+    pool = [synth.pad_or_trim_pcm(synth.to_pcm16(synth.make_clip(rng, k % 5, 16000, 80000)), 80000) for k in range(40)]
+    t0 = time.perf_counter()
+    n = 0
+    for c in range(args.classes):
+        d = ds / f"class_{c:02d}"
+        d.mkdir(parents=True)
+        for i in range(args.per_class):
+            wavio.write_wav_pcm16(d / f"clip_{i:04d}.wav", np.roll(pool[(c + i) % len(pool)], 37 * i), 16000)
+            n += 1
+    gen_s = time.perf_counter() - t0
+
+    ext = P.get("audio_mel_spec")(duration=5.0, n_mels=40, sample_rate=16000, n_fft=512, hop_length=160,
+                                  devices=args.devices)
+    n_dev = len(ext.devices)
+    times = []
+    for r in range(args.repeat + 1):            # first pass = warm-up (engine creation, page cache)
+        t0 = time.perf_counter()
+        loader = AudioFolderLoader(ds)
+        t1 = time.perf_counter()
+        fs = P.FeaturePipeline(loader, ext).run()
+        t2 = time.perf_counter()
+        P.FeaturePipeline.save(fs, root / "out")
+        t3 = time.perf_counter()
+        times.append((t1 - t0, t2 - t1, t3 - t2, t3 - t0))
+    best = min(times[1:], key=lambda x: x[3])
+    assert fs.features.shape == (n, 40, 501)
+    line = {
+        "metric": "Stage-2 end-to-end clips/sec (WAV files -> features.npy), audio_mel_spec",
+        "value": n / best[3], "unit": "clips/s", "n_gpus": n_dev, "clips": n,
+        "seconds": {"loader_scan": best[0], "decode+h2d+kernel+d2h": best[1], "np.save": best[2], "total": best[3]},
+        "extract_only_clips_per_s": n / best[1], "features_bytes": int(fs.features.nbytes),
+        "decode_workers": P.extractors.DECODE_WORKERS, "host_cores": os.cpu_count(),
+        "dataset": f"{args.classes} classes x {args.per_class} PCM16 5 s 16 kHz WAVs on {root}",
+        "dataset_write_s": gen_s, "device_count_visible": B.device_count(),
+    }
+    print(json.dumps(line), flush=True)
+    ext.close()
+    shutil.rmtree(root, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()
