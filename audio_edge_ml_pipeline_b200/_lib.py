@@ -23,7 +23,7 @@ TABLE_WINDOW, TABLE_MEL_DENSE, TABLE_DCT, TABLE_DECIM_TAPS, TABLE_CQT_LENGTHS, T
 
 EXPORTED_SYMBOLS = [
     "b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
-    "b2a_run_host", "b2a_last_launch_count", "b2a_alloc_pinned", "b2a_free_pinned",
+    "b2a_run_host", "b2a_run_host_ragged", "b2a_run_device_ragged", "b2a_last_launch_count", "b2a_alloc_pinned", "b2a_free_pinned",
     "b2a_get_table", "b2a_cqt_geometry", "b2a_last_error", "b2a_abi_version", "b2a_device_count",
 ]
 
@@ -64,6 +64,8 @@ def load_library() -> C.CDLL:
     lib.b2a_out_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     lib.b2a_run_device.argtypes = [vp, vp, i64, vp, vp]
     lib.b2a_run_host.argtypes = [vp, vp, i64, vp]
+    lib.b2a_run_host_ragged.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, i64]
+    lib.b2a_run_device_ragged.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
     lib.b2a_last_launch_count.argtypes = [vp]
     lib.b2a_last_launch_count.restype = i64
     lib.b2a_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -72,7 +74,7 @@ def load_library() -> C.CDLL:
     lib.b2a_cqt_geometry.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp]
     lib.b2a_last_error.restype = C.c_char_p
     for name in ("b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
-                 "b2a_run_host", "b2a_alloc_pinned", "b2a_free_pinned", "b2a_get_table",
+                 "b2a_run_host", "b2a_run_host_ragged", "b2a_run_device_ragged", "b2a_alloc_pinned", "b2a_free_pinned", "b2a_get_table",
                  "b2a_cqt_geometry", "b2a_abi_version", "b2a_device_count"):
         getattr(lib, name).restype = C.c_int
     _lib = lib
@@ -166,6 +168,29 @@ class Engine:
             raise ValueError("out must be C-contiguous float32 (N, rows, frames)")
         _check(self._lib.b2a_run_host(self._h, clips.ctypes.data, n, out.ctypes.data))
         return out
+
+    def run_host_ragged(self, clips: list) -> list:
+        """Variable-length clips (each 1-D, dtype = the engine's input dtype, n_fft <= len <=
+        cfg.n_samples) -> list of (rows, 1 + len // hop) float32 arrays, one launch."""
+        n = len(clips)
+        if n == 0:
+            return []
+        lens = np.array([len(c) for c in clips], dtype=np.int32)
+        starts = np.zeros(n, dtype=np.int64)
+        pos = 0
+        for i, L in enumerate(lens):            # 8-element alignment keeps the TMA staging path
+            starts[i] = pos
+            pos += (int(L) + 7) & ~7
+        packed = np.zeros(pos, dtype=self.in_dtype)
+        for c, s, L in zip(clips, starts, lens):
+            packed[s:s + L] = c
+        frames = 1 + lens // self.cfg.hop_length
+        sizes = self.rows * frames.astype(np.int64)
+        ooff = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+        out = np.empty(int(sizes.sum()), dtype=np.float32)
+        _check(self._lib.b2a_run_host_ragged(self._h, packed.ctypes.data, packed.size, starts.ctypes.data,
+                                             lens.ctypes.data, ooff.ctypes.data, n, out.ctypes.data, out.size))
+        return [out[o:o + sz].reshape(self.rows, f) for o, sz, f in zip(ooff, sizes, frames)]
 
     def run_device(self, d_clips: int, n_clips: int, d_out: int, stream: int = 0) -> None:
         """Raw device pointers (e.g. torch ``tensor.data_ptr()``); asynchronous on ``stream``."""

@@ -292,7 +292,8 @@ int b2a_out_shape(const b2a_handle* h, int32_t* rows, int32_t* frames) {
 int64_t b2a_last_launch_count(const b2a_handle* h) { return h ? h->last_launches : 0; }
 
 static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, float* d_out,
-                           cudaStream_t st, int64_t* launches) {
+                           cudaStream_t st, int64_t* launches, const long long* rag_in = nullptr,
+                           const int* rag_len = nullptr, const long long* rag_out = nullptr) {
     if (n_clips == 0) return B2A_OK;
     if (h->cfg.kind == B2A_KIND_CQT) {
         std::string cerr;
@@ -305,6 +306,7 @@ static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, 
     p.window = h->d_window; p.tw = h->d_tw; p.tw2 = h->d_tw2;
     p.mel_k0 = h->d_k0; p.mel_cnt = h->d_cnt; p.mel_off = h->d_off; p.mel_w = h->d_w;
     p.dct = h->d_dct;
+    p.rag_in_off = rag_in; p.rag_len = rag_len; p.rag_out_off = rag_out;
     p.n_clips = n_clips; p.n_samples = h->cfg.n_samples; p.hop = h->cfg.hop_length;
     p.n_frames = h->frames; p.n_mels = h->cfg.n_mels; p.mel_nnz = (int)h->mel.w.size();
     p.n_mfcc = h->cfg.n_mfcc; p.pad_mode = h->cfg.pad_mode; p.top_db = h->cfg.top_db;
@@ -368,6 +370,71 @@ int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out) 
     CU_TRY(e0);
     CU_TRY(e1);
     return B2A_OK;
+}
+
+int b2a_run_device_ragged(b2a_handle* h, const void* d_clips, const int64_t* d_in_offsets,
+                          const int32_t* d_lengths, const int64_t* d_out_offsets, int64_t n_clips,
+                          float* d_out, void* stream) {
+    if (!h) return fail(B2A_EINVAL, "handle is NULL");
+    if (h->cfg.kind == B2A_KIND_CQT) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
+    if (n_clips < 0) return fail(B2A_EINVAL, "n_clips < 0");
+    if (n_clips > 0 && (!d_clips || !d_out || !d_in_offsets || !d_lengths || !d_out_offsets))
+        return fail(B2A_EINVAL, "NULL buffer");
+    CU_TRY(cudaSetDevice(h->device));
+    h->last_launches = 0;
+    static_assert(sizeof(long long) == sizeof(int64_t), "offset type");
+    return run_device_impl(h, d_clips, n_clips, d_out, (cudaStream_t)stream, &h->last_launches,
+                           (const long long*)d_in_offsets, (const int*)d_lengths, (const long long*)d_out_offsets);
+}
+
+int b2a_run_host_ragged(b2a_handle* h, const void* clips, int64_t total_in, const int64_t* in_offsets,
+                        const int32_t* lengths, const int64_t* out_offsets, int64_t n_clips,
+                        float* out, int64_t total_out) {
+    if (!h) return fail(B2A_EINVAL, "handle is NULL");
+    if (h->cfg.kind == B2A_KIND_CQT) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
+    if (n_clips < 0 || total_in < 0 || total_out < 0) return fail(B2A_EINVAL, "negative size");
+    if (n_clips == 0) { h->last_launches = 0; return B2A_OK; }
+    if (!clips || !out || !in_offsets || !lengths || !out_offsets) return fail(B2A_EINVAL, "NULL buffer");
+    const int hop = h->cfg.hop_length;
+    for (int64_t i = 0; i < n_clips; ++i) {
+        const int64_t L = lengths[i];
+        if (L < h->cfg.n_fft || L > h->cfg.n_samples) return fail(B2A_EINVAL, "clip length outside [n_fft, cfg.n_samples]");
+        if (in_offsets[i] < 0 || in_offsets[i] + L > total_in) return fail(B2A_EINVAL, "input offset out of range");
+        const int64_t need = (int64_t)h->rows * (1 + L / hop);
+        if (out_offsets[i] < 0 || out_offsets[i] + need > total_out) return fail(B2A_EINVAL, "output offset out of range");
+    }
+    CU_TRY(cudaSetDevice(h->device));
+    void* d_in = nullptr; float* d_out = nullptr; long long* d_io = nullptr; long long* d_oo = nullptr; int* d_len = nullptr;
+    int rc = B2A_OK;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(d_io); cudaFree(d_oo); cudaFree(d_len); };
+#define CU_TRY_R(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            cleanup();                                                                     \
+            return fail(e__ == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA,         \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));              \
+        }                                                                                  \
+    } while (0)
+    CU_TRY_R(cudaMalloc(&d_in, (size_t)total_in * h->in_elem));
+    CU_TRY_R(cudaMalloc((void**)&d_out, (size_t)total_out * sizeof(float)));
+    CU_TRY_R(cudaMalloc((void**)&d_io, (size_t)n_clips * 8));
+    CU_TRY_R(cudaMalloc((void**)&d_oo, (size_t)n_clips * 8));
+    CU_TRY_R(cudaMalloc((void**)&d_len, (size_t)n_clips * 4));
+    CU_TRY_R(cudaMemcpyAsync(d_in, clips, (size_t)total_in * h->in_elem, cudaMemcpyHostToDevice, st));
+    CU_TRY_R(cudaMemcpyAsync(d_io, in_offsets, (size_t)n_clips * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY_R(cudaMemcpyAsync(d_oo, out_offsets, (size_t)n_clips * 8, cudaMemcpyHostToDevice, st));
+    CU_TRY_R(cudaMemcpyAsync(d_len, lengths, (size_t)n_clips * 4, cudaMemcpyHostToDevice, st));
+    h->last_launches = 0;
+    rc = run_device_impl(h, d_in, n_clips, d_out, st, &h->last_launches, d_io, d_len, d_oo);
+    if (rc == B2A_OK) {
+        CU_TRY_R(cudaMemcpyAsync(out, d_out, (size_t)total_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CU_TRY_R(cudaStreamSynchronize(st));
+    }
+    cleanup();
+    return rc;
+#undef CU_TRY_R
 }
 
 int b2a_alloc_pinned(size_t bytes, void** out) {

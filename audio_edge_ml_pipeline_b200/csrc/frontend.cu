@@ -116,7 +116,7 @@ size_t front_smem_bytes(int log2nc, int hop, int n_mels, int mel_nnz) {
     return b + 64;
 }
 
-template <int LOG2NC, bool I16, int KIND>
+template <int LOG2NC, bool I16, int KIND, bool RAG>
 __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel(FrontParams p) {
     using G = FftGeom<LOG2NC>;
     using C = FrontCfg<LOG2NC>;
@@ -164,16 +164,19 @@ __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel
     }
     __syncthreads();
 
-    const int n = p.n_samples, nfr = p.n_frames, n_mels = p.n_mels;
+    int n = p.n_samples, nfr = p.n_frames;                  // per clip when RAG
+    const int n_mels = p.n_mels;
     const bool hop_even = (p.hop & 1) == 0;
     const size_t esz = I16 ? 2 : 4;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
 
     for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
-        const long long clip_elem0 = clip * (long long)n;
+        if constexpr (RAG) { n = p.rag_len[clip]; nfr = 1 + n / p.hop; }
+        const long long clip_elem0 = RAG ? p.rag_in_off[clip] : clip * (long long)n;
         const void* cptr = (const unsigned char*)p.clips + (size_t)clip_elem0 * esz;
-        float* inter = (KIND == 0) ? p.out + (size_t)clip * n_mels * nfr
-                                   : p.inter + (size_t)blockIdx.x * n_mels * nfr;
+        float* const outb = RAG ? p.out + p.rag_out_off[clip]
+                                : p.out + (size_t)clip * (KIND == 0 ? n_mels : p.n_mfcc) * nfr;
+        float* inter = (KIND == 0) ? outb : p.inter + (size_t)blockIdx.x * n_mels * p.n_frames;
         float vmax = -3.0e38f, vmin = 3.0e38f;
 
         for (int t0 = 0; t0 < nfr; t0 += F) {
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel
         } else {
             // librosa.feature.mfcc: power_to_db(ref=1.0, top_db) -> DCT-II ortho -> rows [0, n_mfcc)
             // then deep.py:326-328 per-row z-score.
-            float* outc = p.out + (size_t)clip * p.n_mfcc * nfr;
+            float* outc = outb;
             const float thr = vmax - p.top_db;
             float* s_l = s_pow;                       // [n_mels][32] tile of clipped dB
             for (int t0 = 0; t0 < nfr; t0 += 32) {
@@ -319,19 +322,25 @@ __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel
     }
 }
 
-template <int LOG2NC, bool I16, int KIND>
+template <int LOG2NC, bool I16, int KIND, bool RAG>
 static cudaError_t launch_one(const FrontParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto k = front_kernel<LOG2NC, I16, KIND>;
+    auto k = front_kernel<LOG2NC, I16, KIND, RAG>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, kThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
+template <int LOG2NC, bool RAG>
+static cudaError_t launch_r(const FrontParams& p, bool i16, int kind, int grid, size_t smem, cudaStream_t st) {
+    if (kind == 0) return i16 ? launch_one<LOG2NC, true, 0, RAG>(p, grid, smem, st) : launch_one<LOG2NC, false, 0, RAG>(p, grid, smem, st);
+    return i16 ? launch_one<LOG2NC, true, 1, RAG>(p, grid, smem, st) : launch_one<LOG2NC, false, 1, RAG>(p, grid, smem, st);
+}
+
 template <int LOG2NC>
 static cudaError_t launch_l(const FrontParams& p, bool i16, int kind, int grid, size_t smem, cudaStream_t st) {
-    if (kind == 0) return i16 ? launch_one<LOG2NC, true, 0>(p, grid, smem, st) : launch_one<LOG2NC, false, 0>(p, grid, smem, st);
-    return i16 ? launch_one<LOG2NC, true, 1>(p, grid, smem, st) : launch_one<LOG2NC, false, 1>(p, grid, smem, st);
+    return p.rag_len ? launch_r<LOG2NC, true>(p, i16, kind, grid, smem, st)
+                     : launch_r<LOG2NC, false>(p, i16, kind, grid, smem, st);
 }
 
 int front_ctas_per_sm(int log2nc) { return log2nc <= 8 ? 2 : 1; }

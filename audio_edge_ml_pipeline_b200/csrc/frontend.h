@@ -25,6 +25,11 @@ struct FrontParams {
     int mel_wpad;            // floats in mel_wq
     int mel_special;         // 1: the generated straight-line mel code matches this configuration
     const float* dct;        // mfcc only: [n_mfcc][n_mels]
+    // ragged batches (NULL for fixed-length): per-clip element offset into clips, length in samples,
+    // float offset into out; n_samples/n_frames then hold the MAXIMA (scratch sizing)
+    const long long* rag_in_off;
+    const int* rag_len;
+    const long long* rag_out_off;
     long long n_clips;
     int n_samples, hop, n_frames, n_mels, mel_nnz, n_mfcc, pad_mode;
     float top_db;

@@ -126,7 +126,7 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     return L;
 }
 
-template <bool I16, int KIND, bool SPEC>
+template <bool I16, int KIND, bool SPEC, bool RAG>
 __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16);
@@ -140,7 +140,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j = lane & 15, h = lane >> 4;
-    const int hop = p.hop, n = p.n_samples, nfr = p.n_frames, n_mels = p.n_mels, chunk = L.chunk;
+    const int hop = p.hop, n_mels = p.n_mels, chunk = L.chunk;
+    int n = p.n_samples, nfr = p.n_frames;                   // per clip when RAG
 
     // ---- per-CTA tables --------------------------------------------------------------------
     for (int i = tid; i < 128; i += kThreads) {          // s_tw2[r][j] = exp(-i pi (j+16r)/256)
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     for (int i = tid; i < p.mel_wpad; i += kThreads) s_melw[i] = p.mel_wq[i];
     for (int i = tid; i < n_mels; i += kThreads) {
         const int m = p.mel_order[i];                        // position i is served by warp i % 8
-        s_desc[i] = make_int4((p.mel_k0e[m] >> 1) * (PROW / 2), p.mel_cnt4[m], p.mel_off4[m], m * nfr);
+        s_desc[i] = make_int4((p.mel_k0e[m] >> 1) * (PROW / 2), p.mel_cnt4[m], p.mel_off4[m], m);
     }
     for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // bins 256..263
     if (tid == 0) {
@@ -188,7 +189,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     // true: completion arrives on s_bar) with the clip's head/tail zero-filled by plain stores;
     // reflect padding or unaligned clips use plain loads.  Every thread computes the same answer.
     auto stage_issue = [&](long long clip, int t0, E* dst) -> bool {
-        const long long e0 = clip * (long long)n;
+        const int n = RAG ? p.rag_len[clip] : p.n_samples;
+        const long long e0 = RAG ? p.rag_in_off[clip] : clip * (long long)n;
         const E* cptr = reinterpret_cast<const E*>(p.clips) + e0;
         const int c0 = t0 * hop - NFFT / 2;
         const int lo = c0 < 0 ? 0 : c0;
@@ -211,7 +213,6 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
         return nb > 0;
     };
 
-    const int tiles = (nfr + F - 1) / F;
     long long clip = blockIdx.x;
     if (clip >= p.n_clips) return;
     E* const raw0 = reinterpret_cast<E*>(smem + L.off_raw);
@@ -219,8 +220,11 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     bool inflight = stage_issue(clip, 0, raw0);            // prologue: first tile of the first clip
 
     for (; clip < p.n_clips; clip += gridDim.x) {
-        float* inter = (KIND == 0) ? p.out + (size_t)clip * n_mels * nfr
-                                   : p.inter + (size_t)blockIdx.x * n_mels * nfr;
+        if constexpr (RAG) { n = p.rag_len[clip]; nfr = 1 + n / hop; }
+        const int tiles = (nfr + F - 1) / F;
+        float* const outb = RAG ? p.out + p.rag_out_off[clip]
+                                : p.out + (size_t)clip * (KIND == 0 ? n_mels : p.n_mfcc) * nfr;
+        float* inter = (KIND == 0) ? outb : p.inter + (size_t)blockIdx.x * n_mels * p.n_frames;
         float vmax = -3.0e38f, vmin = 3.0e38f;
 
         for (int tile = 0; tile < tiles; ++tile) {
@@ -333,7 +337,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                         }
                         const float vv = db10((a0 + a1) + (a2 + a3));
                         if (valid) {
-                            outp[d.w] = vv;
+                            outp[d.w * nfr] = vv;
                             vmax = fmaxf(vmax, vv);
                             vmin = fminf(vmin, vv);
                         }
@@ -378,7 +382,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                     inter[i] = nrm(inter[i]);
             }
         } else {
-            float* outc = p.out + (size_t)clip * p.n_mfcc * nfr;
+            float* outc = outb;
             const float thr = vmax - p.top_db;
             float* s_l = s_pow;                                   // [n_mels][32] clipped dB tile
             for (int t0 = 0; t0 < nfr; t0 += 32) {
@@ -426,24 +430,27 @@ bool logmel512_has_special(int sample_rate, int n_mels) {
     return sample_rate == B2A_MELSPEC_SR && n_mels == B2A_MELSPEC_NMELS && B2A_MELSPEC_NFFT == NFFT;
 }
 
-template <bool I16, int KIND, bool SPEC>
+template <bool I16, int KIND, bool SPEC, bool RAG>
 static cudaError_t launch_k(const FrontParams& p, int grid, size_t smem, cudaStream_t st) {
-    auto k = logmel512_kernel<I16, KIND, SPEC>;
+    auto k = logmel512_kernel<I16, KIND, SPEC, RAG>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<grid, kThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
 
-template <bool SPEC>
+template <bool SPEC, bool RAG>
 static cudaError_t launch_s(const FrontParams& p, bool i16, int kind, int grid, size_t smem, cudaStream_t st) {
-    if (kind == 0) return i16 ? launch_k<true, 0, SPEC>(p, grid, smem, st) : launch_k<false, 0, SPEC>(p, grid, smem, st);
-    return i16 ? launch_k<true, 1, SPEC>(p, grid, smem, st) : launch_k<false, 1, SPEC>(p, grid, smem, st);
+    if (kind == 0) return i16 ? launch_k<true, 0, SPEC, RAG>(p, grid, smem, st) : launch_k<false, 0, SPEC, RAG>(p, grid, smem, st);
+    return i16 ? launch_k<true, 1, SPEC, RAG>(p, grid, smem, st) : launch_k<false, 1, SPEC, RAG>(p, grid, smem, st);
 }
 
 cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st) {
     const size_t smem = logmel512_smem_bytes(p.hop, p.n_mels, p.mel_wpad, i16);
-    return p.mel_special ? launch_s<true>(p, i16, kind, grid, smem, st) : launch_s<false>(p, i16, kind, grid, smem, st);
+    if (p.rag_len) return p.mel_special ? launch_s<true, true>(p, i16, kind, grid, smem, st)
+                                        : launch_s<false, true>(p, i16, kind, grid, smem, st);
+    return p.mel_special ? launch_s<true, false>(p, i16, kind, grid, smem, st)
+                         : launch_s<false, false>(p, i16, kind, grid, smem, st);
 }
 
 }  // namespace b2a

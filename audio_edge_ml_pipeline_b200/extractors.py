@@ -200,17 +200,25 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
                 return self.extract_batch(a_in[:len(idxs)], a_out[:len(idxs)]).copy()
             return self.extract_batch(np.stack([pending[i][0] for i in idxs]))
 
+        ragged = self.duration is None and self._kind != B.KIND_CQT
+
+        def run_ragged(idxs):
+            """duration=None: clips keep their own lengths; one ragged launch per dtype."""
+            clips = [pending[i][0] for i in idxs]
+            cap = 1 << int(np.ceil(np.log2(max(len(c) for c in clips))))     # few engines: power-of-two maxima
+            return self._engine(cap, clips[0].dtype, self.devices[0]).run_host_ragged(clips)
+
         def flush():
             if not pending:
                 return
-            # group by (length, dtype) keeping loader order inside the batch
+            # group by (length, dtype) — by dtype only when ragged — keeping loader order
             results: list = [None] * len(pending)
             groups: dict = {}
             for idx, (audio, _l, _m, _p) in enumerate(pending):
-                groups.setdefault((len(audio), audio.dtype.str), []).append(idx)
+                groups.setdefault((0 if ragged else len(audio), audio.dtype.str), []).append(idx)
             for (_n, _dt), idxs in groups.items():
                 try:
-                    got = run_group(idxs)
+                    got = run_ragged(idxs) if ragged else run_group(idxs)
                     for k, i in enumerate(idxs):
                         results[i] = got[k]
                 except Exception as exc:  # noqa: BLE001 — same policy as a failing extract()

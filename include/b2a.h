@@ -98,6 +98,20 @@ int b2a_run_device(b2a_handle* h, const void* d_clips, int64_t n_clips, float* d
  * overlaps H2D / kernels / D2H on its own streams and returns when `out` is complete. */
 int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out);
 
+/* Ragged batches (`duration=None` in the reference: every clip keeps its own length and frame
+ * count; deep.py:122-124 is skipped).  mel and mfcc handles only.  Clip i has lengths[i] samples,
+ * n_fft <= lengths[i] <= cfg.n_samples (the handle's n_samples is the MAXIMUM length), stored at
+ * element offset in_offsets[i] of `clips` (a multiple of 8 elements keeps the TMA staging path);
+ * its (rows, 1 + lengths[i]/hop) float32 features are written at float offset out_offsets[i] of
+ * `out`.  Host variant: all five pointers are host pointers, total_in / total_out are the element
+ * counts of `clips` / `out`.  Device variant: all five are device pointers, asynchronous on `stream`. */
+int b2a_run_host_ragged(b2a_handle* h, const void* clips, int64_t total_in, const int64_t* in_offsets,
+                        const int32_t* lengths, const int64_t* out_offsets, int64_t n_clips,
+                        float* out, int64_t total_out);
+int b2a_run_device_ragged(b2a_handle* h, const void* d_clips, const int64_t* d_in_offsets,
+                          const int32_t* d_lengths, const int64_t* d_out_offsets, int64_t n_clips,
+                          float* d_out, void* stream);
+
 /* Number of CUDA kernel launches the last b2a_run_* call on this handle enqueued. */
 int64_t b2a_last_launch_count(const b2a_handle* h);
 

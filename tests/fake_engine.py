@@ -36,6 +36,11 @@ class FakeEngine:
         return L.audio_cqt(y, c.sample_rate, c.hop_length, c.n_bins, c.bins_per_octave,
                            c.fmin if c.fmin > 0 else None, None)
 
+    def run_host_ragged(self, clips):
+        FakeEngine.calls.append((self.device, len(clips)))
+        assert all(len(c) <= self.cfg.n_samples for c in clips)
+        return [self._one(np.asarray(c)) for c in clips]
+
     def run_host(self, clips, out=None):
         FakeEngine.calls.append((self.device, len(clips)))
         res = np.stack([self._one(c) for c in clips]) if len(clips) else np.empty((0, self.rows, self.frames), np.float32)

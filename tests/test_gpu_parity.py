@@ -140,6 +140,40 @@ def test_cqt_config3(dtype):
     assert err.max() <= CQT_TOL, f"per-clip max-abs: {err}"
 
 
+@pytest.mark.parametrize("kind,n_fft,hop", [(B.KIND_MEL, 512, 160), (B.KIND_MFCC, 512, 160), (B.KIND_MEL, 1024, 256)])
+def test_ragged_batch_matches_per_clip_oracle(kind, n_fft, hop):
+    """duration=None: clips of different lengths in ONE launch (b2a_run_host_ragged)."""
+    rng = np.random.default_rng(77)
+    lens = [n_fft, n_fft + 1, 5000, 16000, 16001, 33333, 47999, 80000, 12345, 2 * n_fft + 159]
+    clips = [synth.to_pcm16(synth.make_clip(rng, i % 5, 16000, L_)[:L_]) for i, L_ in enumerate(lens)]
+    clips = [np.pad(c, (0, L_ - len(c))) for c, L_ in zip(clips, lens)]
+    kw = dict(n_fft=n_fft, hop_length=hop, n_mels=40, sample_rate=16000)
+    if kind == B.KIND_MFCC:
+        kw["n_mfcc"] = 13
+    with _engine(kind, 131072, **kw) as e:
+        got = e.run_host_ragged(clips)
+        assert e.last_launch_count == 1
+    for c, g in zip(clips, got):
+        y = L.pcm16_to_float(c)
+        if kind == B.KIND_MEL:
+            ref, tol = L.audio_mel_spec(y, 16000, 40, n_fft, hop), MEL_TOL
+        else:
+            ref, tol = L.audio_mfcc_seq(y, 16000, 13, n_fft, hop, None, n_mels=40), MFCC_TOL
+        assert g.shape == ref.shape == (ref.shape[0], 1 + len(c) // hop)
+        assert np.abs(g - ref).max() <= tol, (len(c), float(np.abs(g - ref).max()))
+
+
+def test_ragged_rejects_bad_lengths():
+    with _engine(B.KIND_MEL, 16000) as e:
+        with pytest.raises(B.B2AError):
+            e.run_host_ragged([np.zeros(100, np.int16)])            # shorter than n_fft
+        with pytest.raises(B.B2AError):
+            e.run_host_ragged([np.zeros(16001, np.int16)])          # longer than cfg.n_samples
+    with _engine(B.KIND_CQT, 110250) as e:
+        with pytest.raises(B.B2AError):
+            e.run_host_ragged([np.zeros(110250, np.int16)])
+
+
 def test_tables_match_oracle():
     with _engine(B.KIND_MEL, 80000) as e:
         w = e.table(B.TABLE_MEL_DENSE).reshape(40, 257)

@@ -161,6 +161,21 @@ def test_rate_mismatch_is_a_per_sample_skip(tmp_path, fake):
     assert fs.n_samples == 1 and fs.metadata[0]["filename"] == "y.wav"
 
 
+def test_duration_none_goes_through_one_ragged_call(tmp_path, fake):
+    """duration=None (reference default): every clip keeps its own frame count."""
+    clips = _make_dataset(tmp_path / "ds", classes=("a",), per=5)
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    ex = P.AudioMelSpectrogram()
+    FakeEngine.calls = []
+    with pytest.raises(ValueError):                    # np.stack of ragged features, as in the reference
+        ex.extract_dataset(AudioFolderLoader(tmp_path / "ds"))
+    assert FakeEngine.calls == [(0, 5)]                # one launch for the whole window
+    for (c, i), pcm in clips.items():
+        got = ex.extract(tmp_path / "ds" / c / f"clip_{i}.wav")
+        assert got.shape == (40, 1 + len(pcm) // 160)
+        assert np.array_equal(got, L.audio_mel_spec(L.pcm16_to_float(pcm)))
+
+
 def test_multi_device_sharding_is_contiguous_and_ordered(fake):
     pcm = synth.make_suite(10, 16000, 4000, seed=3)
     one = P.AudioMelSpectrogram(devices=[0]).extract_batch(pcm)
