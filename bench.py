@@ -191,6 +191,25 @@ def run_reference(args):
     return 0
 
 
+def _bind_to_gpu_numa(gpu: int):
+    """Pin this process to the CPU cores NVML reports as local to `gpu` (PCIe/NUMA locality for the
+    end-to-end leg).  Best effort; returns the number of cores bound or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -204,6 +223,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device — this package has no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = _bind_to_gpu_numa(local)        # pinned staging buffers then live next to this rank's GPU
     from audio_edge_ml_pipeline_b200 import dist as D
     import audio_edge_ml_pipeline_b200 as P
     D.init("nccl", dev)
@@ -317,7 +337,7 @@ def run_ours(args):
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": ne * N_SAMPLES * 2,
                     "d2h_bytes_per_step": ne * N_MELS * N_FRAMES * 4, "clips_per_step": ne,
-                    "steps": e2e_steps, "api": f"get('{ext_name}')(...).extract_batch -> b2a_run_host (pinned host buffers)",
+                    "steps": e2e_steps, "cpu_cores_bound_to_gpu_numa": numa, "api": f"get('{ext_name}')(...).extract_batch -> b2a_run_host (pinned host buffers)",
                     "checksum": checksum},
             "gpu_launches": launches,
             "clocks": clocks,
