@@ -24,7 +24,7 @@ TABLE_WINDOW, TABLE_MEL_DENSE, TABLE_DCT, TABLE_DECIM_TAPS, TABLE_CQT_LENGTHS, T
 EXPORTED_SYMBOLS = [
     "b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
     "b2a_run_host", "b2a_run_host_ragged", "b2a_run_device_ragged", "b2a_last_launch_count", "b2a_alloc_pinned", "b2a_free_pinned",
-    "b2a_get_table", "b2a_cqt_geometry", "b2a_last_error", "b2a_abi_version", "b2a_device_count",
+    "b2a_decode_wav_pcm16_batch", "b2a_get_table", "b2a_cqt_geometry", "b2a_last_error", "b2a_abi_version", "b2a_device_count",
 ]
 
 
@@ -66,6 +66,8 @@ def load_library() -> C.CDLL:
     lib.b2a_run_host.argtypes = [vp, vp, i64, vp]
     lib.b2a_run_host_ragged.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, i64]
     lib.b2a_run_device_ragged.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
+    lib.b2a_decode_wav_pcm16_batch.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp, i32]
+    lib.b2a_decode_wav_pcm16_batch.restype = C.c_int
     lib.b2a_last_launch_count.argtypes = [vp]
     lib.b2a_last_launch_count.restype = i64
     lib.b2a_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -94,6 +96,29 @@ def default_config(kind: int) -> B2AConfig:
 
 def device_count() -> int:
     return int(load_library().b2a_device_count())
+
+
+DEC_OK, DEC_EIO, DEC_EFORMAT, DEC_EUNSUPPORTED, DEC_ERATE = range(5)
+
+
+def decode_wav_pcm16_batch(paths, sample_rate: int, n_samples: int, out: np.ndarray, offsets=None,
+                           durations=None, n_threads: int = 0) -> np.ndarray:
+    """Native threaded decode of mono PCM16 WAV files into ``out[:len(paths)]`` (int16,
+    (>=N, n_samples), C-contiguous).  Returns the per-file B2A_DEC_* status array."""
+    lib = load_library()
+    n = len(paths)
+    status = np.zeros(n, dtype=np.int32)
+    if n == 0:
+        return status
+    assert out.dtype == np.int16 and out.flags.c_contiguous and out.shape[1] == n_samples and out.shape[0] >= n
+    arr = (C.c_char_p * n)(*[str(p).encode() for p in paths])
+    off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.float64)
+    dur = None if durations is None else np.ascontiguousarray(durations, dtype=np.float64)
+    _check(lib.b2a_decode_wav_pcm16_batch(C.cast(arr, C.c_void_p), n, int(sample_rate),
+                                          None if off is None else off.ctypes.data,
+                                          None if dur is None else dur.ctypes.data,
+                                          int(n_samples), out.ctypes.data, status.ctypes.data, int(n_threads)))
+    return status
 
 
 class PinnedArray:

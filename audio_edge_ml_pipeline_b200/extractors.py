@@ -35,6 +35,7 @@ logger = logging.getLogger(__name__)
 
 HOST_BATCH_CLIPS = 4096          # clips decoded and shipped per GPU round in extract_dataset
 DECODE_WORKERS = min(16, os.cpu_count() or 1)   # file reads release the GIL; order is preserved
+NATIVE_DECODE = True             # threaded C decoder for mono PCM16 WAVs (fixed-duration windows)
 
 
 def _make_engine(cfg: B.B2AConfig, device: int):
@@ -254,10 +255,59 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
             if buf:
                 yield buf
 
+        def native_window(items):
+            """Fixed-duration windows: threaded native decode of mono PCM16 WAVs straight into the
+            pinned batch (b2a_decode_wav_pcm16_batch).  Returns (int16 batch view, status) or None."""
+            if self.duration is None or not NATIVE_DECODE:
+                return None
+            n = int(self.duration * self.sample_rate)
+            if n < self._min_samples():
+                return None
+            key = (n, np.dtype(np.int16).str)
+            if key not in staging:
+                eng = self._engine(n, np.int16, self.devices[0])
+                a_in, h1 = _alloc_staging((HOST_BATCH_CLIPS, n), np.int16)
+                a_out, h2 = _alloc_staging((HOST_BATCH_CLIPS, eng.rows, eng.frames), np.float32)
+                staging[key] = (a_in, a_out, h1, h2)
+            offs = np.array([float(m.get("start_time") or 0.0) for _p, _l, m in items])
+            durs = np.array([max(float(m["end_time"]) - o, 0.1) if m.get("end_time") is not None else -1.0
+                             for (_p, _l, m), o in zip(items, offs)])
+            status = B.decode_wav_pcm16_batch([p_ for p_, _l, _m in items], self.sample_rate, n, staging[key][0],
+                                              offs, durs, DECODE_WORKERS)
+            return staging[key][0][:len(items)], staging[key][1][:len(items)], status
+
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=DECODE_WORKERS) as pool:
             for items in window():
-                decoded = list(pool.map(decode, items)) if DECODE_WORKERS > 1 else [decode(it) for it in items]
+                nat = None
+                try:
+                    nat = native_window(items)
+                except Exception as exc:  # noqa: BLE001 — e.g. engine creation failed: per-sample policy below
+                    logger.debug("native decode unavailable: %s", exc)
+                if nat is not None and not nat[2].any():
+                    # every file decoded natively: the pinned batch goes to the GPU(s) as is
+                    try:
+                        got = self.extract_batch(nat[0], nat[1]).copy()
+                    except Exception as exc:  # noqa: BLE001
+                        for sample_path, _l, _m in items:
+                            logger.warning("Skipping %s: %s", sample_path, exc)
+                        continue
+                    for (sample_path, label, meta), g in zip(items, got):
+                        feats.append(g)
+                        metas.append(meta)
+                        if label is not None:
+                            if label not in label_to_idx:
+                                label_to_idx[label] = len(label_to_idx)
+                            labels.append(label_to_idx[label])
+                    continue
+                # general path: Python decoder (more formats, segment slicing, exact error messages)
+                if nat is not None:
+                    todo = [it for it, st in zip(items, nat[2]) if st != 0]
+                    redo = dict(zip((id(it) for it in todo),
+                                    pool.map(decode, todo) if DECODE_WORKERS > 1 else map(decode, todo)))
+                    decoded = [nat[0][k].copy() if nat[2][k] == 0 else redo[id(it)] for k, it in enumerate(items)]
+                else:
+                    decoded = list(pool.map(decode, items)) if DECODE_WORKERS > 1 else [decode(it) for it in items]
                 for (sample_path, label, meta), audio in zip(items, decoded):
                     if isinstance(audio, Exception):
                         logger.warning("Skipping %s: %s", sample_path, audio)

@@ -28,6 +28,7 @@
 #ifndef B2A_H_
 #define B2A_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -111,6 +112,23 @@ int b2a_run_host_ragged(b2a_handle* h, const void* clips, int64_t total_in, cons
 int b2a_run_device_ragged(b2a_handle* h, const void* d_clips, const int64_t* d_in_offsets,
                           const int32_t* d_lengths, const int64_t* d_out_offsets, int64_t n_clips,
                           float* d_out, void* stream);
+
+/* Host-side front end for the common case (no GPU involved): decode n_files mono 16-bit PCM
+ * RIFF/WAVE files that are already at `sample_rate` straight into dst[n_files][n_samples]
+ * (typically pinned memory), applying what deep.py:30-61 applies per clip: optional segment
+ * [offset_s[i], offset_s[i] + duration_s[i]) in native frames (NULL arrays = whole file,
+ * duration < 0 = to the end), truncate to n_samples, right zero-pad.  status[i] receives
+ * B2A_DEC_*; rows whose status is not B2A_DEC_OK are zero-filled and are the caller's to handle
+ * (other formats -> a fuller decoder; otherwise skip the sample as base.py:204-206 does).
+ * n_threads <= 0 picks min(32, hardware threads). */
+#define B2A_DEC_OK            0
+#define B2A_DEC_EIO           1   /* open/read failed                                   */
+#define B2A_DEC_EFORMAT       2   /* not a RIFF/WAVE file or malformed                  */
+#define B2A_DEC_EUNSUPPORTED  3   /* valid WAV, but not mono 16-bit PCM                 */
+#define B2A_DEC_ERATE         4   /* file rate != sample_rate (the reference resamples) */
+int b2a_decode_wav_pcm16_batch(const char* const* paths, int64_t n_files, int32_t sample_rate,
+                               const double* offset_s, const double* duration_s, int32_t n_samples,
+                               int16_t* dst, int32_t* status, int32_t n_threads);
 
 /* Number of CUDA kernel launches the last b2a_run_* call on this handle enqueued. */
 int64_t b2a_last_launch_count(const b2a_handle* h);

@@ -228,6 +228,43 @@ def test_wav_decode_variants(tmp_path):
         wavio.decode_wav(tmp_path / "bad.wav")
 
 
+def test_native_batch_decoder_matches_python_decoder(tmp_path, lib_built):
+    from audio_edge_ml_pipeline_b200 import _lib as B
+    import scipy.io.wavfile as wf
+    rng = np.random.default_rng(11)
+    xs = [synth.to_pcm16(rng.standard_normal(n) * 0.2) for n in (700, 16000, 23456)]
+    for i, x in enumerate(xs):
+        wavio.write_wav_pcm16(tmp_path / f"{i}.wav", x, 16000)
+    (tmp_path / "junk.wav").write_bytes(b"RIFFxxxxjunk")
+    wavio.write_wav_pcm16(tmp_path / "r8k.wav", xs[0], 8000)
+    wf.write(tmp_path / "stereo.wav", 16000, np.stack([xs[1], xs[1]], axis=1))
+    wf.write(tmp_path / "f32.wav", 16000, (xs[1] / 32768).astype(np.float32))
+    names = ["0.wav", "1.wav", "2.wav", "junk.wav", "r8k.wav", "stereo.wav", "f32.wav", "nope.wav"]
+    out = np.full((len(names), 16000), 123, np.int16)
+    st = B.decode_wav_pcm16_batch([tmp_path / n for n in names], 16000, 16000, out, n_threads=3)
+    assert st.tolist() == [B.DEC_OK, B.DEC_OK, B.DEC_OK, B.DEC_EFORMAT, B.DEC_ERATE, B.DEC_EUNSUPPORTED,
+                           B.DEC_EUNSUPPORTED, B.DEC_EIO]
+    for k in range(3):                                  # same samples as load_segment + pad_or_trim
+        ref = wavio.pad_or_trim(wavio.load_segment(tmp_path / names[k], 16000, None, None, min_samples=512), 16000)
+        assert np.array_equal(out[k], ref)
+    assert (out[3:] == 0).all()
+    st = B.decode_wav_pcm16_batch([tmp_path / "2.wav"] * 2, 16000, 16000, out, offsets=[0.5, 1.4], durations=[0.25, -1.0])
+    assert st.tolist() == [0, 0]
+    assert np.array_equal(out[0], wavio.pad_or_trim(wavio.load_segment(tmp_path / "2.wav", 16000, 0.5, 0.75), 16000))
+    assert np.array_equal(out[1], wavio.pad_or_trim(wavio.load_segment(tmp_path / "2.wav", 16000, 1.4, None), 16000))
+
+
+def test_native_and_python_decode_paths_give_the_same_dataset(tmp_path, fake, monkeypatch):
+    _make_dataset(tmp_path / "ds", n=8000, broken={("axe", 1)})
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    loader = AudioFolderLoader(tmp_path / "ds")
+    a = P.AudioMelSpectrogram(duration=0.5).extract_dataset(loader)
+    monkeypatch.setattr(extractors, "NATIVE_DECODE", False)
+    b = P.AudioMelSpectrogram(duration=0.5).extract_dataset(loader)
+    assert np.array_equal(a.features, b.features) and np.array_equal(a.labels, b.labels)
+    assert a.metadata == b.metadata and a.label_names == b.label_names
+
+
 # ---- persistence + config ---------------------------------------------------------------------------
 
 def test_save_layout_and_roundtrip(tmp_path, fake):
