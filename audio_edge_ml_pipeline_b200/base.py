@@ -112,9 +112,12 @@ class BaseFeatureExtractor(ABC):
 
 def assemble_feature_set(extractor, feats, labels, metas, label_to_idx) -> FeatureSet:
     """Tail of the reference's extract_dataset (base.py:216-234)."""
-    if not feats:
-        raise RuntimeError("No features were successfully extracted.")
-    features = np.stack(feats) if not isinstance(feats, np.ndarray) else feats
+    if isinstance(feats, np.ndarray):
+        features = feats
+    else:
+        if not feats:
+            raise RuntimeError("No features were successfully extracted.")
+        features = np.stack(feats)
     lab = np.array(labels, dtype=np.int32) if labels else None
     names = [k for k, _ in sorted(label_to_idx.items(), key=lambda x: x[1])] if label_to_idx else None
     return FeatureSet(features=features, feature_type=extractor.feature_type, modality=extractor.modality,

@@ -80,6 +80,7 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
     def _init_common(self, devices) -> None:
         self._devices_arg = devices
         self._engines: dict = {}
+        self._staging: dict = {}      # (n_samples, dtype) -> pinned (in, out) batch buffers, reused across calls
         self._lock = threading.Lock()
 
     # ---- per-extractor hooks -----------------------------------------------------------
@@ -112,6 +113,11 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
         for e in self._engines.values():
             e.close()
         self._engines.clear()
+        for st in self._staging.values():
+            for hnd in st[2:]:
+                if hnd is not None:
+                    hnd.close()
+        self._staging.clear()
 
     # ---- host-side front end (deep.py:30-61) ---------------------------------------------
     def _prepare(self, sample_path, start_time, end_time) -> np.ndarray:
@@ -183,7 +189,8 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
         label_to_idx: dict = {}
         pending: list = []           # (audio, label, meta, path)
 
-        staging: dict = {}           # (n_samples, dtype) -> (in array, out array, keep-alive handles)
+        staging = self._staging      # (n_samples, dtype) -> (in array, out array, keep-alive handles)
+        final = {"arr": None, "pos": 0, "ok": True}   # features written in place when every window is 'fast'
 
         def run_group(idxs):
             """One (length, dtype) group of the pending window -> (n, rows, T) features."""
@@ -228,7 +235,8 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
             for i, (_a, label, meta, _p) in enumerate(pending):
                 if results[i] is None:
                     continue
-                feats.append(results[i])
+                feats.append(results[i][None])
+                final["ok"] = False
                 metas.append(meta)
                 if label is not None:
                     if label not in label_to_idx:
@@ -287,13 +295,22 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
                 if nat is not None and not nat[2].any():
                     # every file decoded natively: the pinned batch goes to the GPU(s) as is
                     try:
-                        got = self.extract_batch(nat[0], nat[1]).copy()
+                        k = len(items)
+                        if final["arr"] is None and final["ok"] and hasattr(loader, "__len__"):
+                            cap = len(loader) if max_samples is None else min(len(loader), max_samples)
+                            final["arr"] = np.empty((cap,) + nat[1].shape[1:], dtype=np.float32)
+                        if final["arr"] is not None and final["ok"] and final["pos"] + k <= len(final["arr"]):
+                            got = self.extract_batch(nat[0], final["arr"][final["pos"]:final["pos"] + k])
+                            final["pos"] += k
+                        else:
+                            final["ok"] = False
+                            got = self.extract_batch(nat[0], nat[1]).copy()
                     except Exception as exc:  # noqa: BLE001
                         for sample_path, _l, _m in items:
                             logger.warning("Skipping %s: %s", sample_path, exc)
                         continue
-                    for (sample_path, label, meta), g in zip(items, got):
-                        feats.append(g)
+                    feats.append(got)
+                    for sample_path, label, meta in items:
                         metas.append(meta)
                         if label is not None:
                             if label not in label_to_idx:
@@ -315,7 +332,13 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
                     pending.append((audio, label, meta, sample_path))
                 flush()
         flush()
-        return assemble_feature_set(self, feats, labels, metas, label_to_idx)
+        if not feats:
+            raise RuntimeError("No features were successfully extracted.")
+        if final["ok"] and final["arr"] is not None:
+            features = final["arr"][:final["pos"]]              # every window decoded natively: no copy
+        else:
+            features = feats[0] if len(feats) == 1 else np.concatenate(feats)   # ragged shapes -> ValueError
+        return assemble_feature_set(self, features, labels, metas, label_to_idx)
 
 
 @register
