@@ -244,7 +244,7 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
             }
             h->mel_wpad = (int)wq.size();
             const size_t smem512 = b2a::logmel512_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad,
-                                                             cfg->input_dtype == B2A_IN_I16);
+                                                             cfg->input_dtype == B2A_IN_I16, mfcc);
             const bool fits = smem512 <= (size_t)prop.sharedMemPerBlockOptin &&
                               (!mfcc || (size_t)cfg->n_mels * 32 <= 132u * 68u);
             if (fits) {

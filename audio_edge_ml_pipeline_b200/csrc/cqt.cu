@@ -162,9 +162,8 @@ __global__ void __launch_bounds__(kThreads) cqt_octave_kernel(OctParams p) {
     float* s_audio = reinterpret_cast<float*>(smem_raw);
     float2* s_xch = reinterpret_cast<float2*>(s_audio + cl);
     float2* s_spec = s_xch + FR * G::XSTRIDE;
-    uintptr_t q = reinterpret_cast<uintptr_t>(s_spec + F * C::SSTRIDE);
-    q = (q + 15) & ~(uintptr_t)15;
-    float2* s_tw = reinterpret_cast<float2*>(q);
+    const int off_tw = ((cl * 4 + FR * G::XSTRIDE * 8 + F * C::SSTRIDE * 8) + 15) & ~15;   // no integer round trip
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw + off_tw);
     float2* s_tw2 = s_tw + NC;
     float2* s_basis = s_tw2 + NC / 2 + 1;
     int* s_k0 = reinterpret_cast<int*>(s_basis + p.nnz);

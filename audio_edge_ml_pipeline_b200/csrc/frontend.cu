@@ -129,9 +129,10 @@ __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel
     float* s_audio = reinterpret_cast<float*>(smem_raw);
     float2* s_xch = reinterpret_cast<float2*>(s_audio + cl);
     float* s_pow = reinterpret_cast<float*>(s_xch + SLOTS * G::XSTRIDE);
-    uintptr_t q = reinterpret_cast<uintptr_t>(s_pow + F * G::PSTRIDE);
-    q = (q + 15) & ~(uintptr_t)15;
-    float2* s_tw = reinterpret_cast<float2*>(q);
+    // byte offsets from smem_raw (no integer round trip: keeps the shared address space visible
+    // to the compiler, so table reads are LDS, not generic LD)
+    const int off_tw = ((cl * 4 + SLOTS * G::XSTRIDE * 8 + F * G::PSTRIDE * 4) + 15) & ~15;
+    float2* s_tw = reinterpret_cast<float2*>(smem_raw + off_tw);
     float2* s_tw2 = s_tw + NC;
     int* s_k0 = reinterpret_cast<int*>(s_tw2 + NC / 2 + 1);
     int* s_cnt = s_k0 + p.n_mels;

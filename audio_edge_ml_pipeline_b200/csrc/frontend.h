@@ -41,7 +41,7 @@ int front_ctas_per_sm(int log2nc);
 cudaError_t launch_front(const FrontParams& p, int log2nc, bool i16, int kind, int grid, cudaStream_t st);
 
 // specialised n_fft = 512 kernel (logmel512.cu); requires an even hop
-size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16);
+size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc);
 bool logmel512_has_special(int sample_rate, int n_mels);
 cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st);
 

@@ -103,10 +103,10 @@ __device__ __forceinline__ E raw_sample(const E* clip, int s, int n, int pad_mod
 
 struct Layout {
     int chunk;          // samples staged per tile, multiple of 8
-    int off_raw, off_raw2, off_audio, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, total;
+    int off_raw, off_raw2, off_audio, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, off_db, total;
 };
 
-__host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16) {
+__host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc) {
     Layout L;
     L.chunk = (hop * (F - 1) + NFFT + 7) & ~7;
     int o = 0;
@@ -122,6 +122,7 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.off_melk = take(n_mels * 16);
     L.off_red = take(64 * 4);
     L.off_bar = take(16);
+    L.off_db = take(mfcc ? n_mels * 32 * 4 : 0);      // mfcc: [n_mels][32] dB tile feeding the in-tile DCT
     L.total = o;
     return L;
 }
@@ -129,7 +130,8 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
 template <bool I16, int KIND, bool SPEC, bool RAG>
 __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16);
+    const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16, KIND == 1);
+    float* const s_db = reinterpret_cast<float*>(smem + L.off_db);
     float2* const s_xch = reinterpret_cast<float2*>(smem + L.off_xch);
     float* const s_pow = reinterpret_cast<float*>(smem + L.off_pow);
     float2* const s_tw2 = reinterpret_cast<float2*>(smem + L.off_tw2);
@@ -306,6 +308,7 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
 #define B2A_EMIT(M, VAL)                                                            \
     {                                                                               \
         const float vv = db10(VAL);                                                 \
+        if (KIND == 1) s_db[(M) * 32 + lane] = vv;                                  \
         if (valid) { outp[(M) * nfr] = vv; vmax = fmaxf(vmax, vv); vmin = fminf(vmin, vv); } \
     }
                     switch (warp) {
@@ -336,12 +339,30 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                             pr += PROW;
                         }
                         const float vv = db10((a0 + a1) + (a2 + a3));
+                        if (KIND == 1) s_db[d.w * 32 + lane] = vv;
                         if (valid) {
                             outp[d.w * nfr] = vv;
                             vmax = fmaxf(vmax, vv);
                             vmin = fminf(vmin, vv);
                         }
                     }
+                }
+            }
+            if constexpr (KIND == 1) {
+                // (H) DCT-II of this tile straight from shared memory, assuming the top_db clip
+                //     (known only after the clip's last tile) will not engage; checked below.
+                __syncthreads();
+                for (int i = tid; i < p.n_mfcc * 32; i += kThreads) {
+                    const int k = i >> 5, f = i & 31, t = t0 + f;
+                    const float* d = p.dct + (size_t)k * n_mels;
+                    float a0 = 0.f, a1 = 0.f;
+                    int m = 0;
+                    for (; m + 1 < n_mels; m += 2) {
+                        a0 = fmaf(__ldg(d + m), s_db[m * 32 + f], a0);
+                        a1 = fmaf(__ldg(d + m + 1), s_db[(m + 1) * 32 + f], a1);
+                    }
+                    if (m < n_mels) a0 = fmaf(__ldg(d + m), s_db[m * 32 + f], a0);
+                    if (t < nfr) outb[(size_t)k * nfr + t] = a0 + a1;
                 }
             }
         }
@@ -384,36 +405,69 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
         } else {
             float* outc = outb;
             const float thr = vmax - p.top_db;
-            float* s_l = s_pow;                                   // [n_mels][32] clipped dB tile
-            for (int t0 = 0; t0 < nfr; t0 += 32) {
-                __syncthreads();
-                for (int i = tid; i < n_mels * 32; i += kThreads) {
-                    const int m = i >> 5, f = i & 31, t = t0 + f;
-                    s_l[i] = (t < nfr) ? fmaxf(inter[(size_t)m * nfr + t], thr) : 0.f;
-                }
-                __syncthreads();
-                for (int i = tid; i < p.n_mfcc * 32; i += kThreads) {
-                    const int k = i >> 5, f = i & 31, t = t0 + f;
-                    const float* d = p.dct + (size_t)k * n_mels;
-                    float acc = 0.f;
+            if (vmin < thr) {
+                // rare: some band fell more than top_db below the clip's peak, so the clipped dB differ
+                // from what the in-tile DCT saw -> recompute from the raw-dB scratch (L2 resident)
+                float* s_l = s_pow;                               // [n_mels][32] clipped dB tile
+                for (int t0 = 0; t0 < nfr; t0 += 32) {
+                    __syncthreads();
+                    for (int i = tid; i < n_mels * 32; i += kThreads) {
+                        const int m = i >> 5, f = i & 31, t = t0 + f;
+                        s_l[i] = (t < nfr) ? fmaxf(inter[(size_t)m * nfr + t], thr) : 0.f;
+                    }
+                    __syncthreads();
+                    for (int i = tid; i < p.n_mfcc * 32; i += kThreads) {
+                        const int k = i >> 5, f = i & 31, t = t0 + f;
+                        const float* d = p.dct + (size_t)k * n_mels;
+                        float acc = 0.f;
 #pragma unroll 4
-                    for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(d + m), s_l[m * 32 + f], acc);
-                    if (t < nfr) outc[(size_t)k * nfr + t] = acc;
+                        for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(d + m), s_l[m * 32 + f], acc);
+                        if (t < nfr) outc[(size_t)k * nfr + t] = acc;
+                    }
                 }
+                __syncthreads();
+                for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // s_l reuse
             }
-            __syncthreads();
-            for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // s_l reuse
+            __syncthreads();                                      // in-tile DCT stores visible CTA-wide
+            // deep.py:326-328: per-row z-score.  Rows up to 32*ZR frames stay in registers (one L2
+            // sweep, ZR independent loads in flight); longer rows take the three-sweep form.
+            constexpr int ZR = 24;
             const float fn = (float)nfr;
             for (int k = warp; k < p.n_mfcc; k += kWarps) {
                 float* row = outc + (size_t)k * nfr;
                 const float x0 = row[0];
-                float s = 0.f;
-                for (int t = lane; t < nfr; t += 32) s += row[t] - x0;
-                const float mean = x0 + __fdiv_rn(warp_sum(s), fn);
-                float ss = 0.f;
-                for (int t = lane; t < nfr; t += 32) { const float d = row[t] - mean; ss = fmaf(d, d, ss); }
-                const float sd = sqrtf(__fdiv_rn(warp_sum(ss), fn)) + 1e-8f;
-                for (int t = lane; t < nfr; t += 32) row[t] = __fdiv_rn(row[t] - mean, sd);
+                if (nfr <= 32 * ZR) {
+                    float x[ZR];
+                    float s_ = 0.f;
+#pragma unroll
+                    for (int u = 0; u < ZR; ++u) {
+                        const int t = lane + 32 * u;
+                        x[u] = (t < nfr) ? row[t] : x0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < ZR; ++u) s_ += x[u] - x0;       // padding lanes contribute 0
+                    const float mean = x0 + __fdiv_rn(warp_sum(s_), fn);
+                    float ss = 0.f;
+#pragma unroll
+                    for (int u = 0; u < ZR; ++u) {
+                        const float d = x[u] - mean;
+                        if (lane + 32 * u < nfr) ss = fmaf(d, d, ss);
+                    }
+                    const float sd = sqrtf(__fdiv_rn(warp_sum(ss), fn)) + 1e-8f;
+#pragma unroll
+                    for (int u = 0; u < ZR; ++u) {
+                        const int t = lane + 32 * u;
+                        if (t < nfr) row[t] = __fdiv_rn(x[u] - mean, sd);
+                    }
+                } else {
+                    float s_ = 0.f;
+                    for (int t = lane; t < nfr; t += 32) s_ += row[t] - x0;
+                    const float mean = x0 + __fdiv_rn(warp_sum(s_), fn);
+                    float ss = 0.f;
+                    for (int t = lane; t < nfr; t += 32) { const float d = row[t] - mean; ss = fmaf(d, d, ss); }
+                    const float sd = sqrtf(__fdiv_rn(warp_sum(ss), fn)) + 1e-8f;
+                    for (int t = lane; t < nfr; t += 32) row[t] = __fdiv_rn(row[t] - mean, sd);
+                }
             }
         }
         __syncthreads();
@@ -422,8 +476,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
 
 }  // namespace
 
-size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16) {
-    return (size_t)make_layout(hop, n_mels, mel_wpad, i16).total + 128;
+size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc) {
+    return (size_t)make_layout(hop, n_mels, mel_wpad, i16, mfcc).total + 128;
 }
 
 bool logmel512_has_special(int sample_rate, int n_mels) {
@@ -446,7 +500,7 @@ static cudaError_t launch_s(const FrontParams& p, bool i16, int kind, int grid, 
 }
 
 cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st) {
-    const size_t smem = logmel512_smem_bytes(p.hop, p.n_mels, p.mel_wpad, i16);
+    const size_t smem = logmel512_smem_bytes(p.hop, p.n_mels, p.mel_wpad, i16, kind == 1);
     if (p.rag_len) return p.mel_special ? launch_s<true, true>(p, i16, kind, grid, smem, st)
                                         : launch_s<false, true>(p, i16, kind, grid, smem, st);
     return p.mel_special ? launch_s<true, false>(p, i16, kind, grid, smem, st)
