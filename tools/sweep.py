@@ -1,7 +1,7 @@
 """Throughput sweep over configurations (device-resident, CUDA events) — profiling aid."""
 import sys, json, time
 import numpy as np, torch
-sys.path.insert(0, ".")
+sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1]))
 from audio_edge_ml_pipeline_b200 import _lib as B
 
 def run(kind, n_clips, **kw):
