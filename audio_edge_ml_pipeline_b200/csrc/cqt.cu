@@ -145,7 +145,8 @@ static size_t oct_smem_bytes(int log2nc, int hop, int n_rows, int nnz) {
     cl = (cl + 7) & ~(size_t)7;
     size_t b = cl * 4 + (size_t)FR * (NC + NC / 16) * 8 + (size_t)F * (NC + 1) * 8;
     b = (b + 15) & ~(size_t)15;
-    b += (size_t)NC * 8 + (size_t)(NC / 2 + 1) * 8 + (size_t)nnz * 8 + (size_t)n_rows * 12 + 128 * 4;
+    const int R1 = log2nc >= 8 ? 16 : (1 << (log2nc - 4));
+    b += (size_t)NC * 8 + (size_t)(NC / 2 + 1) * 8 + (size_t)(16 / R1) * (R1 - 1) * T * 8 + (size_t)nnz * 8 + (size_t)n_rows * 12 + 128 * 4;
     return b + 64;
 }
 
@@ -165,7 +166,8 @@ __global__ void __launch_bounds__(kThreads) cqt_octave_kernel(OctParams p) {
     const int off_tw = ((cl * 4 + FR * G::XSTRIDE * 8 + F * C::SSTRIDE * 8) + 15) & ~15;   // no integer round trip
     float2* s_tw = reinterpret_cast<float2*>(smem_raw + off_tw);
     float2* s_tw2 = s_tw + NC;
-    float2* s_basis = s_tw2 + NC / 2 + 1;
+    float2* s_twp = s_tw2 + NC / 2 + 1;
+    float2* s_basis = s_twp + FftTwp<LOG2NC>::SIZE;
     int* s_k0 = reinterpret_cast<int*>(s_basis + p.nnz);
     int* s_cnt = s_k0 + p.n_rows;
     int* s_off = s_cnt + p.n_rows;
@@ -174,6 +176,7 @@ __global__ void __launch_bounds__(kThreads) cqt_octave_kernel(OctParams p) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < NC; i += kThreads) s_tw[i] = p.tw[i];
     for (int i = tid; i < NC / 2 + 1; i += kThreads) s_tw2[i] = p.tw2[i];
+    FftTwp<LOG2NC>::fill(s_twp, p.tw, tid, kThreads);
     for (int i = tid; i < p.nnz; i += kThreads) s_basis[i] = p.basis[i];
     for (int i = tid; i < p.n_rows; i += kThreads) { s_k0[i] = p.k0[i]; s_cnt[i] = p.cnt[i]; s_off[i] = p.off[i]; }
 
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kThreads) cqt_octave_kernel(OctParams p) {
             for (int t = 0; t < 16; ++t) xb[xpad(16 * j + t)] = v[t];
         }
         frame_sync<T>();
-        fft_tail_passes<LOG2NC, false>(xb, s_tw, nullptr, j);
+        fft_tail_passes<LOG2NC, false>(xb, s_tw, nullptr, s_twp, j);
         {
             float2* sp = s_spec + f * C::SSTRIDE;
 #pragma unroll

@@ -122,13 +122,32 @@ template <int T> __device__ __forceinline__ void frame_sync() {
     if constexpr (T <= 32) __syncwarp(); else __syncthreads();
 }
 
+// Pass-2 twiddles re-ordered per thread: entry [(u*(R1-1) + (t-1))*T + j] = exp(-2 pi i t k / (16 R1))
+// with k = (j + T u) & 15.  Lanes read consecutive entries (a lookup into the natural-order table is
+// a stride-t access across lanes: up to 16-way bank conflicts in the ncu source view).
+template <int LOG2NC> struct FftTwp {
+    using G = FftGeom<LOG2NC>;
+    static constexpr int NB = 16 / G::R1;
+    static constexpr int SIZE = NB * (G::R1 - 1) * G::T;       // float2 entries
+    static __device__ __forceinline__ void fill(float2* __restrict__ s_twp, const float2* __restrict__ tw_global,
+                                                int tid, int nthreads) {
+        constexpr int TWS = G::NC / (16 * G::R1);
+        for (int i = tid; i < SIZE; i += nthreads) {
+            const int j = i % G::T, r = i / G::T;
+            const int u = r / (G::R1 - 1), t = r % (G::R1 - 1) + 1;
+            const int k = (j + G::T * u) & 15;
+            s_twp[i] = tw_global[(t * k) * TWS];
+        }
+    }
+};
+
 // Passes 2.. of the packed FFT on one frame.  `xb` is this frame's exchange slot holding the
 // output of pass 1 (index 16*j + t, padded); on return it holds Z[0..NC) in natural order.
 // `tw` = exp(-2 pi i k / NC), k in [0, NC), in shared memory.  `tw1` (optional) = this thread's
 // pass-2 twiddles hoisted to registers by the caller when R1 == 16 && 16/R1 == 1.
 template <int LOG2NC, bool HOISTED>
 __device__ __forceinline__ void fft_tail_passes(float2* __restrict__ xb, const float2* __restrict__ tw,
-                                                const float2* tw1, int j) {
+                                                const float2* tw1, const float2* __restrict__ twp, int j) {
     using G = FftGeom<LOG2NC>;
     constexpr int NC = G::NC, T = G::T, R1 = G::R1, R2 = G::R2;
     float2 v[16];
@@ -136,7 +155,6 @@ __device__ __forceinline__ void fft_tail_passes(float2* __restrict__ xb, const f
     {
         constexpr int NB = 16 / R1;                 // butterflies per thread
         constexpr int STR = NC / R1;                // input stride
-        constexpr int TWS = NC / (16 * R1);         // twiddle index scale
 #pragma unroll
         for (int u = 0; u < NB; ++u) {
             const int jb = j + T * u;
@@ -145,7 +163,7 @@ __device__ __forceinline__ void fft_tail_passes(float2* __restrict__ xb, const f
             for (int t = 0; t < R1; ++t) {
                 float2 x = xb[xpad(jb + t * STR)];
                 if (t > 0) {
-                    const float2 w = HOISTED ? tw1[t - 1] : tw[(t * k) * TWS];
+                    const float2 w = HOISTED ? tw1[t - 1] : twp[(u * (R1 - 1) + (t - 1)) * T + j];
                     x = cmul(x, w);
                 }
                 v[u * R1 + t] = x;

@@ -94,7 +94,7 @@ template <int LOG2NC> struct FrontCfg {
     static constexpr int F = (LOG2NC <= 8) ? 32 : 16;                 // frames per tile
     static constexpr int FR = kThreads / G::T;                        // frames per FFT round
     static constexpr int ROUNDS = (F + FR - 1) / FR;
-    static constexpr int MINB = (LOG2NC <= 8) ? 2 : 1;
+    static constexpr int MINB = (LOG2NC <= 9) ? 2 : 1;
 };
 
 size_t front_smem_bytes(int log2nc, int hop, int n_mels, int mel_nnz) {
@@ -111,6 +111,7 @@ size_t front_smem_bytes(int log2nc, int hop, int n_mels, int mel_nnz) {
     b = (b + 15) & ~(size_t)15;
     b += (size_t)NC * 8;                                // tw
     b += (size_t)(NC / 2 + 1) * 8;                      // tw2
+    b += (size_t)(16 / (log2nc >= 8 ? 16 : (1 << (log2nc - 4)))) * ((log2nc >= 8 ? 16 : (1 << (log2nc - 4))) - 1) * T * 8;   // per-thread pass-2 twiddles
     b += (size_t)n_mels * 3 * 4 + (size_t)mel_nnz * 4;  // banded mel
     b += 128 * 4;                                       // reduction scratch
     return b + 64;
@@ -134,7 +135,8 @@ __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel
     const int off_tw = ((cl * 4 + SLOTS * G::XSTRIDE * 8 + F * G::PSTRIDE * 4) + 15) & ~15;
     float2* s_tw = reinterpret_cast<float2*>(smem_raw + off_tw);
     float2* s_tw2 = s_tw + NC;
-    int* s_k0 = reinterpret_cast<int*>(s_tw2 + NC / 2 + 1);
+    float2* s_twp = s_tw2 + NC / 2 + 1;
+    int* s_k0 = reinterpret_cast<int*>(s_twp + FftTwp<LOG2NC>::SIZE);
     int* s_cnt = s_k0 + p.n_mels;
     int* s_off = s_cnt + p.n_mels;
     float* s_w = reinterpret_cast<float*>(s_off + p.n_mels);
@@ -145,6 +147,7 @@ __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel
     // ---- per-CTA tables ---------------------------------------------------------------------
     for (int i = tid; i < NC; i += kThreads) s_tw[i] = p.tw[i];
     for (int i = tid; i < NC / 2 + 1; i += kThreads) s_tw2[i] = p.tw2[i];
+    FftTwp<LOG2NC>::fill(s_twp, p.tw, tid, kThreads);
     for (int i = tid; i < p.n_mels; i += kThreads) { s_k0[i] = p.mel_k0[i]; s_cnt[i] = p.mel_cnt[i]; s_off[i] = p.mel_off[i]; }
     for (int i = tid; i < p.mel_nnz; i += kThreads) s_w[i] = p.mel_w[i];
 
@@ -209,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel
                     for (int t = 0; t < 16; ++t) xb[xpad(16 * j + t)] = v[t];
                 }
                 frame_sync<T>();
-                fft_tail_passes<LOG2NC, HOIST>(xb, s_tw, tw1, j);
+                fft_tail_passes<LOG2NC, HOIST>(xb, s_tw, tw1, s_twp, j);
                 {
                     float* pw = s_pow + f * G::PSTRIDE;
 #pragma unroll
@@ -344,7 +347,7 @@ static cudaError_t launch_l(const FrontParams& p, bool i16, int kind, int grid, 
                      : launch_r<LOG2NC, false>(p, i16, kind, grid, smem, st);
 }
 
-int front_ctas_per_sm(int log2nc) { return log2nc <= 8 ? 2 : 1; }
+int front_ctas_per_sm(int log2nc) { return log2nc <= 9 ? 2 : 1; }
 
 cudaError_t launch_front(const FrontParams& p, int log2nc, bool i16, int kind, int grid, cudaStream_t st) {
     const size_t smem = front_smem_bytes(log2nc, p.hop, p.n_mels, p.mel_nnz);
