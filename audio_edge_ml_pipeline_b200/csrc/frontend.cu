@@ -331,6 +331,12 @@ static cudaError_t launch_one(const FrontParams& p, int grid, size_t smem, cudaS
     auto k = front_kernel<LOG2NC, I16, KIND, RAG>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
+    // persistent CTAs: never launch more than fit at once (shared memory may allow fewer than MINB)
+    int occ = 0, dev = 0, sms = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, kThreads, smem) == cudaSuccess && occ > 0 &&
+        cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+        grid = grid < occ * sms ? grid : occ * sms;
     k<<<grid, kThreads, smem, st>>>(p);
     return cudaGetLastError();
 }
