@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(kDecThreads) cqt_decimate_kernel(
     __syncthreads();
 
     // Accumulation order and precision matter here: six cascaded stages feed CQT bins that sit
-    // 80 dB below the clip's peak.  The 64 taps around the centre carry almost all of the filter's
-    // energy and are accumulated in fp64 (B200 issues DFMA at half the FFMA rate); the 319 small
+    // 80 dB below the clip's peak.  The 32 taps around the centre carry almost all of the filter's
+    // energy and are accumulated in fp64 (B200 issues DFMA at half the FFMA rate); the 351 small
     // outer taps run in fp32 from the tails inwards so their running sums stay small.  The oracle
     // accumulates everything in float64 (oracle/librosa_restated.py: decimate2).
     float acc[kDecR];
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kDecThreads) cqt_decimate_kernel(
     for (int r = 0; r < kDecR; ++r) { acc[r] = 0.f; accd[r] = 0.0; }
     const int lb = tid * kDecR + (kDecHalf - 1);     // local index of A[m_0], B[m_0]
     constexpr int kChunks = kDecHalf / kDecU;        // 24
-    constexpr int kMidLo = 10, kMidHi = 14;          // chunks [10,14) = taps j in [160, 224)
+    constexpr int kMidLo = 11, kMidHi = 13;          // chunks [11,13) = taps j in [176, 208)
     auto chunk_f32 = [&](int i0) {
         float xa[kDecR + kDecU - 1], xb[kDecR + kDecU - 1];
         const int l0 = lb - i0 - (kDecU - 1);

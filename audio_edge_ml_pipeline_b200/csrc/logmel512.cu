@@ -6,13 +6,16 @@
 //     pass-2 results never leave registers — only the 8 rows the mirror lane needs go through
 //     shared memory (X[k] needs Z[k] and Z[256-k], which lives in lane 16-j);
 //   * the next tile's raw PCM is fetched by one cp.async.bulk (TMA bulk copy, mbarrier
-//     completion) while the current tile is being transformed, then widened int16 -> fp32 once
-//     per sample in shared memory (frames overlap 3.2x, so per-frame conversion would cost 3.2x);
-//   * power tile is [bin][frame] with a 34-word row so the two frames of a warp write disjoint
-//     banks and the mel phase (lane = frame, weights warp-uniform, 128-bit broadcast loads)
-//     reads conflict-free;
+//     completion) into the other of two ping-pong buffers while the current tile is being
+//     transformed; pass 1 reads the packed int16 pairs directly (one 32-bit word = one complex
+//     point) and widens them in registers, the exact 1/32768 riding on the window;
+//   * power tile is [bin pair][frame] with a 68-word row so the two frames of a warp write
+//     disjoint banks and the mel phase (lane = frame, band warp-uniform) reads it with
+//     conflict-free 64-bit loads; for the headline configuration the band loop is generated at
+//     build time (gen_mel.cpp) with the 490 filter weights as FFMA immediates;
 //   * raw dB goes to the output buffer (L2-resident), per-clip max/min stay in registers, and
-//     the same CTA normalises the clip in place a few microseconds later.
+//     the same CTA normalises the clip in place a few microseconds later (mfcc: in-tile DCT-II,
+//     recomputed from an L2 scratch only when the top_db clip engages, then a z-score per row).
 //
 // Reference arithmetic: deep.py:126-134 (mel), :318-328 (mfcc) via librosa 0.11.0.
 #include "frontend.h"
@@ -103,7 +106,7 @@ __device__ __forceinline__ E raw_sample(const E* clip, int s, int n, int pad_mod
 
 struct Layout {
     int chunk;          // samples staged per tile, multiple of 8
-    int off_raw, off_raw2, off_audio, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, off_db, total;
+    int off_raw, off_raw2, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, off_db, total;
 };
 
 __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc) {
@@ -114,7 +117,6 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     const int esz = i16 ? 2 : 4;                // two raw buffers (ping-pong), read directly by pass 1
     L.off_raw = take(L.chunk * esz);
     L.off_raw2 = take(L.chunk * esz);
-    L.off_audio = L.off_raw;
     L.off_xch = take(16 * XSLOT * 8);
     L.off_pow = take(PROWS * PROW * 4);
     L.off_tw2 = take(8 * 16 * 8);
