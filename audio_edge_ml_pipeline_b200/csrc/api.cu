@@ -343,6 +343,7 @@ int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out) 
         // ~64 MiB of input per chunk, two chunks in flight
         int64_t cc = (int64_t)((64u << 20) / in_clip);
         cc = std::max<int64_t>(1, std::min<int64_t>(cc, 4096));
+        if (h->cfg.kind == B2A_KIND_CQT) cc = std::max<int64_t>(cc, 1024);   // one full CQT chunk per copy
         h->chunk_clips = cc;
         for (int i = 0; i < 2; ++i) {
             CU_TRY(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
