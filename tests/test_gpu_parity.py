@@ -76,6 +76,18 @@ def test_mel_reflect_padding_option():
     assert np.abs(got - ref).max() <= MEL_TOL
 
 
+def test_mel_against_the_reference_c_implementation_golden():
+    """CUDA path vs the REFERENCE's own C implementation of audio_mel_spec (model_to_c.py:505-624,
+    compiled by oracle/build_ref.py; fixture tests/golden/logmel_ref_c_1s.npz) — no oracle in between.
+    The fixture inputs stay inside 80 dB so the template's missing top_db clip never engages."""
+    from pathlib import Path
+    g = np.load(Path(__file__).resolve().parent / "golden" / "logmel_ref_c_1s.npz")
+    with _engine(B.KIND_MEL, 16000) as e:
+        got = e.run_host(g["pcm"])
+    assert got.shape == g["ref"].shape
+    assert np.abs(got - g["ref"]).max() <= MEL_TOL
+
+
 def test_mel_silence_is_all_zero_and_finite():
     pcm = np.zeros((3, 80000), np.int16)
     with _engine(B.KIND_MEL, 80000) as e:
