@@ -213,7 +213,7 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
         h->grid_cap = h->sm_count * b2a::front_ctas_per_sm(h->log2nc);
         if (n_fft == 512 && (cfg->hop_length % 2) == 0) {
             // tables of the specialised kernel: bands padded to float4 groups, |X|^2 -> 4|X|^2 folded
-            // into the weights (x0.25 is exact), bands dealt to the 8 warps in snake order by size
+            // into the weights (x0.25 is exact), bands dealt to the mel warps in snake order by size
             std::vector<float> wq;
             std::vector<int> k0e(cfg->n_mels), cnt4(cfg->n_mels), off4(cfg->n_mels), order;
             for (int m = 0; m < cfg->n_mels; ++m) {
@@ -231,9 +231,10 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
             for (int m = 0; m < cfg->n_mels; ++m) idx[m] = m;
             std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return cnt4[a] > cnt4[b]; });
             order.assign(cfg->n_mels, 0);
-            for (int i = 0; i < cfg->n_mels; ++i) {           // position i is served by warp i % 8
-                const int rnd = i / 8, w = i % 8;
-                const int src = rnd * 8 + ((rnd & 1) ? 7 - w : w);
+            const int MW = b2a::logmel512_mel_warps();
+            for (int i = 0; i < cfg->n_mels; ++i) {           // position i is served by mel warp i % MW
+                const int rnd = i / MW, w = i % MW;
+                const int src = rnd * MW + ((rnd & 1) ? MW - 1 - w : w);
                 order[i] = idx[std::min(src, cfg->n_mels - 1)];
             }
             {   // the snake can alias at the ragged end; fall back to identity if not a permutation
@@ -245,8 +246,7 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
             h->mel_wpad = (int)wq.size();
             const size_t smem512 = b2a::logmel512_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad,
                                                              cfg->input_dtype == B2A_IN_I16, mfcc);
-            const bool fits = smem512 <= (size_t)prop.sharedMemPerBlockOptin &&
-                              (!mfcc || (size_t)cfg->n_mels * 32 <= 132u * 68u);
+            const bool fits = smem512 <= (size_t)prop.sharedMemPerBlockOptin;
             if (fits) {
                 CU_TRY_H(upload(wq, &h->d_wq));
                 CU_TRY_H(upload(k0e, &h->d_k0e));
@@ -254,7 +254,7 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
                 CU_TRY_H(upload(off4, &h->d_off4));
                 CU_TRY_H(upload(order, &h->d_order));
                 h->use512 = true;
-                h->grid_cap = h->sm_count * (smem512 * 2 <= (size_t)prop.sharedMemPerMultiprocessor - 2048 ? 2 : 1);
+                h->grid_cap = h->sm_count * b2a::logmel512_ctas_per_sm();
             }
         }
         if (mfcc) {

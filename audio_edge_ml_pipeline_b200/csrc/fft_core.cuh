@@ -16,10 +16,19 @@
 
 namespace b2a {
 
-__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// ---- packed FP32 (sm_100a FADD2 / FMUL2 / FFMA2) -----------------------------------------------
+// A complex point is a float2 in an aligned register pair.  Blackwell's packed-FP32 instructions
+// work on such pairs with free per-half negation, half swap (.LO_HI) and scalar broadcast operand
+// modifiers, so a complex add is ONE instruction and a complex multiply TWO (FMUL2 + FFMA2):
+// the same FMA-pipe cycles as the scalar form but half the issue slots, which is what bounds
+// these kernels (tools/ubench/fp32_issue.cu: FFMA2 issues every 2 cycles per scheduler, scalar
+// FFMA every cycle).  ptxas folds the make_float2(...) permutations below into operand modifiers.
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+    // (a.x b.x - a.y b.y, a.y b.x + a.x b.y) = a * (b.x, b.x) + swap(a) * (-b.y, b.y)
+    return __ffma2_rn(make_float2(a.y, a.x), make_float2(-b.y, b.y), __fmul2_rn(a, bc2(b.x)));
 }
 // multiply by -i
 __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a.x); }
@@ -28,25 +37,23 @@ __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a
 #define B2A_COS_PI_8 0.92387953251128675613f
 #define B2A_SIN_PI_8 0.38268343236508977173f
 
-// Fused twiddle butterflies: (e + w*o, e - w*o) in 6 FFMA instead of a 4-op complex multiply
-// plus 4 adds.  The second output is formed as 2e - first (one extra rounding, ~1 ulp).
+// Fused twiddle butterflies: (e + w*o, e - w*o) in 3 FFMA2.  The second output is formed as
+// 2e - first (one extra rounding, ~1 ulp).
 __device__ __forceinline__ void bfly_w(float2 e, float2 o, float wr, float wi, float2& a, float2& b) {
-    a.x = fmaf(-o.y, wi, fmaf(o.x, wr, e.x));
-    a.y = fmaf(o.y, wr, fmaf(o.x, wi, e.y));
-    b.x = fmaf(2.0f, e.x, -a.x);
-    b.y = fmaf(2.0f, e.y, -a.y);
+    a = __ffma2_rn(make_float2(o.y, o.x), make_float2(-wi, wi), __ffma2_rn(o, bc2(wr), e));
+    b = __ffma2_rn(e, bc2(2.0f), make_float2(-a.x, -a.y));
 }
 // w = s(1 - i):  w*o = s((o.x + o.y), (o.y - o.x))
 __device__ __forceinline__ void bfly_p(float2 e, float2 o, float2& a, float2& b) {
-    const float su = o.x + o.y, di = o.y - o.x;
-    a = make_float2(fmaf(B2A_SQRT1_2, su, e.x), fmaf(B2A_SQRT1_2, di, e.y));
-    b = make_float2(fmaf(-B2A_SQRT1_2, su, e.x), fmaf(-B2A_SQRT1_2, di, e.y));
+    const float2 t = __fadd2_rn(o, make_float2(o.y, -o.x));
+    a = __ffma2_rn(t, bc2(B2A_SQRT1_2), e);
+    b = __ffma2_rn(t, bc2(-B2A_SQRT1_2), e);
 }
 // w = s(-1 - i): w*o = s((o.y - o.x), -(o.x + o.y))
 __device__ __forceinline__ void bfly_m(float2 e, float2 o, float2& a, float2& b) {
-    const float su = o.x + o.y, di = o.y - o.x;
-    a = make_float2(fmaf(B2A_SQRT1_2, di, e.x), fmaf(-B2A_SQRT1_2, su, e.y));
-    b = make_float2(fmaf(-B2A_SQRT1_2, di, e.x), fmaf(B2A_SQRT1_2, su, e.y));
+    const float2 t = __fadd2_rn(make_float2(o.y, -o.x), make_float2(-o.x, -o.y));
+    a = __ffma2_rn(t, bc2(B2A_SQRT1_2), e);
+    b = __ffma2_rn(t, bc2(-B2A_SQRT1_2), e);
 }
 
 // In-place forward DFT (e^{-2 pi i nk/N}), natural order in and out.
@@ -214,12 +221,10 @@ __device__ __forceinline__ void fft_tail_passes(float2* __restrict__ xb, const f
 //   A = Z[k], Bz = Z[NC-k] (Z[NC] == Z[0]), w = exp(-i pi k / NC)
 //   returns 2*X[k] in xk and 2*X[NC-k] in xnk  (the factor 2 is removed by the caller)
 __device__ __forceinline__ void rfft_split(float2 A, float2 Bz, float2 w, float2& xk, float2& xnk) {
-    const float2 E = make_float2(A.x + Bz.x, A.y - Bz.y);
-    const float2 O = make_float2(A.y + Bz.y, Bz.x - A.x);
-    xk.x = fmaf(-O.y, w.y, fmaf(O.x, w.x, E.x));          // E + w*O
-    xk.y = fmaf(O.y, w.x, fmaf(O.x, w.y, E.y));
-    xnk.x = fmaf(2.0f, E.x, -xk.x);                        // conj(E - w*O) = conj(2E - xk)
-    xnk.y = fmaf(-2.0f, E.y, xk.y);
+    const float2 E = __fadd2_rn(A, make_float2(Bz.x, -Bz.y));
+    const float2 O = __fadd2_rn(make_float2(A.y, -A.x), make_float2(Bz.y, Bz.x));
+    xk = __ffma2_rn(make_float2(O.y, O.x), make_float2(-w.y, w.y), __ffma2_rn(O, bc2(w.x), E));   // E + w*O
+    xnk = __ffma2_rn(make_float2(E.x, -E.y), bc2(2.0f), make_float2(-xk.x, xk.y));   // conj(E - w*O) = conj(2E - xk)
 }
 
 }  // namespace b2a

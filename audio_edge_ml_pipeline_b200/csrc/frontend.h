@@ -43,6 +43,8 @@ cudaError_t launch_front(const FrontParams& p, int log2nc, bool i16, int kind, i
 // specialised n_fft = 512 kernel (logmel512.cu); requires an even hop
 size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc);
 bool logmel512_has_special(int sample_rate, int n_mels);
+int logmel512_ctas_per_sm();     // persistent warp-specialised CTAs per SM (1)
+int logmel512_mel_warps();       // mel (consumer) warps per CTA: table-driven bands are dealt round-robin to them
 cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st);
 
 }  // namespace b2a

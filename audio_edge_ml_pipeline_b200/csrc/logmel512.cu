@@ -1,21 +1,28 @@
 // logmel512.cu — the headline kernel: n_fft = 512 fused log-mel / MFCC front end, sm_100a only.
 //
-// Same arithmetic as frontend.cu (the generic n_fft kernel) but laid out for the 16 x 16
-// decomposition of the 256-point packed FFT:
-//   * one half-warp per frame, 16 complex points per lane in registers for both radix-16 passes;
-//     pass-2 results never leave registers — only the 8 rows the mirror lane needs go through
-//     shared memory (X[k] needs Z[k] and Z[256-k], which lives in lane 16-j);
-//   * the next tile's raw PCM is fetched by one cp.async.bulk (TMA bulk copy, mbarrier
-//     completion) into the other of two ping-pong buffers while the current tile is being
-//     transformed; pass 1 reads the packed int16 pairs directly (one 32-bit word = one complex
-//     point) and widens them in registers, the exact 1/32768 riding on the window;
-//   * power tile is [bin pair][frame] with a 68-word row so the two frames of a warp write
-//     disjoint banks and the mel phase (lane = frame, band warp-uniform) reads it with
-//     conflict-free 64-bit loads; for the headline configuration the band loop is generated at
-//     build time (gen_mel.cpp) with the 490 filter weights as FFMA immediates;
-//   * raw dB goes to the output buffer (L2-resident), per-clip max/min stay in registers, and
-//     the same CTA normalises the clip in place a few microseconds later (mfcc: in-tile DCT-II,
-//     recomputed from an L2 scratch only when the top_db clip engages, then a z-score per row).
+// One persistent, warp-specialised CTA per SM (640 threads):
+//   * 16 FFT warps (setmaxnreg 112).  One half-warp per frame, 16 complex points per lane in
+//     registers for both radix-16 passes of the 256-point packed FFT, all complex arithmetic in
+//     packed FP32 (FADD2 / FMUL2 / FFMA2, fft_core.cuh).  Pass 1 reads the packed int16 pairs
+//     straight from the raw PCM tile (one 32-bit word = one complex point) and widens them in
+//     registers, the exact 1/32768 riding on the window; pass-2 results never leave registers —
+//     only the 8 rows the mirror lane needs go through shared memory (X[k] needs Z[k] and
+//     Z[256-k], which lives in lane 16-j).  4|X|^2 goes to a [bin pair][frame] power tile.
+//     These warps never touch global memory and never meet a CTA-wide barrier.
+//   * 4 mel warps (setmaxnreg 32).  Warp 0's lane 0 is the TMA producer: one cp.async.bulk per
+//     32-frame tile of raw PCM into a 3-deep ring, issued three tiles ahead (also across clip
+//     boundaries).  All four consume power tiles (2-deep ring): lane = frame, band warp-uniform;
+//     for the headline configuration the band sweep is generated at build time (gen_mel.cpp)
+//     with the 490 filter weights as FFMA immediates and every power pair loaded once.  Raw dB
+//     goes to the output buffer (L2-resident), per-clip max/min stay in registers, and after a
+//     clip's last tile the same warps normalise it in place (mfcc: in-tile DCT-II, recomputed
+//     from an L2 scratch only when the top_db clip engages, then a z-score per row).
+//   * Hand-off by mbarriers only: raw_full (TMA tx bytes) -> FFT; pow_full (16 warp arrivals)
+//     -> mel; pow_empty (4 warp arrivals) -> FFT.  pow_full of tile i also tells the producer
+//     that raw slot i % 3 is free again.
+// The FFT phase is FMA-pipe bound; mel, dB, normalisation, staging and every global access now
+// overlap it instead of alternating with it (profiles/: the phase-alternating predecessor spent
+// 58 % of its time in the FFT rounds).
 //
 // Reference arithmetic: deep.py:126-134 (mel), :318-328 (mfcc) via librosa 0.11.0.
 #include "frontend.h"
@@ -29,13 +36,19 @@ namespace b2a {
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kWarps = kThreads / 32;
+constexpr int kFftWarps = 16, kMelWarps = 4;
+constexpr int kThreads = 32 * (kFftWarps + kMelWarps);
+constexpr int kMelThreads = 32 * kMelWarps;
+constexpr int kFftRegs = 104, kMelRegs = 64;    // 512*112 + 128*32 = 640*96 (the launch allocation)
 constexpr int NC = 256, NFFT = 512, F = 32;     // complex points, frame length, frames per tile
+constexpr int ROUNDS = F / (2 * kFftWarps);     // rounds of 2 frames per FFT warp per tile
+constexpr int NRAW = 3, NPOW = 2;               // ring depths: raw PCM tiles, power tiles
 constexpr int XS = 18;                          // exchange row stride (float2): 128-bit pass-1 stores and
 constexpr int XSLOT = 16 * XS + 2;              // 64-bit pass-2 loads are both conflict-free
 constexpr int PROW = 68;                        // power tile: row = 2 adjacent bins x (32 frames + 2 pad)
 constexpr int PROWS = 132;                      // bin pairs (0,1)..(256,257) + 3 zero rows for 8-bin padding
+static_assert(ROUNDS >= 1 && ROUNDS * 2 * kFftWarps == F, "tile must be a whole number of rounds");
+static_assert(B2A_MELSPEC_WARPS == kMelWarps, "regenerate gen/mel_special.inc for this warp count");
 
 __device__ __forceinline__ float db10(float s) {
     // 10*log10(max(amin, s)); the argument is >= 1e-10, never denormal -> lg2.approx.ftz
@@ -78,6 +91,9 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -91,6 +107,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// barrier among the mel warps only (named barrier 1); the FFT warps never stop for it
+__device__ __forceinline__ void mel_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kMelThreads) : "memory");
 }
 
 // sample s of a clip in its storage type; zero (or the reflected sample) outside [0, n)
@@ -106,7 +126,8 @@ __device__ __forceinline__ E raw_sample(const E* clip, int s, int n, int pad_mod
 
 struct Layout {
     int chunk;          // samples staged per tile, multiple of 8
-    int off_raw, off_raw2, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, off_db, total;
+    int raw_bytes;      // bytes of one raw slot (multiple of 16)
+    int off_raw, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, off_db, total;
 };
 
 __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc) {
@@ -114,23 +135,22 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.chunk = (hop * (F - 1) + NFFT + 7) & ~7;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
-    const int esz = i16 ? 2 : 4;                // two raw buffers (ping-pong), read directly by pass 1
-    L.off_raw = take(L.chunk * esz);
-    L.off_raw2 = take(L.chunk * esz);
-    L.off_xch = take(16 * XSLOT * 8);
-    L.off_pow = take(PROWS * PROW * 4);
+    L.raw_bytes = (L.chunk * (i16 ? 2 : 4) + 15) & ~15;
+    L.off_raw = take(NRAW * L.raw_bytes);             // ring of raw PCM tiles, read directly by pass 1
+    L.off_xch = take(2 * kFftWarps * XSLOT * 8);      // one exchange slot per half-warp
+    L.off_pow = take(NPOW * PROWS * PROW * 4);        // ring of power tiles
     L.off_tw2 = take(8 * 16 * 8);
     L.off_melw = take(mel_wpad * 4);
     L.off_melk = take(n_mels * 16);
     L.off_red = take(64 * 4);
-    L.off_bar = take(16);
+    L.off_bar = take((NRAW + 2 * NPOW) * 8);
     L.off_db = take(mfcc ? n_mels * 32 * 4 : 0);      // mfcc: [n_mels][32] dB tile feeding the in-tile DCT
     L.total = o;
     return L;
 }
 
 template <bool I16, int KIND, bool SPEC, bool RAG>
-__global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
+__global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16, KIND == 1);
     float* const s_db = reinterpret_cast<float*>(smem + L.off_db);
@@ -140,12 +160,13 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     float* const s_melw = reinterpret_cast<float*>(smem + L.off_melw);
     int4* const s_desc = reinterpret_cast<int4*>(smem + L.off_melk);
     float* const s_red = reinterpret_cast<float*>(smem + L.off_red);
-    uint64_t* const s_bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    uint64_t* const bar_raw_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    uint64_t* const bar_pow_full = bar_raw_full + NRAW;
+    uint64_t* const bar_pow_empty = bar_pow_full + NPOW;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int j = lane & 15, h = lane >> 4;
     const int hop = p.hop, n_mels = p.n_mels, chunk = L.chunk;
-    int n = p.n_samples, nfr = p.n_frames;                   // per clip when RAG
+    using E = typename std::conditional<I16, int16_t, float>::type;
 
     // ---- per-CTA tables --------------------------------------------------------------------
     for (int i = tid; i < 128; i += kThreads) {          // s_tw2[r][j] = exp(-i pi (j+16r)/256)
@@ -154,314 +175,316 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
     }
     for (int i = tid; i < p.mel_wpad; i += kThreads) s_melw[i] = p.mel_wq[i];
     for (int i = tid; i < n_mels; i += kThreads) {
-        const int m = p.mel_order[i];                        // position i is served by warp i % 8
+        const int m = p.mel_order[i];                        // position i is served by mel warp i % kMelWarps
         s_desc[i] = make_int4((p.mel_k0e[m] >> 1) * (PROW / 2), p.mel_cnt4[m], p.mel_off4[m], m);
     }
-    for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // bins 256..263
+    for (int b = 0; b < NPOW; ++b)                           // bins 256..263 of every power tile
+        for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[b * PROWS * PROW + 128 * PROW + i] = 0.f;
     if (tid == 0) {
-        mbar_init(s_bar, 1);
+        for (int i = 0; i < NRAW; ++i) mbar_init(bar_raw_full + i, 1);
+        for (int i = 0; i < NPOW; ++i) { mbar_init(bar_pow_full + i, kFftWarps); mbar_init(bar_pow_empty + i, kMelWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-
-    // ---- per-thread constants ----------------------------------------------------------------
-    float2 win[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const int q = j + 16 * t;
-        // int16 path: the exact power-of-two 1/32768 of librosa.load rides on the window
-        const float sc = I16 ? (1.0f / 32768.0f) : 1.0f;
-        win[t] = make_float2(__ldg(p.window + 2 * q) * sc, __ldg(p.window + 2 * q + 1) * sc);
-    }
-    float2 tw1[15];
-#pragma unroll
-    for (int t = 1; t < 16; ++t) tw1[t - 1] = p.tw[t * j];
-    float2* const xs = s_xch + (2 * warp + h) * XSLOT;       // this frame's exchange slot
-    float4* const x1 = reinterpret_cast<float4*>(xs + XS * j);   // pass-1 store base (row j, 2 points per store)
-    float2* const x2 = xs + j;                               // pass-2 load base (column j, stride XS)
-    float2* const mst = xs + j;                              // mirror store base: M[(row-8)*16 + j]
-    const float2* const mld = xs + (j ? 16 - j : 16);        // mirror load base:  M[(7-r)*16 + ...]
-    const float2* const t2 = s_tw2 + j;
     __syncthreads();
+    if (blockIdx.x >= p.n_clips) return;
 
-    using E = typename std::conditional<I16, int16_t, float>::type;
-    constexpr int V = 16 / (int)sizeof(E);                   // samples per 16 bytes
-    const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
-    uint32_t bar_parity = 0;
-    int buf = 0;                                             // which raw buffer holds the current tile
-
-    // Stage tile (clip, t0) into dst.  Aligned zero-padded clips go by one TMA bulk copy (returns
-    // true: completion arrives on s_bar) with the clip's head/tail zero-filled by plain stores;
-    // reflect padding or unaligned clips use plain loads.  Every thread computes the same answer.
-    auto stage_issue = [&](long long clip, int t0, E* dst) -> bool {
-        const int n = RAG ? p.rag_len[clip] : p.n_samples;
-        const long long e0 = RAG ? p.rag_in_off[clip] : clip * (long long)n;
-        const E* cptr = reinterpret_cast<const E*>(p.clips) + e0;
-        const int c0 = t0 * hop - NFFT / 2;
-        const int lo = c0 < 0 ? 0 : c0;
-        const int hi = (c0 + chunk < n) ? c0 + chunk : n;
-        const bool ok = p.pad_mode == 0 && base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
-                        (((lo - c0) & (V - 1)) == 0);
-        if (!ok) {
-            for (int i = tid; i < chunk; i += kThreads) dst[i] = raw_sample<E>(cptr, c0 + i, n, p.pad_mode);
-            return false;
+    if (warp < kFftWarps) {
+        // =========================== FFT warps ===================================================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFftRegs));
+        const int j = lane & 15, h = lane >> 4;
+        float2 win[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int q = j + 16 * t;
+            // int16 path: the exact power-of-two 1/32768 of librosa.load rides on the window
+            const float sc = I16 ? (1.0f / 32768.0f) : 1.0f;
+            win[t] = make_float2(__ldg(p.window + 2 * q) * sc, __ldg(p.window + 2 * q + 1) * sc);
         }
-        const int nb = ((hi - lo) / V) * V;                  // bulk part, whole 16-byte units
-        const int head = lo - c0;                            // [0, head) and [head+nb, chunk) are not
-        for (int i = tid; i < head; i += kThreads) dst[i] = (E)0;                 // written by the bulk copy
-        for (int i = head + nb + tid; i < chunk; i += kThreads) dst[i] = raw_sample<E>(cptr, c0 + i, n, 0);
-        if (tid == 0 && nb > 0) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // generic reads -> async write
-            mbar_expect_tx(s_bar, (uint32_t)(nb * sizeof(E)));
-            bulk_g2s(dst + head, cptr + lo, (uint32_t)(nb * sizeof(E)), s_bar);
-        }
-        return nb > 0;
-    };
+        float2 tw1[15];
+#pragma unroll
+        for (int t = 1; t < 16; ++t) tw1[t - 1] = p.tw[t * j];
+        float2* const xs = s_xch + (2 * warp + h) * XSLOT;       // this frame's exchange slot
+        float4* const x1 = reinterpret_cast<float4*>(xs + XS * j);   // pass-1 store base (row j, 2 points per store)
+        float2* const x2 = xs + j;                               // pass-2 load base (column j, stride XS)
+        float2* const mst = xs + j;                              // mirror store base: M[(row-8)*16 + j]
+        const float2* const mld = xs + (j ? 16 - j : 16);        // mirror load base:  M[(7-r)*16 + ...]
+        const float2* const t2 = s_tw2 + j;
 
-    long long clip = blockIdx.x;
-    if (clip >= p.n_clips) return;
-    E* const raw0 = reinterpret_cast<E*>(smem + L.off_raw);
-    E* const raw1 = reinterpret_cast<E*>(smem + L.off_raw2);
-    bool inflight = stage_issue(clip, 0, raw0);            // prologue: first tile of the first clip
-
-    for (; clip < p.n_clips; clip += gridDim.x) {
-        if constexpr (RAG) { n = p.rag_len[clip]; nfr = 1 + n / hop; }
-        const int tiles = (nfr + F - 1) / F;
-        float* const outb = RAG ? p.out + p.rag_out_off[clip]
-                                : p.out + (size_t)clip * (KIND == 0 ? n_mels : p.n_mfcc) * nfr;
-        float* inter = (KIND == 0) ? outb : p.inter + (size_t)blockIdx.x * n_mels * p.n_frames;
-        float vmax = -3.0e38f, vmin = 3.0e38f;
-
-        for (int tile = 0; tile < tiles; ++tile) {
-            const int t0 = tile * F;
-            const E* const cur = buf ? raw1 : raw0;
-            // (A) this tile's samples have landed (bulk copy) / are visible (plain stores)
-            if (inflight) { mbar_wait(s_bar, bar_parity); bar_parity ^= 1; }
-            __syncthreads();
-
-            // (D) prefetch the next tile (possibly the next clip's first tile) into the other buffer
-            {
-                long long nclip = clip;
-                int nt0 = t0 + F;
-                if (tile + 1 == tiles) { nclip = clip + gridDim.x; nt0 = 0; }
-                inflight = (nclip < p.n_clips) ? stage_issue(nclip, nt0, buf ? raw0 : raw1) : false;
-                buf ^= 1;
-            }
-
-            // (E) two rounds of 16 frames: window, radix-16, exchange, radix-16, mirror, |X|^2
+        uint32_t it = 0;                                         // tiles this CTA has processed
+        for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
+            const int nfr = RAG ? 1 + p.rag_len[clip] / hop : p.n_frames;
+            const int tiles = (nfr + F - 1) / F;
+            for (int tile = 0; tile < tiles; ++tile, ++it) {
+                const int t0 = tile * F;
+                const uint32_t rb = it % NRAW, pb = it % NPOW;
+                mbar_wait(bar_raw_full + rb, (it / NRAW) & 1);           // this tile's samples have landed
+                const E* const cur = reinterpret_cast<const E*>(smem + L.off_raw + rb * L.raw_bytes);
+                float* const pw = s_pow + pb * (PROWS * PROW);
+                bool pow_free = false;
 #pragma unroll 1
-            for (int r = 0; r < 2; ++r) {
-                if (t0 + 16 * r + 2 * warp >= nfr) continue;        // both frames past the clip's end
-                const int f = 16 * r + 2 * warp + h;
-                float2 v[16];
-                if constexpr (I16) {
-                    // one 32-bit word = one packed complex point (two int16 samples)
-                    const uint32_t* a = reinterpret_cast<const uint32_t*>(cur) + ((f * hop) >> 1) + j;
+                for (int r = 0; r < ROUNDS; ++r) {
+                    const int f0 = 2 * kFftWarps * r + 2 * warp;
+                    if (t0 + f0 >= nfr) break;                          // both frames past the clip's end
+                    const int f = f0 + h;
+                    float2 v[16];
+                    if constexpr (I16) {
+                        // one 32-bit word = one packed complex point (two int16 samples)
+                        const uint32_t* a = reinterpret_cast<const uint32_t*>(cur) + ((f * hop) >> 1) + j;
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const float2 x = cvt_pcm2(a[16 * t]);
-                        v[t] = make_float2(x.x * win[t].x, x.y * win[t].y);
+                        for (int t = 0; t < 16; ++t) v[t] = __fmul2_rn(cvt_pcm2(a[16 * t]), win[t]);
+                    } else {
+                        const float* a = cur + f * hop + 2 * j;
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) v[t] = __fmul2_rn(*reinterpret_cast<const float2*>(a + 32 * t), win[t]);
                     }
-                } else {
-                    const float* a = cur + f * hop + 2 * j;
+                    Dft<16>::run(v);
 #pragma unroll
-                    for (int t = 0; t < 16; ++t) {
-                        const float2 x = *reinterpret_cast<const float2*>(a + 32 * t);
-                        v[t] = make_float2(x.x * win[t].x, x.y * win[t].y);
+                    for (int t = 0; t < 16; t += 2) x1[t >> 1] = make_float4(v[t].x, v[t].y, v[t + 1].x, v[t + 1].y);
+                    __syncwarp();
+                    v[0] = x2[0];
+#pragma unroll
+                    for (int t = 1; t < 16; ++t) v[t] = cmul(x2[XS * t], tw1[t - 1]);
+                    Dft<16>::run(v);                                   // v[t] = Z[j + 16 t]
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 8; t < 16; ++t) mst[(t - 8) * 16] = v[t];
+                    mst[8 * 16] = v[0];                                // "row 16": Z[256] == Z[0] for lane 0
+                    __syncwarp();
+                    if (!pow_free) {                                   // the mel warps are done with this slot
+                        mbar_wait(bar_pow_empty + pb, ((it / NPOW) & 1) ^ 1);
+                        pow_free = true;
                     }
+                    // element (bin k, frame f) lives at word (k>>1)*PROW + 2f + (k&1)
+                    float* pk = pw + (j >> 1) * PROW + 2 * f + (j & 1);                 // bin j + 16 r2
+                    float* pn = pw + ((NC - j) >> 1) * PROW + 2 * f + (j & 1);          // bin 256 - j - 16 r2
+#pragma unroll
+                    for (int r2 = 0; r2 < 8; ++r2) {
+                        const float2 B = mld[(7 - r2) * 16];
+                        float2 xk, xnk;
+                        rfft_split(v[r2], B, t2[16 * r2], xk, xnk);    // 2 X[k], 2 X[256-k]
+                        pk[8 * r2 * PROW] = xk.x * xk.x + xk.y * xk.y;         // 4|X|^2: the 1/4 lives
+                        pn[-8 * r2 * PROW] = xnk.x * xnk.x + xnk.y * xnk.y;    // in the mel weights
+                    }
+                    if (j == 0) pw[(NC / 4) * PROW + 2 * f] = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
+                    __syncwarp();
                 }
-                Dft<16>::run(v);
-#pragma unroll
-                for (int t = 0; t < 16; t += 2) x1[t >> 1] = make_float4(v[t].x, v[t].y, v[t + 1].x, v[t + 1].y);
+                // a warp with no frame in this tile still takes its turn on both barriers: every
+                // pow_full phase must collect exactly one arrival per warp
+                if (!pow_free) mbar_wait(bar_pow_empty + pb, ((it / NPOW) & 1) ^ 1);
                 __syncwarp();
-                v[0] = x2[0];
-#pragma unroll
-                for (int t = 1; t < 16; ++t) v[t] = cmul(x2[XS * t], tw1[t - 1]);
-                Dft<16>::run(v);                                   // v[t] = Z[j + 16 t]
-                __syncwarp();
-#pragma unroll
-                for (int t = 8; t < 16; ++t) mst[(t - 8) * 16] = v[t];
-                mst[8 * 16] = v[0];                                // "row 16": Z[256] == Z[0] for lane 0
-                __syncwarp();
-                // element (bin k, frame f) lives at word (k>>1)*PROW + 2f + (k&1)
-                float* pk = s_pow + (j >> 1) * PROW + 2 * f + (j & 1);                 // bin j + 16 r2
-                float* pn = s_pow + ((NC - j) >> 1) * PROW + 2 * f + (j & 1);          // bin 256 - j - 16 r2
-#pragma unroll
-                for (int r2 = 0; r2 < 8; ++r2) {
-                    const float2 B = mld[(7 - r2) * 16];
-                    float2 xk, xnk;
-                    rfft_split(v[r2], B, t2[16 * r2], xk, xnk);    // 2 X[k], 2 X[256-k]
-                    pk[8 * r2 * PROW] = xk.x * xk.x + xk.y * xk.y;         // 4|X|^2: the 1/4 lives
-                    pn[-8 * r2 * PROW] = xnk.x * xnk.x + xnk.y * xnk.y;    // in the mel weights
-                }
-                if (j == 0) s_pow[(NC / 4) * PROW + 2 * f] = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
-                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pow_full + pb);
             }
-            __syncthreads();                                       // (F) power tile complete
+        }
+    } else {
+        // =========================== mel warps (warp 0 of them also stages the raw tiles) =========
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMelRegs));
+        const int mw = warp - kFftWarps, mtid = tid - 32 * kFftWarps;
+        constexpr int V = 16 / (int)sizeof(E);                   // samples per 16 bytes
+        const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
 
-            // (G) mel bands: lane = frame, warp-uniform band; per 4-bin step one 128-bit broadcast
-            //     weight load and two 64-bit power loads (bands padded with zero weights)
-            {
-                const int t = t0 + lane;
-                const bool valid = t < nfr;
-                float* const outp = inter + t;
-                const float2* pl = reinterpret_cast<const float2*>(s_pow) + lane;
-                if constexpr (SPEC) {
-                    // headline configuration: every band unrolled, weights are FFMA immediates
+        // Stage tile (clip, t0) into raw slot `slot`.  Aligned zero-padded clips go by one TMA bulk
+        // copy with the clip's head/tail zero-filled by plain stores; reflect padding or unaligned
+        // clips use plain loads.  Exactly one arrival on the slot's barrier either way.
+        auto stage = [&](long long clip, int t0, uint32_t slot) {
+            E* const dst = reinterpret_cast<E*>(smem + L.off_raw + slot * L.raw_bytes);
+            uint64_t* const bar = bar_raw_full + slot;
+            const int n = RAG ? p.rag_len[clip] : p.n_samples;
+            const long long e0 = RAG ? p.rag_in_off[clip] : clip * (long long)n;
+            const E* cptr = reinterpret_cast<const E*>(p.clips) + e0;
+            const int c0 = t0 * hop - NFFT / 2;
+            const int lo = c0 < 0 ? 0 : c0;
+            const int hi = (c0 + chunk < n) ? c0 + chunk : n;
+            const bool ok = p.pad_mode == 0 && base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
+                            (((lo - c0) & (V - 1)) == 0);
+            const int nb = ok ? ((hi - lo) / V) * V : 0;         // bulk part, whole 16-byte units
+            if (nb == 0) {
+                for (int i = lane; i < chunk; i += 32) dst[i] = raw_sample<E>(cptr, c0 + i, n, p.pad_mode);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar);
+                return;
+            }
+            const int head = lo - c0;                            // [0, head) and [head+nb, chunk) are not
+            for (int i = lane; i < head; i += 32) dst[i] = (E)0;                 // written by the bulk copy
+            for (int i = head + nb + lane; i < chunk; i += 32) dst[i] = raw_sample<E>(cptr, c0 + i, n, 0);
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses -> async write
+                mbar_expect_tx(bar, (uint32_t)(nb * sizeof(E)));
+                bulk_g2s(dst + head, cptr + lo, (uint32_t)(nb * sizeof(E)), bar);
+            }
+        };
+        // producer cursor: runs NRAW tiles ahead of the consumers
+        long long pclip = blockIdx.x;
+        int ptile = 0;
+        uint32_t pit = 0;
+        auto stage_next = [&]() {
+            if (pclip >= p.n_clips) return;
+            stage(pclip, ptile * F, pit % NRAW);
+            ++pit;
+            const int pnfr = RAG ? 1 + p.rag_len[pclip] / hop : p.n_frames;
+            if (++ptile * F >= pnfr) { ptile = 0; pclip += gridDim.x; }
+        };
+        if (mw == 0)
+            for (int i = 0; i < NRAW; ++i) stage_next();
+
+        uint32_t it = 0;
+        for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
+            const int nfr = RAG ? 1 + p.rag_len[clip] / hop : p.n_frames;
+            const int tiles = (nfr + F - 1) / F;
+            float* const outb = RAG ? p.out + p.rag_out_off[clip]
+                                    : p.out + (size_t)clip * (KIND == 0 ? n_mels : p.n_mfcc) * nfr;
+            float* const inter = (KIND == 0) ? outb : p.inter + (size_t)blockIdx.x * n_mels * p.n_frames;
+            float vmax = -3.0e38f, vmin = 3.0e38f;
+
+            for (int tile = 0; tile < tiles; ++tile, ++it) {
+                const int t0 = tile * F;
+                const uint32_t pb = it % NPOW;
+                mbar_wait(bar_pow_full + pb, (it / NPOW) & 1);     // power tile complete ...
+                if (mw == 0) stage_next();                         // ... and raw slot it % NRAW is free again
+                // mel bands: lane = frame, warp-uniform band
+                {
+                    const int t = t0 + lane;
+                    const bool valid = t < nfr;
+                    float* const outp = inter + t;
+                    const float2* pl = reinterpret_cast<const float2*>(s_pow + pb * (PROWS * PROW)) + lane;
+                    if constexpr (SPEC) {
+                        // headline configuration: every band unrolled, weights are FFMA immediates
 #define B2A_EMIT(M, VAL)                                                            \
     {                                                                               \
         const float vv = db10(VAL);                                                 \
         if (KIND == 1) s_db[(M) * 32 + lane] = vv;                                  \
-        if (valid) { outp[(M) * nfr] = vv; vmax = fmaxf(vmax, vv); vmin = fminf(vmin, vv); } \
+        if (valid) outp[(M) * nfr] = vv;      /* predicated store: the band sweep stays one basic block */ \
+        vmax = fmaxf(vmax, valid ? vv : vmax);                                      \
+        vmin = fminf(vmin, valid ? vv : vmin);                                      \
     }
-                    switch (warp) {
-                        case 0: B2A_MEL_WARP0(pl, B2A_EMIT) break;
-                        case 1: B2A_MEL_WARP1(pl, B2A_EMIT) break;
-                        case 2: B2A_MEL_WARP2(pl, B2A_EMIT) break;
-                        case 3: B2A_MEL_WARP3(pl, B2A_EMIT) break;
-                        case 4: B2A_MEL_WARP4(pl, B2A_EMIT) break;
-                        case 5: B2A_MEL_WARP5(pl, B2A_EMIT) break;
-                        case 6: B2A_MEL_WARP6(pl, B2A_EMIT) break;
-                        default: B2A_MEL_WARP7(pl, B2A_EMIT) break;
-                    }
+                        switch (mw) {
+                            case 0: B2A_MEL_WARP0(pl, B2A_EMIT) break;
+                            case 1: B2A_MEL_WARP1(pl, B2A_EMIT) break;
+                            case 2: B2A_MEL_WARP2(pl, B2A_EMIT) break;
+                            default: B2A_MEL_WARP3(pl, B2A_EMIT) break;
+                        }
 #undef B2A_EMIT
-                } else {
-                    for (int i = warp; i < n_mels; i += kWarps) {
-                        const int4 d = s_desc[i];      // {pair-row offset (float2), n 4-bin steps, weight offset, m*nfr}
-                        const float2* pr = pl + d.x;
-                        const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+                    } else {
+                        // per 4-bin step one 128-bit broadcast weight load and two 64-bit power
+                        // loads (bands padded with zero weights)
+                        for (int i = mw; i < n_mels; i += kMelWarps) {
+                            const int4 d = s_desc[i];      // {pair-row offset (float2), n 4-bin steps, weight offset, m}
+                            const float2* pr = pl + d.x;
+                            const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
+                            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 1
-                        for (int q4 = 0; q4 < d.y; ++q4) {
-                            const float4 w = *wq++;
-                            const float2 p0 = pr[0], p1 = pr[PROW / 2];
-                            a0 = fmaf(w.x, p0.x, a0);
-                            a1 = fmaf(w.y, p0.y, a1);
-                            a2 = fmaf(w.z, p1.x, a2);
-                            a3 = fmaf(w.w, p1.y, a3);
-                            pr += PROW;
+                            for (int q4 = 0; q4 < d.y; ++q4) {
+                                const float4 w = *wq++;
+                                const float2 p0 = pr[0], p1 = pr[PROW / 2];
+                                a0 = fmaf(w.x, p0.x, a0);
+                                a1 = fmaf(w.y, p0.y, a1);
+                                a2 = fmaf(w.z, p1.x, a2);
+                                a3 = fmaf(w.w, p1.y, a3);
+                                pr += PROW;
+                            }
+                            const float vv = db10((a0 + a1) + (a2 + a3));
+                            if (KIND == 1) s_db[d.w * 32 + lane] = vv;
+                            if (valid) {
+                                outp[d.w * nfr] = vv;
+                                vmax = fmaxf(vmax, vv);
+                                vmin = fminf(vmin, vv);
+                            }
                         }
-                        const float vv = db10((a0 + a1) + (a2 + a3));
-                        if (KIND == 1) s_db[d.w * 32 + lane] = vv;
-                        if (valid) {
-                            outp[d.w * nfr] = vv;
-                            vmax = fmaxf(vmax, vv);
-                            vmin = fminf(vmin, vv);
-                        }
                     }
                 }
-            }
-            if constexpr (KIND == 1) {
-                // (H) DCT-II of this tile straight from shared memory, assuming the top_db clip
-                //     (known only after the clip's last tile) will not engage; checked below.
-                __syncthreads();
-                for (int i = tid; i < p.n_mfcc * 32; i += kThreads) {
-                    const int k = i >> 5, f = i & 31, t = t0 + f;
-                    const float* d = p.dct + (size_t)k * n_mels;
-                    float a0 = 0.f, a1 = 0.f;
-                    int m = 0;
-                    for (; m + 1 < n_mels; m += 2) {
-                        a0 = fmaf(__ldg(d + m), s_db[m * 32 + f], a0);
-                        a1 = fmaf(__ldg(d + m + 1), s_db[(m + 1) * 32 + f], a1);
-                    }
-                    if (m < n_mels) a0 = fmaf(__ldg(d + m), s_db[m * 32 + f], a0);
-                    if (t < nfr) outb[(size_t)k * nfr + t] = a0 + a1;
-                }
-            }
-        }
-
-        // ---- per-clip reductions ---------------------------------------------------------------
-        vmax = warp_max(vmax); vmin = warp_min(vmin);
-        if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
-        __syncthreads();
-        {
-            const float a = (lane < kWarps) ? s_red[lane] : -3.0e38f;
-            const float b = (lane < kWarps) ? s_red[32 + lane] : 3.0e38f;
-            vmax = warp_max(a); vmin = warp_min(b);
-        }
-        if constexpr (KIND == 0) {
-            const float lo = fmaxf(vmin - vmax, -p.top_db);
-            const float range = (0.0f - lo) + 1e-8f;
-            const float inv = __frcp_rn(range);
-            // x / range by one Newton step on x * (1/range): correctly rounded for these operand
-            // ranges (so the clip's peak is exactly 1.0, as with numpy's true division)
-            auto nrm = [&](float x) {
-                const float num = fmaxf(x - vmax, -p.top_db) - lo;
-                const float q = num * inv;
-                return fmaf(fmaf(-q, range, num), inv, q);
-            };
-            const int total = n_mels * nfr;
-            if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(inter) & 15) == 0)) {
-                float4* o4 = reinterpret_cast<float4*>(inter);
-                for (int i = tid; i < total / 4; i += kThreads) {
-                    float4 x = o4[i];
-                    x.x = nrm(x.x);
-                    x.y = nrm(x.y);
-                    x.z = nrm(x.z);
-                    x.w = nrm(x.w);
-                    o4[i] = x;
-                }
-            } else {
-                for (int i = tid; i < total; i += kThreads)
-                    inter[i] = nrm(inter[i]);
-            }
-        } else {
-            float* outc = outb;
-            const float thr = vmax - p.top_db;
-            if (vmin < thr) {
-                // rare: some band fell more than top_db below the clip's peak, so the clipped dB differ
-                // from what the in-tile DCT saw -> recompute from the raw-dB scratch (L2 resident)
-                float* s_l = s_pow;                               // [n_mels][32] clipped dB tile
-                for (int t0 = 0; t0 < nfr; t0 += 32) {
-                    __syncthreads();
-                    for (int i = tid; i < n_mels * 32; i += kThreads) {
-                        const int m = i >> 5, f = i & 31, t = t0 + f;
-                        s_l[i] = (t < nfr) ? fmaxf(inter[(size_t)m * nfr + t], thr) : 0.f;
-                    }
-                    __syncthreads();
-                    for (int i = tid; i < p.n_mfcc * 32; i += kThreads) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pow_empty + pb);    // the FFT warps may refill this slot
+                if constexpr (KIND == 1) {
+                    // DCT-II of this tile straight from shared memory, assuming the top_db clip
+                    // (known only after the clip's last tile) will not engage; checked below.
+                    mel_sync();
+                    for (int i = mtid; i < p.n_mfcc * 32; i += kMelThreads) {
                         const int k = i >> 5, f = i & 31, t = t0 + f;
                         const float* d = p.dct + (size_t)k * n_mels;
-                        float acc = 0.f;
-#pragma unroll 4
-                        for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(d + m), s_l[m * 32 + f], acc);
-                        if (t < nfr) outc[(size_t)k * nfr + t] = acc;
+                        float a0 = 0.f, a1 = 0.f;
+                        int m = 0;
+                        for (; m + 1 < n_mels; m += 2) {
+                            a0 = fmaf(__ldg(d + m), s_db[m * 32 + f], a0);
+                            a1 = fmaf(__ldg(d + m + 1), s_db[(m + 1) * 32 + f], a1);
+                        }
+                        if (m < n_mels) a0 = fmaf(__ldg(d + m), s_db[m * 32 + f], a0);
+                        if (t < nfr) outb[(size_t)k * nfr + t] = a0 + a1;
                     }
+                    mel_sync();                                    // s_db is rewritten by the next tile
                 }
-                __syncthreads();
-                for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[128 * PROW + i] = 0.f;   // s_l reuse
             }
-            __syncthreads();                                      // in-tile DCT stores visible CTA-wide
-            // deep.py:326-328: per-row z-score.  Rows up to 32*ZR frames stay in registers (one L2
-            // sweep, ZR independent loads in flight); longer rows take the three-sweep form.
-            constexpr int ZR = 24;
-            const float fn = (float)nfr;
-            for (int k = warp; k < p.n_mfcc; k += kWarps) {
-                float* row = outc + (size_t)k * nfr;
-                const float x0 = row[0];
-                if (nfr <= 32 * ZR) {
-                    float x[ZR];
-                    float s_ = 0.f;
-#pragma unroll
-                    for (int u = 0; u < ZR; ++u) {
-                        const int t = lane + 32 * u;
-                        x[u] = (t < nfr) ? row[t] : x0;
+
+            // ---- per-clip reductions (mel warps only) ----------------------------------------------
+            vmax = warp_max(vmax); vmin = warp_min(vmin);
+            if (lane == 0) { s_red[mw] = vmax; s_red[32 + mw] = vmin; }
+            mel_sync();                                            // also: every warp's raw dB stores are visible
+            {
+                const float a = (lane < kMelWarps) ? s_red[lane] : -3.0e38f;
+                const float b = (lane < kMelWarps) ? s_red[32 + lane] : 3.0e38f;
+                vmax = warp_max(a); vmin = warp_min(b);
+            }
+            if constexpr (KIND == 0) {
+                const float lo = fmaxf(vmin - vmax, -p.top_db);
+                const float range = (0.0f - lo) + 1e-8f;
+                const float inv = __frcp_rn(range);
+                // x / range by one Newton step on x * (1/range): correctly rounded for these operand
+                // ranges (so the clip's peak is exactly 1.0, as with numpy's true division)
+                auto nrm = [&](float x) {
+                    const float num = fmaxf(x - vmax, -p.top_db) - lo;
+                    const float q = num * inv;
+                    return fmaf(fmaf(-q, range, num), inv, q);
+                };
+                const int total = n_mels * nfr;
+                if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(inter) & 15) == 0)) {
+                    float4* o4 = reinterpret_cast<float4*>(inter);
+                    const int n4 = total / 4;
+                    int i = mtid;
+                    for (; i + 3 * kMelThreads < n4; i += 4 * kMelThreads) {   // 4 independent L2 round trips in flight
+                        float4 x0 = o4[i], x1 = o4[i + kMelThreads], x2 = o4[i + 2 * kMelThreads], x3 = o4[i + 3 * kMelThreads];
+                        x0.x = nrm(x0.x); x0.y = nrm(x0.y); x0.z = nrm(x0.z); x0.w = nrm(x0.w);
+                        x1.x = nrm(x1.x); x1.y = nrm(x1.y); x1.z = nrm(x1.z); x1.w = nrm(x1.w);
+                        x2.x = nrm(x2.x); x2.y = nrm(x2.y); x2.z = nrm(x2.z); x2.w = nrm(x2.w);
+                        x3.x = nrm(x3.x); x3.y = nrm(x3.y); x3.z = nrm(x3.z); x3.w = nrm(x3.w);
+                        o4[i] = x0; o4[i + kMelThreads] = x1; o4[i + 2 * kMelThreads] = x2; o4[i + 3 * kMelThreads] = x3;
                     }
-#pragma unroll
-                    for (int u = 0; u < ZR; ++u) s_ += x[u] - x0;       // padding lanes contribute 0
-                    const float mean = x0 + __fdiv_rn(warp_sum(s_), fn);
-                    float ss = 0.f;
-#pragma unroll
-                    for (int u = 0; u < ZR; ++u) {
-                        const float d = x[u] - mean;
-                        if (lane + 32 * u < nfr) ss = fmaf(d, d, ss);
-                    }
-                    const float sd = sqrtf(__fdiv_rn(warp_sum(ss), fn)) + 1e-8f;
-#pragma unroll
-                    for (int u = 0; u < ZR; ++u) {
-                        const int t = lane + 32 * u;
-                        if (t < nfr) row[t] = __fdiv_rn(x[u] - mean, sd);
+                    for (; i < n4; i += kMelThreads) {
+                        float4 x = o4[i];
+                        x.x = nrm(x.x); x.y = nrm(x.y); x.z = nrm(x.z); x.w = nrm(x.w);
+                        o4[i] = x;
                     }
                 } else {
+                    for (int i = mtid; i < total; i += kMelThreads) inter[i] = nrm(inter[i]);
+                }
+            } else {
+                float* outc = outb;
+                const float thr = vmax - p.top_db;
+                if (vmin < thr) {
+                    // rare: some band fell more than top_db below the clip's peak, so the clipped dB differ
+                    // from what the in-tile DCT saw -> recompute from the raw-dB scratch (L2 resident)
+                    float* s_l = s_db;                                // [n_mels][32] clipped dB tile
+                    for (int t0 = 0; t0 < nfr; t0 += 32) {
+                        mel_sync();
+                        for (int i = mtid; i < n_mels * 32; i += kMelThreads) {
+                            const int m = i >> 5, f = i & 31, t = t0 + f;
+                            s_l[i] = (t < nfr) ? fmaxf(inter[(size_t)m * nfr + t], thr) : 0.f;
+                        }
+                        mel_sync();
+                        for (int i = mtid; i < p.n_mfcc * 32; i += kMelThreads) {
+                            const int k = i >> 5, f = i & 31, t = t0 + f;
+                            const float* d = p.dct + (size_t)k * n_mels;
+                            float acc = 0.f;
+#pragma unroll 4
+                            for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(d + m), s_l[m * 32 + f], acc);
+                            if (t < nfr) outc[(size_t)k * nfr + t] = acc;
+                        }
+                    }
+                }
+                mel_sync();                                           // DCT stores visible to every mel warp
+                // deep.py:326-328: per-row z-score, three sweeps over an L2-resident row
+                const float fn = (float)nfr;
+                for (int k = mw; k < p.n_mfcc; k += kMelWarps) {
+                    float* row = outc + (size_t)k * nfr;
+                    const float x0 = row[0];
                     float s_ = 0.f;
                     for (int t = lane; t < nfr; t += 32) s_ += row[t] - x0;
                     const float mean = x0 + __fdiv_rn(warp_sum(s_), fn);
@@ -471,8 +494,8 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
                     for (int t = lane; t < nfr; t += 32) row[t] = __fdiv_rn(row[t] - mean, sd);
                 }
             }
+            mel_sync();                                               // s_red / s_db are reused by the next clip
         }
-        __syncthreads();
     }
 }
 
@@ -481,6 +504,9 @@ __global__ void __launch_bounds__(kThreads, 2) logmel512_kernel(FrontParams p) {
 size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc) {
     return (size_t)make_layout(hop, n_mels, mel_wpad, i16, mfcc).total + 128;
 }
+
+int logmel512_ctas_per_sm() { return 1; }
+int logmel512_mel_warps() { return kMelWarps; }
 
 bool logmel512_has_special(int sample_rate, int n_mels) {
     return sample_rate == B2A_MELSPEC_SR && n_mels == B2A_MELSPEC_NMELS && B2A_MELSPEC_NFFT == NFFT;
