@@ -42,7 +42,10 @@ constexpr int kMelThreads = 32 * kMelWarps;
 constexpr int kFftRegs = 104, kMelRegs = 64;    // 512*112 + 128*32 = 640*96 (the launch allocation)
 constexpr int NC = 256, NFFT = 512, F = 32;     // complex points, frame length, frames per tile
 constexpr int ROUNDS = F / (2 * kFftWarps);     // rounds of 2 frames per FFT warp per tile
-constexpr int NRAW = 3, NPOW = 2;               // ring depths: raw PCM tiles, power tiles
+constexpr int NRAW = 3;                         // ring depth of raw PCM tiles
+// ring depth of power tiles: 3 absorbs the mel warps' per-clip normalisation pause; float32 input
+// doubles the raw ring, leaving room for 2
+__host__ __device__ constexpr int npow(bool i16) { return i16 ? 3 : 2; }
 constexpr int XS = 18;                          // exchange row stride (float2): 128-bit pass-1 stores and
 constexpr int XSLOT = 16 * XS + 2;              // 64-bit pass-2 loads are both conflict-free
 constexpr int PROW = 68;                        // power tile: row = 2 adjacent bins x (32 frames + 2 pad)
@@ -138,12 +141,12 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.raw_bytes = (L.chunk * (i16 ? 2 : 4) + 15) & ~15;
     L.off_raw = take(NRAW * L.raw_bytes);             // ring of raw PCM tiles, read directly by pass 1
     L.off_xch = take(2 * kFftWarps * XSLOT * 8);      // one exchange slot per half-warp
-    L.off_pow = take(NPOW * PROWS * PROW * 4);        // ring of power tiles
+    L.off_pow = take(npow(i16) * PROWS * PROW * 4);   // ring of power tiles
     L.off_tw2 = take(8 * 16 * 8);
     L.off_melw = take(mel_wpad * 4);
     L.off_melk = take(n_mels * 16);
     L.off_red = take(64 * 4);
-    L.off_bar = take((NRAW + 2 * NPOW) * 8);
+    L.off_bar = take((NRAW + 2 * 3) * 8);
     L.off_db = take(mfcc ? n_mels * 32 * 4 : 0);      // mfcc: [n_mels][32] dB tile feeding the in-tile DCT
     L.total = o;
     return L;
@@ -162,16 +165,17 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
     float* const s_red = reinterpret_cast<float*>(smem + L.off_red);
     uint64_t* const bar_raw_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* const bar_pow_full = bar_raw_full + NRAW;
-    uint64_t* const bar_pow_empty = bar_pow_full + NPOW;
+    uint64_t* const bar_pow_empty = bar_pow_full + 3;
 
+    constexpr int NPOW = npow(I16);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hop = p.hop, n_mels = p.n_mels, chunk = L.chunk;
     using E = typename std::conditional<I16, int16_t, float>::type;
 
     // ---- per-CTA tables --------------------------------------------------------------------
-    for (int i = tid; i < 128; i += kThreads) {          // s_tw2[r][j] = exp(-i pi (j+16r)/256)
-        const int r = i >> 4, jj = i & 15;
-        s_tw2[i] = p.tw2[jj + 16 * r];
+    for (int i = tid; i < 128; i += kThreads) {          // s_tw2[r/2][j][r&1] = exp(-i pi (j+16r)/256): the split
+        const int r = i >> 4, jj = i & 15;               // step reads two twiddles per conflict-free 128-bit load
+        s_tw2[(r >> 1) * 32 + jj * 2 + (r & 1)] = p.tw2[jj + 16 * r];
     }
     for (int i = tid; i < p.mel_wpad; i += kThreads) s_melw[i] = p.mel_wq[i];
     for (int i = tid; i < n_mels; i += kThreads) {
@@ -208,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
         float2* const x2 = xs + j;                               // pass-2 load base (column j, stride XS)
         float2* const mst = xs + j;                              // mirror store base: M[(row-8)*16 + j]
         const float2* const mld = xs + (j ? 16 - j : 16);        // mirror load base:  M[(7-r)*16 + ...]
-        const float2* const t2 = s_tw2 + j;
+        const float4* const t2 = reinterpret_cast<const float4*>(s_tw2) + j;
 
         uint32_t it = 0;                                         // tiles this CTA has processed
         for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
@@ -260,8 +264,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
 #pragma unroll
                     for (int r2 = 0; r2 < 8; ++r2) {
                         const float2 B = mld[(7 - r2) * 16];
+                        float4 w4;
+                        if ((r2 & 1) == 0) w4 = t2[16 * (r2 >> 1)];
+                        const float2 w = (r2 & 1) ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);
                         float2 xk, xnk;
-                        rfft_split(v[r2], B, t2[16 * r2], xk, xnk);    // 2 X[k], 2 X[256-k]
+                        rfft_split(v[r2], B, w, xk, xnk);              // 2 X[k], 2 X[256-k]
                         pk[8 * r2 * PROW] = xk.x * xk.x + xk.y * xk.y;         // 4|X|^2: the 1/4 lives
                         pn[-8 * r2 * PROW] = xnk.x * xnk.x + xnk.y * xnk.y;    // in the mel weights
                     }
@@ -327,6 +334,26 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
         if (mw == 0)
             for (int i = 0; i < NRAW; ++i) stage_next();
 
+        // Deferred normalisation (mel): the previous clip is rewritten in place a slice per tile of
+        // the current one, its raw dB (L2) prefetched into registers BEFORE the wait for the power
+        // tile, so the L2 round trip hides behind that wait and the band sweep.
+        constexpr int NPF = 3;                                   // float4 per thread per tile
+        float4* nq = nullptr;                                    // previous clip's features, as float4
+        int nq_n4 = 0, nq_done = 0;                              // float4 count, float4 already rewritten
+        float nq_vmax = 0.f, nq_lo = 0.f, nq_range = 1.f, nq_inv = 1.f;
+        auto nrm = [&](float x) {
+            // x / range by one Newton step on x * (1/range): correctly rounded for these operand
+            // ranges (so the clip's peak is exactly 1.0, as with numpy's true division)
+            const float num = fmaxf(x - nq_vmax, -p.top_db) - nq_lo;
+            const float q = num * nq_inv;
+            return fmaf(fmaf(-q, nq_range, num), nq_inv, q);
+        };
+        auto nrm4 = [&](float4 x) { return make_float4(nrm(x.x), nrm(x.y), nrm(x.z), nrm(x.w)); };
+        auto nq_finish = [&]() {                                 // whatever is left of the previous clip
+            for (int i = nq_done + mtid; i < nq_n4; i += kMelThreads) nq[i] = nrm4(nq[i]);
+            nq_done = nq_n4;
+        };
+
         uint32_t it = 0;
         for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
             const int nfr = RAG ? 1 + p.rag_len[clip] / hop : p.n_frames;
@@ -339,6 +366,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
             for (int tile = 0; tile < tiles; ++tile, ++it) {
                 const int t0 = tile * F;
                 const uint32_t pb = it % NPOW;
+                float4 nx[NPF];
+                const bool nq_live = KIND == 0 && nq_done < nq_n4;
+                if (nq_live) {
+#pragma unroll
+                    for (int k = 0; k < NPF; ++k) {
+                        const int i = nq_done + mtid + k * kMelThreads;
+                        if (i < nq_n4) nx[k] = nq[i];
+                    }
+                }
                 mbar_wait(bar_pow_full + pb, (it / NPOW) & 1);     // power tile complete ...
                 if (mw == 0) stage_next();                         // ... and raw slot it % NRAW is free again
                 // mel bands: lane = frame, warp-uniform band
@@ -348,6 +384,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     float* const outp = inter + t;
                     const float2* pl = reinterpret_cast<const float2*>(s_pow + pb * (PROWS * PROW)) + lane;
                     if constexpr (SPEC) {
+                        const uint32_t pla = smem_u32(pl);
+#define B2A_LDS2(DST, ADDR, OFF) \
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(DST.x), "=f"(DST.y) : "r"(ADDR), "n"(OFF))
                         // headline configuration: every band unrolled, weights are FFMA immediates
 #define B2A_EMIT(M, VAL)                                                            \
     {                                                                               \
@@ -358,12 +397,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
         vmin = fminf(vmin, valid ? vv : vmin);                                      \
     }
                         switch (mw) {
-                            case 0: B2A_MEL_WARP0(pl, B2A_EMIT) break;
-                            case 1: B2A_MEL_WARP1(pl, B2A_EMIT) break;
-                            case 2: B2A_MEL_WARP2(pl, B2A_EMIT) break;
-                            default: B2A_MEL_WARP3(pl, B2A_EMIT) break;
+                            case 0: B2A_MEL_WARP0(pla, B2A_EMIT) break;
+                            case 1: B2A_MEL_WARP1(pla, B2A_EMIT) break;
+                            case 2: B2A_MEL_WARP2(pla, B2A_EMIT) break;
+                            default: B2A_MEL_WARP3(pla, B2A_EMIT) break;
                         }
 #undef B2A_EMIT
+#undef B2A_LDS2
                     } else {
                         // per 4-bin step one 128-bit broadcast weight load and two 64-bit power
                         // loads (bands padded with zero weights)
@@ -394,6 +434,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_pow_empty + pb);    // the FFT warps may refill this slot
+                if (nq_live) {
+#pragma unroll
+                    for (int k = 0; k < NPF; ++k) {
+                        const int i = nq_done + mtid + k * kMelThreads;
+                        if (i < nq_n4) nq[i] = nrm4(nx[k]);
+                    }
+                    nq_done += NPF * kMelThreads;
+                    if (tile + 1 == tiles) nq_finish();            // short clip after a long one
+                }
                 if constexpr (KIND == 1) {
                     // DCT-II of this tile straight from shared memory, assuming the top_db clip
                     // (known only after the clip's last tile) will not engage; checked below.
@@ -424,36 +473,19 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                 vmax = warp_max(a); vmin = warp_min(b);
             }
             if constexpr (KIND == 0) {
-                const float lo = fmaxf(vmin - vmax, -p.top_db);
-                const float range = (0.0f - lo) + 1e-8f;
-                const float inv = __frcp_rn(range);
-                // x / range by one Newton step on x * (1/range): correctly rounded for these operand
-                // ranges (so the clip's peak is exactly 1.0, as with numpy's true division)
-                auto nrm = [&](float x) {
-                    const float num = fmaxf(x - vmax, -p.top_db) - lo;
-                    const float q = num * inv;
-                    return fmaf(fmaf(-q, range, num), inv, q);
-                };
+                nq_finish();                                          // (only if this clip had no tile)
+                nq_vmax = vmax;
+                nq_lo = fmaxf(vmin - vmax, -p.top_db);
+                nq_range = (0.0f - nq_lo) + 1e-8f;
+                nq_inv = __frcp_rn(nq_range);
                 const int total = n_mels * nfr;
                 if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(inter) & 15) == 0)) {
-                    float4* o4 = reinterpret_cast<float4*>(inter);
-                    const int n4 = total / 4;
-                    int i = mtid;
-                    for (; i + 3 * kMelThreads < n4; i += 4 * kMelThreads) {   // 4 independent L2 round trips in flight
-                        float4 x0 = o4[i], x1 = o4[i + kMelThreads], x2 = o4[i + 2 * kMelThreads], x3 = o4[i + 3 * kMelThreads];
-                        x0.x = nrm(x0.x); x0.y = nrm(x0.y); x0.z = nrm(x0.z); x0.w = nrm(x0.w);
-                        x1.x = nrm(x1.x); x1.y = nrm(x1.y); x1.z = nrm(x1.z); x1.w = nrm(x1.w);
-                        x2.x = nrm(x2.x); x2.y = nrm(x2.y); x2.z = nrm(x2.z); x2.w = nrm(x2.w);
-                        x3.x = nrm(x3.x); x3.y = nrm(x3.y); x3.z = nrm(x3.z); x3.w = nrm(x3.w);
-                        o4[i] = x0; o4[i + kMelThreads] = x1; o4[i + 2 * kMelThreads] = x2; o4[i + 3 * kMelThreads] = x3;
-                    }
-                    for (; i < n4; i += kMelThreads) {
-                        float4 x = o4[i];
-                        x.x = nrm(x.x); x.y = nrm(x.y); x.z = nrm(x.z); x.w = nrm(x.w);
-                        o4[i] = x;
-                    }
+                    nq = reinterpret_cast<float4*>(inter);            // rewritten during the next clip's tiles
+                    nq_n4 = total / 4;
+                    nq_done = 0;
                 } else {
                     for (int i = mtid; i < total; i += kMelThreads) inter[i] = nrm(inter[i]);
+                    nq_n4 = nq_done = 0;
                 }
             } else {
                 float* outc = outb;
@@ -496,6 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
             }
             mel_sync();                                               // s_red / s_db are reused by the next clip
         }
+        if constexpr (KIND == 0) nq_finish();                         // the CTA's last clip
     }
 }
 
