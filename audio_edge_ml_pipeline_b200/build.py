@@ -35,6 +35,7 @@ def _fingerprint() -> str:
         if p.is_file():
             h.update(p.name.encode())
             h.update(p.read_bytes())
+    h.update(os.environ.get("B2A_NVCC_EXTRA", "").encode())
     return h.hexdigest()
 
 
@@ -56,7 +57,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     tgt = CSRC / "gen" / "mel_special.inc"
     if not tgt.exists() or tgt.read_text() != inc:
         tgt.write_text(inc)
-    flags = list(NVCC_FLAGS)
+    flags = list(NVCC_FLAGS) + os.environ.get("B2A_NVCC_EXTRA", "").split()
     procs = []
     objs = []
     for src in SOURCES:

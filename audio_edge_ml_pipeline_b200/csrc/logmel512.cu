@@ -34,6 +34,13 @@
 
 namespace b2a {
 
+#ifdef B2A_TRACE   // debugging aid (tools/trace_ws.py): clock64 stamps of CTA 0's hand-offs, never in a product build
+__device__ long long g_trace[8 * 512];
+#define B2A_STAMP(SLOT, K) do { if (blockIdx.x == 0 && lane == 0 && (K) < 512u) g_trace[(SLOT) * 512 + (K)] = clock64(); } while (0)
+#else
+#define B2A_STAMP(SLOT, K) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int kFftWarps = 16, kMelWarps = 4;
@@ -42,10 +49,10 @@ constexpr int kMelThreads = 32 * kMelWarps;
 constexpr int kFftRegs = 104, kMelRegs = 64;    // 512*112 + 128*32 = 640*96 (the launch allocation)
 constexpr int NC = 256, NFFT = 512, F = 32;     // complex points, frame length, frames per tile
 constexpr int ROUNDS = F / (2 * kFftWarps);     // rounds of 2 frames per FFT warp per tile
-constexpr int NRAW = 3;                         // ring depth of raw PCM tiles
+constexpr int NRAW = 4;                         // ring depth of raw PCM tiles
 // ring depth of power tiles: 3 absorbs the mel warps' per-clip normalisation pause; float32 input
 // doubles the raw ring, leaving room for 2
-__host__ __device__ constexpr int npow(bool i16) { return i16 ? 3 : 2; }
+__host__ __device__ constexpr int npow(bool i16) { return i16 ? 2 : 2; }
 constexpr int XS = 18;                          // exchange row stride (float2): 128-bit pass-1 stores and
 constexpr int XSLOT = 16 * XS + 2;              // 64-bit pass-2 loads are both conflict-free
 constexpr int PROW = 68;                        // power tile: row = 2 adjacent bins x (32 frames + 2 pad)
@@ -221,10 +228,14 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
             for (int tile = 0; tile < tiles; ++tile, ++it) {
                 const int t0 = tile * F;
                 const uint32_t rb = it % NRAW, pb = it % NPOW;
+                if (warp == 0) B2A_STAMP(1, it);
+                if (warp == kFftWarps - 1) B2A_STAMP(3, it);
                 mbar_wait(bar_raw_full + rb, (it / NRAW) & 1);           // this tile's samples have landed
+                if (warp == 0) B2A_STAMP(2, it);
+                if (warp == kFftWarps - 1) B2A_STAMP(4, it);
+                bool pow_free = false;
                 const E* const cur = reinterpret_cast<const E*>(smem + L.off_raw + rb * L.raw_bytes);
                 float* const pw = s_pow + pb * (PROWS * PROW);
-                bool pow_free = false;
 #pragma unroll 1
                 for (int r = 0; r < ROUNDS; ++r) {
                     const int f0 = 2 * kFftWarps * r + 2 * warp;
@@ -326,6 +337,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
         uint32_t pit = 0;
         auto stage_next = [&]() {
             if (pclip >= p.n_clips) return;
+            B2A_STAMP(0, pit);
             stage(pclip, ptile * F, pit % NRAW);
             ++pit;
             const int pnfr = RAG ? 1 + p.rag_len[pclip] / hop : p.n_frames;
@@ -375,7 +387,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                         if (i < nq_n4) nx[k] = nq[i];
                     }
                 }
+                if (mw == 0) B2A_STAMP(5, it);
                 mbar_wait(bar_pow_full + pb, (it / NPOW) & 1);     // power tile complete ...
+                if (mw == 0) B2A_STAMP(6, it);
                 if (mw == 0) stage_next();                         // ... and raw slot it % NRAW is free again
                 // mel bands: lane = frame, warp-uniform band
                 {
@@ -569,3 +583,10 @@ cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid,
 }
 
 }  // namespace b2a
+
+#ifdef B2A_TRACE
+extern "C" int b2a_debug_trace_read(long long* out, int n) {
+    if (n > 8 * 512) n = 8 * 512;
+    return (int)cudaMemcpyFromSymbol(out, b2a::g_trace, sizeof(long long) * n);
+}
+#endif
