@@ -52,7 +52,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     gen = objdir / "gen_mel"
     subprocess.run(["g++", "-O2", "-std=c++17", str(CSRC / "gen_mel.cpp"), str(CSRC / "tables.cpp"), "-o", str(gen)],
                    check=True)
-    inc = subprocess.run([str(gen), "16000", "512", "40", "4"], check=True, capture_output=True, text=True).stdout
+    inc = subprocess.run([str(gen), "16000", "512", "40", "4", "13"], check=True, capture_output=True, text=True).stdout
     (CSRC / "gen").mkdir(exist_ok=True)
     tgt = CSRC / "gen" / "mel_special.inc"
     if not tgt.exists() or tgt.read_text() != inc:

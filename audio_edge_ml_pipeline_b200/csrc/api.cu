@@ -245,7 +245,7 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
             }
             h->mel_wpad = (int)wq.size();
             const size_t smem512 = b2a::logmel512_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad,
-                                                             cfg->input_dtype == B2A_IN_I16, mfcc);
+                                                             cfg->input_dtype == B2A_IN_I16, mfcc ? cfg->n_mfcc : 0);
             const bool fits = smem512 <= (size_t)prop.sharedMemPerBlockOptin;
             if (fits) {
                 CU_TRY_H(upload(wq, &h->d_wq));

@@ -41,7 +41,7 @@ int front_ctas_per_sm(int log2nc);
 cudaError_t launch_front(const FrontParams& p, int log2nc, bool i16, int kind, int grid, cudaStream_t st);
 
 // specialised n_fft = 512 kernel (logmel512.cu); requires an even hop
-size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc);
+size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc);   // n_mfcc = 0: mel
 bool logmel512_has_special(int sample_rate, int n_mels);
 int logmel512_ctas_per_sm();     // persistent warp-specialised CTAs per SM (1)
 int logmel512_mel_warps();       // mel (consumer) warps per CTA: table-driven bands are dealt round-robin to them

@@ -57,8 +57,10 @@ constexpr int XS = 18;                          // exchange row stride (float2):
 constexpr int XSLOT = 16 * XS + 2;              // 64-bit pass-2 loads are both conflict-free
 constexpr int PROW = 68;                        // power tile: row = 2 adjacent bins x (32 frames + 2 pad)
 constexpr int PROWS = 132;                      // bin pairs (0,1)..(256,257) + 3 zero rows for 8-bin padding
+constexpr int kZFast = 16;                      // mfcc: up to this many coefficients take the one-sweep z-score
 static_assert(ROUNDS >= 1 && ROUNDS * 2 * kFftWarps == F, "tile must be a whole number of rounds");
 static_assert(B2A_MELSPEC_WARPS == kMelWarps, "regenerate gen/mel_special.inc for this warp count");
+static_assert(B2A_DCTSPEC_NMFCC <= kZFast && kMelWarps == 4, "generated DCT: coefficients k = warp + 4 g, g < 4");
 
 __device__ __forceinline__ float db10(float s) {
     // 10*log10(max(amin, s)); the argument is >= 1e-10, never denormal -> lg2.approx.ftz
@@ -137,10 +139,12 @@ __device__ __forceinline__ E raw_sample(const E* clip, int s, int n, int pad_mod
 struct Layout {
     int chunk;          // samples staged per tile, multiple of 8
     int raw_bytes;      // bytes of one raw slot (multiple of 16)
-    int off_raw, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, off_db, total;
+    int gp;             // mfcc: DCT coefficients per mel warp, padded to a multiple of 4
+    int off_raw, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, off_db, off_dct, off_part, total;
 };
 
-__host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc) {
+__host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc) {
+    const bool mfcc = n_mfcc > 0;
     Layout L;
     L.chunk = (hop * (F - 1) + NFFT + 7) & ~7;
     int o = 0;
@@ -152,9 +156,12 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.off_tw2 = take(8 * 16 * 8);
     L.off_melw = take(mel_wpad * 4);
     L.off_melk = take(n_mels * 16);
-    L.off_red = take(64 * 4);
+    L.off_red = take((64 + 2 * kZFast) * 4);          // per-warp max/min, then (mean, sd) per coefficient
     L.off_bar = take((NRAW + 2 * 3) * 8);
     L.off_db = take(mfcc ? n_mels * 32 * 4 : 0);      // mfcc: [n_mels][32] dB tile feeding the in-tile DCT
+    L.off_part = take(mfcc && n_mfcc <= kZFast ? 2 * kMelWarps * n_mfcc * 32 * 4 : 0);   // generated DCT: partial sums
+    L.gp = 4 * ((((n_mfcc + kMelWarps - 1) / kMelWarps) + 3) / 4);
+    L.off_dct = take(mfcc ? n_mels * kMelWarps * L.gp * 4 : 0);   // mfcc: DCT-II basis as [mel][mel warp][gp]
     L.total = o;
     return L;
 }
@@ -162,7 +169,8 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
 template <bool I16, int KIND, bool SPEC, bool RAG>
 __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
-    const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16, KIND == 1);
+    constexpr bool MFCC = KIND >= 1;          // KIND 2: mfcc with the generated DCT (headline bands, 13 coefficients)
+    const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16, MFCC ? p.n_mfcc : 0);
     float* const s_db = reinterpret_cast<float*>(smem + L.off_db);
     float2* const s_xch = reinterpret_cast<float2*>(smem + L.off_xch);
     float* const s_pow = reinterpret_cast<float*>(smem + L.off_pow);
@@ -170,6 +178,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
     float* const s_melw = reinterpret_cast<float*>(smem + L.off_melw);
     int4* const s_desc = reinterpret_cast<int4*>(smem + L.off_melk);
     float* const s_red = reinterpret_cast<float*>(smem + L.off_red);
+    float* const s_zs = s_red + 64;
+    float* const s_dct = reinterpret_cast<float*>(smem + L.off_dct);
+    float* const s_part = reinterpret_cast<float*>(smem + L.off_part);
     uint64_t* const bar_raw_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* const bar_pow_full = bar_raw_full + NRAW;
     uint64_t* const bar_pow_empty = bar_pow_full + 3;
@@ -188,6 +199,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
     for (int i = tid; i < n_mels; i += kThreads) {
         const int m = p.mel_order[i];                        // position i is served by mel warp i % kMelWarps
         s_desc[i] = make_int4((p.mel_k0e[m] >> 1) * (PROW / 2), p.mel_cnt4[m], p.mel_off4[m], m);
+    }
+    if constexpr (MFCC) {
+        // DCT-II basis re-laid out so that mel warp w finds its coefficients k = w + 4 g, g < gp, as
+        // consecutive floats per mel band (128-bit broadcast loads in the in-tile DCT)
+        for (int i = tid; i < n_mels * kMelWarps * L.gp; i += kThreads) {
+            const int g = i % L.gp, w = (i / L.gp) % kMelWarps, m = i / (L.gp * kMelWarps);
+            const int k = w + kMelWarps * g;
+            s_dct[i] = k < p.n_mfcc ? p.dct[(size_t)k * n_mels + m] : 0.f;
+        }
     }
     for (int b = 0; b < NPOW; ++b)                           // bins 256..263 of every power tile
         for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[b * PROWS * PROW + 128 * PROW + i] = 0.f;
@@ -361,30 +381,55 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
             return fmaf(fmaf(-q, nq_range, num), nq_inv, q);
         };
         auto nrm4 = [&](float4 x) { return make_float4(nrm(x.x), nrm(x.y), nrm(x.z), nrm(x.w)); };
+        // mfcc: the deferred pass is the per-row z-score (deep.py:326-328), element-wise because rows of
+        // n_frames floats do not keep 16-byte alignment; (mean, sd) per coefficient wait in s_zs.
+        constexpr int NPZ = 4;                                   // floats per thread per tile
+        float* nz = nullptr;
+        int nz_nfr = 1;
+        float nz_inv = 1.f;
+        const bool zfast = MFCC && p.n_mfcc <= kZFast;
+        auto zs1 = [&](float x, int i) {
+            const int k = __float2int_rd(((float)i + 0.5f) * nz_inv);    // row of element i (never near an integer)
+            return __fdiv_rn(x - s_zs[2 * k], s_zs[2 * k + 1]);
+        };
         auto nq_finish = [&]() {                                 // whatever is left of the previous clip
-            for (int i = nq_done + mtid; i < nq_n4; i += kMelThreads) nq[i] = nrm4(nq[i]);
+            if constexpr (!MFCC) {
+                for (int i = nq_done + mtid; i < nq_n4; i += kMelThreads) nq[i] = nrm4(nq[i]);
+            } else {
+                for (int i = nq_done + mtid; i < nq_n4; i += kMelThreads) nz[i] = zs1(nz[i], i);
+            }
             nq_done = nq_n4;
         };
+        float zS[4] = {0.f, 0.f, 0.f, 0.f}, zQ[4] = {0.f, 0.f, 0.f, 0.f}, zx0[4] = {0.f, 0.f, 0.f, 0.f};
 
         uint32_t it = 0;
         for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
             const int nfr = RAG ? 1 + p.rag_len[clip] / hop : p.n_frames;
             const int tiles = (nfr + F - 1) / F;
             float* const outb = RAG ? p.out + p.rag_out_off[clip]
-                                    : p.out + (size_t)clip * (KIND == 0 ? n_mels : p.n_mfcc) * nfr;
-            float* const inter = (KIND == 0) ? outb : p.inter + (size_t)blockIdx.x * n_mels * p.n_frames;
+                                    : p.out + (size_t)clip * (MFCC ? p.n_mfcc : n_mels) * nfr;
+            float* const inter = MFCC ? p.inter + (size_t)blockIdx.x * n_mels * p.n_frames : outb;
             float vmax = -3.0e38f, vmin = 3.0e38f;
 
             for (int tile = 0; tile < tiles; ++tile, ++it) {
                 const int t0 = tile * F;
                 const uint32_t pb = it % NPOW;
-                float4 nx[NPF];
-                const bool nq_live = KIND == 0 && nq_done < nq_n4;
+                float4 nx[MFCC ? 1 : NPF];
+                float zx[MFCC ? NPZ : 1];
+                const bool nq_live = nq_done < nq_n4;
                 if (nq_live) {
+                    if constexpr (!MFCC) {
 #pragma unroll
-                    for (int k = 0; k < NPF; ++k) {
-                        const int i = nq_done + mtid + k * kMelThreads;
-                        if (i < nq_n4) nx[k] = nq[i];
+                        for (int k = 0; k < NPF; ++k) {
+                            const int i = nq_done + mtid + k * kMelThreads;
+                            if (i < nq_n4) nx[k] = nq[i];
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NPZ; ++k) {
+                            const int i = nq_done + mtid + k * kMelThreads;
+                            if (i < nq_n4) zx[k] = nz[i];
+                        }
                     }
                 }
                 if (mw == 0) B2A_STAMP(5, it);
@@ -399,6 +444,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     const float2* pl = reinterpret_cast<const float2*>(s_pow + pb * (PROWS * PROW)) + lane;
                     if constexpr (SPEC) {
                         const uint32_t pla = smem_u32(pl);
+                        float dacc[KIND == 2 ? B2A_DCTSPEC_NMFCC : 1];     // this warp's bands' share of each coefficient
+#pragma unroll
+                        for (int k = 0; k < (KIND == 2 ? B2A_DCTSPEC_NMFCC : 1); ++k) dacc[k] = 0.f;
 #define B2A_LDS2(DST, ADDR, OFF) \
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(DST.x), "=f"(DST.y) : "r"(ADDR), "n"(OFF))
                         // headline configuration: every band unrolled, weights are FFMA immediates
@@ -406,6 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
     {                                                                               \
         const float vv = db10(VAL);                                                 \
         if (KIND == 1) s_db[(M) * 32 + lane] = vv;                                  \
+        if (KIND == 2) B2A_DCT_BAND_##M(vv, dacc)                                   \
         if (valid) outp[(M) * nfr] = vv;      /* predicated store: the band sweep stays one basic block */ \
         vmax = fmaxf(vmax, valid ? vv : vmax);                                      \
         vmin = fminf(vmin, valid ? vv : vmin);                                      \
@@ -418,6 +467,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                         }
 #undef B2A_EMIT
 #undef B2A_LDS2
+                        if constexpr (KIND == 2) {
+                            float* const pp = s_part + ((it & 1) * kMelWarps + mw) * (B2A_DCTSPEC_NMFCC * 32) + lane;
+#pragma unroll
+                            for (int k = 0; k < B2A_DCTSPEC_NMFCC; ++k) pp[k * 32] = dacc[k];
+                        }
                     } else {
                         // per 4-bin step one 128-bit broadcast weight load and two 64-bit power
                         // loads (bands padded with zero weights)
@@ -437,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                                 pr += PROW;
                             }
                             const float vv = db10((a0 + a1) + (a2 + a3));
-                            if (KIND == 1) s_db[d.w * 32 + lane] = vv;
+                            if (MFCC) s_db[d.w * 32 + lane] = vv;
                             if (valid) {
                                 outp[d.w * nfr] = vv;
                                 vmax = fmaxf(vmax, vv);
@@ -449,29 +503,101 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_pow_empty + pb);    // the FFT warps may refill this slot
                 if (nq_live) {
+                    if constexpr (!MFCC) {
 #pragma unroll
-                    for (int k = 0; k < NPF; ++k) {
-                        const int i = nq_done + mtid + k * kMelThreads;
-                        if (i < nq_n4) nq[i] = nrm4(nx[k]);
+                        for (int k = 0; k < NPF; ++k) {
+                            const int i = nq_done + mtid + k * kMelThreads;
+                            if (i < nq_n4) nq[i] = nrm4(nx[k]);
+                        }
+                        nq_done += NPF * kMelThreads;
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NPZ; ++k) {
+                            const int i = nq_done + mtid + k * kMelThreads;
+                            if (i < nq_n4) nz[i] = zs1(zx[k], i);
+                        }
+                        nq_done += NPZ * kMelThreads;
                     }
-                    nq_done += NPF * kMelThreads;
                     if (tile + 1 == tiles) nq_finish();            // short clip after a long one
+                }
+                if constexpr (KIND == 2) {
+                    // generated DCT: the four warps' partial sums meet in shared memory (double
+                    // buffered by tile parity: one barrier per tile); warp mw finishes k = mw + 4 g
+                    mel_sync();
+                    const int t = t0 + lane;
+                    const bool valid = t < nfr;
+                    const float* const pp = s_part + (it & 1) * (kMelWarps * B2A_DCTSPEC_NMFCC * 32) + lane;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const int k = mw + kMelWarps * g;
+                        float ag = 0.f;
+                        if (k < B2A_DCTSPEC_NMFCC) {
+                            ag = (pp[k * 32] + pp[(B2A_DCTSPEC_NMFCC + k) * 32]) +
+                                 (pp[(2 * B2A_DCTSPEC_NMFCC + k) * 32] + pp[(3 * B2A_DCTSPEC_NMFCC + k) * 32]);
+                            if (valid) outb[(size_t)k * nfr + t] = ag;
+                        }
+                        if (tile == 0) zx0[g] = __shfl_sync(0xffffffffu, ag, 0);
+                        const float dd = valid ? ag - zx0[g] : 0.f;
+                        zS[g] += dd;
+                        zQ[g] = fmaf(dd, dd, zQ[g]);
+                    }
                 }
                 if constexpr (KIND == 1) {
                     // DCT-II of this tile straight from shared memory, assuming the top_db clip
                     // (known only after the clip's last tile) will not engage; checked below.
+                    // lane = frame; this warp owns coefficients k = mw + 4 g.  One conflict-free dB
+                    // load and one 128-bit broadcast basis load feed four FMAs.
                     mel_sync();
-                    for (int i = mtid; i < p.n_mfcc * 32; i += kMelThreads) {
-                        const int k = i >> 5, f = i & 31, t = t0 + f;
-                        const float* d = p.dct + (size_t)k * n_mels;
-                        float a0 = 0.f, a1 = 0.f;
-                        int m = 0;
-                        for (; m + 1 < n_mels; m += 2) {
-                            a0 = fmaf(__ldg(d + m), s_db[m * 32 + f], a0);
-                            a1 = fmaf(__ldg(d + m + 1), s_db[(m + 1) * 32 + f], a1);
+                    const int t = t0 + lane;
+                    const bool valid = t < nfr;
+                    const float* const dbl = s_db + lane;
+                    for (int c = 0; c < L.gp / 4; ++c) {
+                        const float4* w4 = reinterpret_cast<const float4*>(s_dct + mw * L.gp) + c;
+                        float a[4] = {0.f, 0.f, 0.f, 0.f};
+                        // software pipeline: the loads of the next four bands are in flight while the
+                        // current four are multiplied (this warp has its scheduler's LSU latency to itself)
+                        const int ws = kMelWarps * L.gp / 4;
+                        float dq[4];
+                        float4 wq[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int m = u < n_mels ? u : n_mels - 1;
+                            dq[u] = dbl[m * 32];
+                            wq[u] = w4[m * ws];
                         }
-                        if (m < n_mels) a0 = fmaf(__ldg(d + m), s_db[m * 32 + f], a0);
-                        if (t < nfr) outb[(size_t)k * nfr + t] = a0 + a1;
+                        for (int m0 = 0; m0 < n_mels; m0 += 4) {
+                            float dc[4];
+                            float4 wc[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) { dc[u] = dq[u]; wc[u] = wq[u]; }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int m = m0 + 4 + u < n_mels ? m0 + 4 + u : n_mels - 1;
+                                dq[u] = dbl[m * 32];
+                                wq[u] = w4[m * ws];
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                if (m0 + u < n_mels) {
+                                    a[0] = fmaf(wc[u].x, dc[u], a[0]);
+                                    a[1] = fmaf(wc[u].y, dc[u], a[1]);
+                                    a[2] = fmaf(wc[u].z, dc[u], a[2]);
+                                    a[3] = fmaf(wc[u].w, dc[u], a[3]);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            const int k = mw + kMelWarps * (4 * c + g);
+                            if (k < p.n_mfcc && valid) outb[(size_t)k * nfr + t] = a[g];
+                            if (c == 0) {
+                                // running sums about the row's first sample for the one-sweep z-score
+                                if (tile == 0) zx0[g] = __shfl_sync(0xffffffffu, a[g], 0);
+                                const float dd = valid ? a[g] - zx0[g] : 0.f;
+                                zS[g] += dd;
+                                zQ[g] = fmaf(dd, dd, zQ[g]);
+                            }
+                        }
                     }
                     mel_sync();                                    // s_db is rewritten by the next tile
                 }
@@ -486,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                 const float b = (lane < kMelWarps) ? s_red[32 + lane] : 3.0e38f;
                 vmax = warp_max(a); vmin = warp_min(b);
             }
-            if constexpr (KIND == 0) {
+            if constexpr (!MFCC) {
                 nq_finish();                                          // (only if this clip had no tile)
                 nq_vmax = vmax;
                 nq_lo = fmaxf(vmin - vmax, -p.top_db);
@@ -525,9 +651,35 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                         }
                     }
                 }
+                nq_finish();                                          // the previous clip's z-score, if any is left
+                const float fn = (float)nfr;
+                if (zfast && !(vmin < thr)) {
+                    // common case: mean and variance from the running sums; the rows are rewritten
+                    // during the next clip's tiles (deferred, prefetched)
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float S = warp_sum(zS[g]), Q = warp_sum(zQ[g]);
+                        const int k = mw + kMelWarps * g;
+                        if (lane == 0 && k < p.n_mfcc) {
+                            const float md = __fdiv_rn(S, fn);
+                            s_zs[2 * k] = zx0[g] + md;
+                            s_zs[2 * k + 1] = sqrtf(fmaxf(fmaf(-md, md, __fdiv_rn(Q, fn)), 0.f)) + 1e-8f;
+                        }
+                        zS[g] = 0.f; zQ[g] = 0.f;
+                    }
+                    nz = outc;
+                    nz_nfr = nfr;
+                    nz_inv = __fdiv_rn(1.0f, fn);
+                    nq_n4 = p.n_mfcc * nfr;
+                    nq_done = 0;
+                    mel_sync();
+                    continue;
+                }
+#pragma unroll
+                for (int g = 0; g < 4; ++g) { zS[g] = 0.f; zQ[g] = 0.f; }
+                nq_n4 = nq_done = 0;
                 mel_sync();                                           // DCT stores visible to every mel warp
                 // deep.py:326-328: per-row z-score, three sweeps over an L2-resident row
-                const float fn = (float)nfr;
                 for (int k = mw; k < p.n_mfcc; k += kMelWarps) {
                     float* row = outc + (size_t)k * nfr;
                     const float x0 = row[0];
@@ -542,14 +694,14 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
             }
             mel_sync();                                               // s_red / s_db are reused by the next clip
         }
-        if constexpr (KIND == 0) nq_finish();                         // the CTA's last clip
+        nq_finish();                                                  // the CTA's last clip
     }
 }
 
 }  // namespace
 
-size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, bool mfcc) {
-    return (size_t)make_layout(hop, n_mels, mel_wpad, i16, mfcc).total + 128;
+size_t logmel512_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc) {
+    return (size_t)make_layout(hop, n_mels, mel_wpad, i16, n_mfcc).total + 128;
 }
 
 int logmel512_ctas_per_sm() { return 1; }
@@ -571,11 +723,15 @@ static cudaError_t launch_k(const FrontParams& p, int grid, size_t smem, cudaStr
 template <bool SPEC, bool RAG>
 static cudaError_t launch_s(const FrontParams& p, bool i16, int kind, int grid, size_t smem, cudaStream_t st) {
     if (kind == 0) return i16 ? launch_k<true, 0, SPEC, RAG>(p, grid, smem, st) : launch_k<false, 0, SPEC, RAG>(p, grid, smem, st);
+    if constexpr (SPEC) {
+        if (p.n_mfcc == B2A_DCTSPEC_NMFCC)      // headline mfcc: generated DCT
+            return i16 ? launch_k<true, 2, SPEC, RAG>(p, grid, smem, st) : launch_k<false, 2, SPEC, RAG>(p, grid, smem, st);
+    }
     return i16 ? launch_k<true, 1, SPEC, RAG>(p, grid, smem, st) : launch_k<false, 1, SPEC, RAG>(p, grid, smem, st);
 }
 
 cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st) {
-    const size_t smem = logmel512_smem_bytes(p.hop, p.n_mels, p.mel_wpad, i16, kind == 1);
+    const size_t smem = logmel512_smem_bytes(p.hop, p.n_mels, p.mel_wpad, i16, kind == 1 ? p.n_mfcc : 0);
     if (p.rag_len) return p.mel_special ? launch_s<true, true>(p, i16, kind, grid, smem, st)
                                         : launch_s<false, true>(p, i16, kind, grid, smem, st);
     return p.mel_special ? launch_s<true, false>(p, i16, kind, grid, smem, st)
