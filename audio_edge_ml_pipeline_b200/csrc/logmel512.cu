@@ -53,8 +53,8 @@ constexpr int NRAW = 4;                         // ring depth of raw PCM tiles
 // ring depth of power tiles: 3 absorbs the mel warps' per-clip normalisation pause; float32 input
 // doubles the raw ring, leaving room for 2
 __host__ __device__ constexpr int npow(bool i16) { return i16 ? 2 : 2; }
-constexpr int XS = 18;                          // exchange row stride (float2): 128-bit pass-1 stores and
-constexpr int XSLOT = 16 * XS + 2;              // 64-bit pass-2 loads are both conflict-free
+constexpr int XS = 17;                          // exchange row stride (float2): 64-bit pass-1 stores (row j) and
+constexpr int XSLOT = 16 * XS + 2;              // 64-bit pass-2 loads (column j) are both conflict-free
 constexpr int PROW = 68;                        // power tile: row = 2 adjacent bins x (32 frames + 2 pad)
 constexpr int PROWS = 132;                      // bin pairs (0,1)..(256,257) + 3 zero rows for 8-bin padding
 constexpr int kZFast = 16;                      // mfcc: up to this many coefficients take the one-sweep z-score
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
 #pragma unroll
         for (int t = 1; t < 16; ++t) tw1[t - 1] = p.tw[t * j];
         float2* const xs = s_xch + (2 * warp + h) * XSLOT;       // this frame's exchange slot
-        float4* const x1 = reinterpret_cast<float4*>(xs + XS * j);   // pass-1 store base (row j, 2 points per store)
+        float2* const x1 = xs + XS * j;                          // pass-1 store base (row j)
         float2* const x2 = xs + j;                               // pass-2 load base (column j, stride XS)
         float2* const mst = xs + j;                              // mirror store base: M[(row-8)*16 + j]
         const float2* const mld = xs + (j ? 16 - j : 16);        // mirror load base:  M[(7-r)*16 + ...]
@@ -274,7 +274,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     }
                     Dft<16>::run(v);
 #pragma unroll
-                    for (int t = 0; t < 16; t += 2) x1[t >> 1] = make_float4(v[t].x, v[t].y, v[t + 1].x, v[t + 1].y);
+                    for (int t = 0; t < 16; ++t) x1[t] = v[t];         // (128-bit stores would need 4 MOVs each to
+                                                                       //  line the register pairs up)
                     __syncwarp();
                     v[0] = x2[0];
 #pragma unroll
@@ -332,23 +333,35 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
             const int c0 = t0 * hop - NFFT / 2;
             const int lo = c0 < 0 ? 0 : c0;
             const int hi = (c0 + chunk < n) ? c0 + chunk : n;
+            // samples the tile's valid frames read (a clip's last tile is mostly past its end; filling
+            // the whole chunk cost this one warp ~5000 cycles per clip and stalled the pipeline)
+            const int nfr = 1 + n / hop;
+            const int vf = nfr - t0 < F ? nfr - t0 : F;
+            const int need = ((vf - 1) * hop + NFFT + V - 1) & ~(V - 1);      // <= chunk
             const bool ok = p.pad_mode == 0 && base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
                             (((lo - c0) & (V - 1)) == 0);
             const int nb = ok ? ((hi - lo) / V) * V : 0;         // bulk part, whole 16-byte units
             if (nb == 0) {
-                for (int i = lane; i < chunk; i += 32) dst[i] = raw_sample<E>(cptr, c0 + i, n, p.pad_mode);
+                for (int i = lane; i < need; i += 32) dst[i] = raw_sample<E>(cptr, c0 + i, n, p.pad_mode);
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar);
                 return;
             }
-            const int head = lo - c0;                            // [0, head) and [head+nb, chunk) are not
-            for (int i = lane; i < head; i += 32) dst[i] = (E)0;                 // written by the bulk copy
-            for (int i = head + nb + lane; i < chunk; i += 32) dst[i] = raw_sample<E>(cptr, c0 + i, n, 0);
+            // [0, head) and [head+nb, need) are not written by the bulk copy: zeros (centre padding),
+            // except for the clip's last < V samples
+            const int head = lo - c0, tb = head + nb;
+            const int4 z4 = make_int4(0, 0, 0, 0);
+            for (int i = lane * V; i < head; i += 32 * V) *reinterpret_cast<int4*>(dst + i) = z4;
+            if (tb < need) {
+                if (lane < V) dst[tb + lane] = raw_sample<E>(cptr, c0 + tb + lane, n, 0);
+                for (int i = tb + V + lane * V; i < need; i += 32 * V) *reinterpret_cast<int4*>(dst + i) = z4;
+            }
             __syncwarp();
             if (lane == 0) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses -> async write
-                mbar_expect_tx(bar, (uint32_t)(nb * sizeof(E)));
-                bulk_g2s(dst + head, cptr + lo, (uint32_t)(nb * sizeof(E)), bar);
+                const int cb = (nb < need - head ? nb : need - head) * (int)sizeof(E);    // never more than needed
+                mbar_expect_tx(bar, (uint32_t)cb);
+                bulk_g2s(dst + head, cptr + lo, (uint32_t)cb, bar);
             }
         };
         // producer cursor: runs NRAW tiles ahead of the consumers
