@@ -70,13 +70,23 @@ sass = subprocess.run(["cuobjdump", "-sass", str(ROOT / "audio_edge_ml_pipeline_
                       capture_output=True, text=True).stdout
 cnt = collections.Counter()
 cur = None
+MNEMONICS = ("UBLKCP", "SYNCS", "USETMAXREG", "FFMA2", "FADD2", "FMUL2", "FFMA", "FADD", "FMUL", "LDS", "STS", "SHFL", "BAR")
 for ln in sass.splitlines():
     if "Function :" in ln:
         cur = ln.split("Function :")[1].strip()
-    for m in ("UBLKCP", "SYNCS", "UTMALDG", "DFMA", "LDS", "STS", "FFMA"):
-        if f" {m}" in ln and cur and "logmel512_kernelILb1ELi0" in cur:
-            cnt[m] += 1
+        continue
+    if not (cur and "logmel512_kernelILb1ELi0ELb1ELb0" in cur):
+        continue
+    tok = ln.split()
+    for t in tok[1:3]:                      # opcode is the 2nd token, or the 3rd after a predicate
+        op = t.split(".")[0].rstrip(";")
+        if op in MNEMONICS:
+            cnt[op] += 1
+            break
 (ROOT / "profiles" / f"{rnd}_sass_evidence.txt").write_text(
-    "logmel512_kernel<int16, mel> SASS mnemonic counts (cuobjdump -sass libb2a.so):\n" +
-    "\n".join(f"  {k}: {v}" for k, v in sorted(cnt.items())) + "\nUBLKCP = cp.async.bulk (TMA bulk copy), SYNCS = mbarrier ops\n")
+    "logmel512_kernel<int16, mel, generated-mel> static SASS mnemonic counts (cuobjdump -sass libb2a.so):\n" +
+    "\n".join(f"  {k}: {v}" for k, v in sorted(cnt.items())) +
+    "\nUBLKCP = cp.async.bulk (TMA bulk copy); SYNCS = mbarrier init/arrive/try_wait; USETMAXREG = setmaxnreg\n"
+    "(FFT warps 104 registers, mel/producer warps 64); FFMA2/FADD2/FMUL2 = packed FP32 (two lanes of a\n"
+    "complex point per instruction); BAR = the mel warps' named barrier + the one-off prologue barrier.\n")
 print("\n".join(lines[:40]))
