@@ -665,6 +665,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     }
                 }
                 nq_finish();                                          // the previous clip's z-score, if any is left
+                mel_sync();                                           // ... by every warp, before s_zs changes
                 const float fn = (float)nfr;
                 if (zfast && !(vmin < thr)) {
                     // common case: mean and variance from the running sums; the rows are rewritten
