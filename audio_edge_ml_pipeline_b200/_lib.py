@@ -25,6 +25,8 @@ EXPORTED_SYMBOLS = [
     "b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
     "b2a_run_host", "b2a_run_host_ragged", "b2a_run_device_ragged", "b2a_last_launch_count", "b2a_alloc_pinned", "b2a_free_pinned",
     "b2a_decode_wav_pcm16_batch", "b2a_get_table", "b2a_cqt_geometry", "b2a_last_error", "b2a_abi_version", "b2a_device_count",
+    "b2a_resampler_create", "b2a_resampler_destroy", "b2a_resampler_out_len", "b2a_resampler_geometry",
+    "b2a_resampler_design", "b2a_resampler_run_host", "b2a_resampler_run_device", "b2a_resampler_last_error",
 ]
 
 
@@ -75,6 +77,18 @@ def load_library() -> C.CDLL:
     lib.b2a_get_table.argtypes = [vp, i32, vp, C.POINTER(i64)]
     lib.b2a_cqt_geometry.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), vp, vp, vp]
     lib.b2a_last_error.restype = C.c_char_p
+    lib.b2a_resampler_create.argtypes = [i32, i32, i32, C.POINTER(vp)]
+    lib.b2a_resampler_destroy.argtypes = [vp]
+    lib.b2a_resampler_out_len.argtypes = [vp, i64]
+    lib.b2a_resampler_out_len.restype = i64
+    lib.b2a_resampler_geometry.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp]
+    lib.b2a_resampler_design.argtypes = [i32, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp, i64]
+    lib.b2a_resampler_run_host.argtypes = [vp, vp, i32, i64, vp]
+    lib.b2a_resampler_run_device.argtypes = [vp, vp, i32, i64, vp, vp]
+    lib.b2a_resampler_last_error.restype = C.c_char_p
+    for name in ("b2a_resampler_create", "b2a_resampler_destroy", "b2a_resampler_geometry", "b2a_resampler_design",
+                 "b2a_resampler_run_host", "b2a_resampler_run_device"):
+        getattr(lib, name).restype = C.c_int
     for name in ("b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
                  "b2a_run_host", "b2a_run_host_ragged", "b2a_run_device_ragged", "b2a_alloc_pinned", "b2a_free_pinned", "b2a_get_table",
                  "b2a_cqt_geometry", "b2a_abi_version", "b2a_device_count"):
@@ -243,3 +257,77 @@ class Engine:
         _check(self._lib.b2a_cqt_geometry(self._h, C.byref(no), C.byref(nf), a.ctypes.data, b.ctypes.data,
                                           c.ctypes.data))
         return dict(n_octaves=no.value, n_filters=nf.value, n_fft=a, hop=b, sig_len=c)
+
+
+# ---------------------------------------------------------------------------------------------
+# Rational resampler (files whose rate differs from the extractor's sample_rate; deep.py:44-50)
+# ---------------------------------------------------------------------------------------------
+
+def _check_rs(rc: int) -> None:
+    if rc != 0:
+        raise B2AError(rc, load_library().b2a_resampler_last_error().decode(errors="replace"))
+
+
+def resampler_design(orig_sr: int, target_sr: int):
+    """(up, down, half_len, poly[up, K] float32) of the library's resampler — host only, no GPU."""
+    lib = load_library()
+    up, down, half, k = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int32()
+    _check_rs(lib.b2a_resampler_design(orig_sr, target_sr, C.byref(up), C.byref(down), C.byref(half), C.byref(k), None, 0))
+    poly = np.empty((up.value, k.value), dtype=np.float32)
+    _check_rs(lib.b2a_resampler_design(orig_sr, target_sr, None, None, None, None, poly.ctypes.data_as(C.c_void_p), poly.size))
+    return up.value, down.value, half.value, poly
+
+
+class Resampler:
+    """One (orig_sr -> target_sr, device) resampler; GPU only (raises B2AError without a device)."""
+
+    def __init__(self, orig_sr: int, target_sr: int, device: int = 0):
+        self._lib = load_library()
+        self._h = C.c_void_p()
+        _check_rs(self._lib.b2a_resampler_create(int(orig_sr), int(target_sr), int(device), C.byref(self._h)))
+        self.orig_sr, self.target_sr, self.device = int(orig_sr), int(target_sr), int(device)
+
+    def out_len(self, n_in: int) -> int:
+        return int(self._lib.b2a_resampler_out_len(self._h, int(n_in)))
+
+    def run_host(self, y: np.ndarray) -> np.ndarray:
+        """1-D int16 (PCM, scaled by 1/32768) or float32 samples -> float32 at the target rate."""
+        if y.dtype != np.int16:
+            y = y.astype(np.float32, copy=False)
+        y = np.ascontiguousarray(y)
+        if y.ndim != 1:
+            raise ValueError("resampler input must be 1-D (mono)")
+        out = np.empty(self.out_len(len(y)), dtype=np.float32)
+        _check_rs(self._lib.b2a_resampler_run_host(self._h, y.ctypes.data_as(C.c_void_p),
+                                                   IN_I16 if y.dtype == np.int16 else IN_F32, len(y),
+                                                   out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            self._lib.b2a_resampler_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+_resamplers: dict = {}
+
+
+def resample(y: np.ndarray, orig_sr: int, target_sr: int, device: int = 0) -> np.ndarray:
+    """librosa.resample(y, orig_sr, target_sr, res_type="soxr_hq") stand-in (see Resampler)."""
+    key = (int(orig_sr), int(target_sr), int(device))
+    r = _resamplers.get(key)
+    if r is None:
+        r = _resamplers[key] = Resampler(*key)
+    return r.run_host(y)

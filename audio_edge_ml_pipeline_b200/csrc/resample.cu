@@ -1,0 +1,229 @@
+// resample.cu — rational polyphase resampler (files whose rate differs from `sample_rate`).
+//
+// Stands in for the soxr_hq resampling librosa.load performs inside `_load_segment`
+// (reference src/preprocessing/feature_extraction/audio/deep.py:44-50): zero-phase Kaiser-sinc
+// low-pass at the decimator's specification (tables.h: design_resampler), zero-extended edges,
+// output length ceil(n * target / orig) as librosa.resample fixes it.  libsoxr is not available
+// offline, so parity against its exact output is unpinned; the oracle
+// (oracle/librosa_restated.py: resample_restated) evaluates the same closed form through
+// scipy.signal.resample_poly.  sm_100a only, no CPU path.
+//
+//   y[m] = sum_i poly[(m*down + half) % up][i] * x[(m*down + half) / up - i]
+//
+// One CTA produces 256 consecutive outputs: the input window they share is staged once in shared
+// memory (int16 widened there), every thread walks its own phase row with 128-bit tap loads (the
+// table, <= a few hundred KB, stays in L1/L2) and four independent accumulators.
+#include "../../include/b2a.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "tables.h"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+thread_local std::string g_rs_err;
+
+template <bool I16>
+__global__ void __launch_bounds__(kThreads) resample_kernel(const void* __restrict__ in, long long n_in,
+                                                            float* __restrict__ out, long long n_out,
+                                                            const float* __restrict__ poly, int up, int down,
+                                                            int K, int half_len, int win) {
+    extern __shared__ __align__(16) float s_x[];
+    const long long m0 = (long long)blockIdx.x * kThreads;
+    // newest sample any output of this CTA touches, oldest = that of the first output minus K-1
+    const long long k_first = (m0 * down + half_len) / up;
+    const long long k_lo = k_first - (K - 1);
+    for (int i = threadIdx.x; i < win; i += kThreads) {
+        const long long k = k_lo + i;
+        float v = 0.f;
+        if (k >= 0 && k < n_in)
+            v = I16 ? (float)((const int16_t*)in)[k] * (1.0f / 32768.0f) : ((const float*)in)[k];
+        s_x[i] = v;
+    }
+    __syncthreads();
+    const long long m = m0 + threadIdx.x;
+    if (m >= n_out) return;
+    const long long u = m * down + half_len;
+    const int p = (int)(u % up);
+    const float* xs = s_x + (int)(u / up - k_lo);            // x[(u / up) - i] = xs[-i]
+    const float4* h4 = reinterpret_cast<const float4*>(poly + (size_t)p * K);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < K / 4; ++i) {
+        const float4 h = __ldg(h4 + i);
+        a0 = fmaf(h.x, xs[-4 * i], a0);
+        a1 = fmaf(h.y, xs[-4 * i - 1], a1);
+        a2 = fmaf(h.z, xs[-4 * i - 2], a2);
+        a3 = fmaf(h.w, xs[-4 * i - 3], a3);
+    }
+    out[m] = (a0 + a1) + (a2 + a3);
+}
+
+}  // namespace
+
+struct b2a_resampler {
+    int device = 0, orig = 0, target = 0;
+    b2a::ResamplerDesign d;
+    float* d_poly = nullptr;
+    void* d_in = nullptr;
+    float* d_out = nullptr;
+    size_t cap_in = 0, cap_out = 0;          // bytes
+    cudaStream_t stream = nullptr;
+};
+
+namespace {
+
+int rs_fail(int code, const std::string& msg) { g_rs_err = msg; return code; }
+
+#define RS_TRY(expr)                                                                      \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess)                                                           \
+            return rs_fail(e__ == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA,     \
+                           std::string(#expr) + ": " + cudaGetErrorString(e__));          \
+    } while (0)
+
+int rs_launch(b2a_resampler* r, const void* d_in, int in_dtype, long long n_in, float* d_out, cudaStream_t st) {
+    const long long n_out = b2a_resampler_out_len(r, n_in);
+    if (n_out <= 0) return B2A_OK;
+    const int K = r->d.taps_per_phase;
+    // input samples spanned by 256 consecutive outputs, plus the filter length
+    const int win = K + (int)(((long long)(kThreads - 1) * r->d.down + r->d.up - 1) / r->d.up) + 2;
+    const size_t smem = (size_t)win * sizeof(float);
+    const unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
+    if (in_dtype == B2A_IN_I16) {
+        auto k = resample_kernel<true>;
+        RS_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, r->d.up, r->d.down, K, r->d.half_len, win);
+    } else {
+        auto k = resample_kernel<false>;
+        RS_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, r->d.up, r->d.down, K, r->d.half_len, win);
+    }
+    RS_TRY(cudaGetLastError());
+    return B2A_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2a_resampler_last_error(void) { return g_rs_err.c_str(); }
+
+int b2a_resampler_create(int32_t orig_sr, int32_t target_sr, int32_t device, b2a_resampler** out) {
+    if (!out) return rs_fail(B2A_EINVAL, "out is NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return rs_fail(B2A_ENODEVICE, "no CUDA device: the resampler has no CPU path");
+    }
+    if (device < 0 || device >= n_dev) return rs_fail(B2A_EINVAL, "device index out of range");
+    b2a_resampler* r = new (std::nothrow) b2a_resampler();
+    if (!r) return rs_fail(B2A_ENOMEM, "out of host memory");
+    const char* err = nullptr;
+    if (!b2a::design_resampler(orig_sr, target_sr, &r->d, &err)) {
+        delete r;
+        return rs_fail(B2A_EINVAL, err ? err : "resampler design failed");
+    }
+    r->device = device; r->orig = orig_sr; r->target = target_sr;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r->d_poly, r->d.poly.size() * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(r->d_poly, r->d.poly.data(), r->d.poly.size() * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        b2a_resampler_destroy(r);
+        return rs_fail(e == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA, cudaGetErrorString(e));
+    }
+    *out = r;
+    return B2A_OK;
+}
+
+int b2a_resampler_destroy(b2a_resampler* r) {
+    if (!r) return B2A_OK;
+    cudaSetDevice(r->device);
+    if (r->stream) { cudaStreamSynchronize(r->stream); cudaStreamDestroy(r->stream); }
+    cudaFree(r->d_poly); cudaFree(r->d_in); cudaFree(r->d_out);
+    delete r;
+    return B2A_OK;
+}
+
+int64_t b2a_resampler_out_len(const b2a_resampler* r, int64_t n_in) {
+    if (!r || n_in <= 0) return 0;
+    // librosa.resample: int(np.ceil(n * target / orig)), with the ratio in lowest terms
+    return (n_in * r->d.up + r->d.down - 1) / r->d.down;
+}
+
+int b2a_resampler_geometry(const b2a_resampler* r, int32_t* up, int32_t* down, int32_t* half_len,
+                           int32_t* taps_per_phase, float* poly /* [up][taps_per_phase] or NULL */) {
+    if (!r) return rs_fail(B2A_EINVAL, "resampler is NULL");
+    if (up) *up = r->d.up;
+    if (down) *down = r->d.down;
+    if (half_len) *half_len = r->d.half_len;
+    if (taps_per_phase) *taps_per_phase = r->d.taps_per_phase;
+    if (poly) std::copy(r->d.poly.begin(), r->d.poly.end(), poly);
+    return B2A_OK;
+}
+
+int b2a_resampler_design(int32_t orig_sr, int32_t target_sr, int32_t* up, int32_t* down, int32_t* half_len,
+                         int32_t* taps_per_phase, float* poly, int64_t poly_capacity) {
+    b2a::ResamplerDesign d;
+    const char* err = nullptr;
+    if (!b2a::design_resampler(orig_sr, target_sr, &d, &err)) return rs_fail(B2A_EINVAL, err ? err : "design failed");
+    if (up) *up = d.up;
+    if (down) *down = d.down;
+    if (half_len) *half_len = d.half_len;
+    if (taps_per_phase) *taps_per_phase = d.taps_per_phase;
+    if (poly) {
+        if (poly_capacity < (int64_t)d.poly.size()) return rs_fail(B2A_EINVAL, "poly buffer too small");
+        std::copy(d.poly.begin(), d.poly.end(), poly);
+    }
+    return B2A_OK;
+}
+
+int b2a_resampler_run_device(b2a_resampler* r, const void* d_in, int32_t in_dtype, int64_t n_in,
+                             float* d_out, void* stream) {
+    if (!r) return rs_fail(B2A_EINVAL, "resampler is NULL");
+    if (n_in < 0) return rs_fail(B2A_EINVAL, "n_in < 0");
+    if (in_dtype != B2A_IN_I16 && in_dtype != B2A_IN_F32) return rs_fail(B2A_EINVAL, "unknown input dtype");
+    if (n_in == 0) return B2A_OK;
+    if (!d_in || !d_out) return rs_fail(B2A_EINVAL, "NULL buffer");
+    RS_TRY(cudaSetDevice(r->device));
+    return rs_launch(r, d_in, in_dtype, n_in, d_out, (cudaStream_t)stream);
+}
+
+int b2a_resampler_run_host(b2a_resampler* r, const void* in, int32_t in_dtype, int64_t n_in, float* out) {
+    if (!r) return rs_fail(B2A_EINVAL, "resampler is NULL");
+    if (n_in < 0) return rs_fail(B2A_EINVAL, "n_in < 0");
+    if (in_dtype != B2A_IN_I16 && in_dtype != B2A_IN_F32) return rs_fail(B2A_EINVAL, "unknown input dtype");
+    if (n_in == 0) return B2A_OK;
+    if (!in || !out) return rs_fail(B2A_EINVAL, "NULL buffer");
+    RS_TRY(cudaSetDevice(r->device));
+    const size_t in_bytes = (size_t)n_in * (in_dtype == B2A_IN_I16 ? 2 : 4);
+    const size_t out_bytes = (size_t)b2a_resampler_out_len(r, n_in) * sizeof(float);
+    if (in_bytes > r->cap_in) {
+        cudaFree(r->d_in); r->d_in = nullptr; r->cap_in = 0;
+        RS_TRY(cudaMalloc(&r->d_in, in_bytes));
+        r->cap_in = in_bytes;
+    }
+    if (out_bytes > r->cap_out) {
+        cudaFree(r->d_out); r->d_out = nullptr; r->cap_out = 0;
+        RS_TRY(cudaMalloc((void**)&r->d_out, out_bytes));
+        r->cap_out = out_bytes;
+    }
+    RS_TRY(cudaMemcpyAsync(r->d_in, in, in_bytes, cudaMemcpyHostToDevice, r->stream));
+    const int rc = rs_launch(r, r->d_in, in_dtype, n_in, r->d_out, r->stream);
+    if (rc != B2A_OK) return rc;
+    RS_TRY(cudaMemcpyAsync(out, r->d_out, out_bytes, cudaMemcpyDeviceToHost, r->stream));
+    RS_TRY(cudaStreamSynchronize(r->stream));
+    return B2A_OK;
+}
+
+}  // extern "C"

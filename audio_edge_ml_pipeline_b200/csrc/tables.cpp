@@ -122,6 +122,45 @@ std::vector<double> decimator_taps() {
     return h;
 }
 
+// ---- rational resampler ------------------------------------------------------------------
+bool design_resampler(int orig_sr, int target_sr, ResamplerDesign* d, const char** err) {
+    if (orig_sr <= 0 || target_sr <= 0) { *err = "resampler: sample rates must be positive"; return false; }
+    int a = orig_sr, b = target_sr;
+    while (b) { const int t = a % b; a = b; b = t; }
+    d->up = target_sr / a;
+    d->down = orig_sr / a;
+    if (d->up > kResampleMaxUp) { *err = "resampler: target/orig reduces to an up-factor above 4096"; return false; }
+    const double lo = (double)std::min(orig_sr, target_sr);
+    const double fs_up = (double)d->up * (double)orig_sr;            // rate the prototype runs at
+    d->half_len = (int)std::llround(95.5 * fs_up / lo);
+    const long long ntot = 2LL * d->half_len + 1;
+    if (ntot > (1LL << 26)) { *err = "resampler: filter too long for this ratio"; return false; }
+    const double atten = 125.0, pass = 0.913, stop = 1.0;
+    const double beta = 0.1102 * (atten - 8.7);
+    const double fc = 0.5 * (pass + stop) * 0.5 * lo / fs_up;        // cycles per prototype sample
+    std::vector<double> g((size_t)ntot);
+    const double i0b = bessel_i0(beta);
+    double sum = 0;
+    for (long long i = 0; i < ntot; ++i) {
+        const double m = (double)(i - d->half_len);
+        const double x = 2.0 * fc * m;
+        const double sinc = (x == 0.0) ? 1.0 : std::sin(kPi * x) / (kPi * x);
+        const double r = m / (double)d->half_len;
+        const double w = bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / i0b;
+        g[(size_t)i] = 2.0 * fc * sinc * w;
+        sum += g[(size_t)i];
+    }
+    const int K = (int)(((ntot + d->up - 1) / d->up + 3) & ~3LL);
+    d->taps_per_phase = K;
+    d->poly.assign((size_t)d->up * K, 0.f);
+    for (int p = 0; p < d->up; ++p)
+        for (int i = 0; i < K; ++i) {
+            const long long j = p + (long long)d->up * i;
+            if (j < ntot) d->poly[(size_t)p * K + i] = (float)((double)d->up * g[(size_t)j] / sum);
+        }
+    return true;
+}
+
 // ---- CQT plan ----------------------------------------------------------------------------
 static const double kHannBandwidth = 1.50018310546875;   // librosa window_bandwidth("hann")
 static const double kC1 = 32.70319566257483;             // librosa.note_to_hz("C1")

@@ -35,6 +35,22 @@ std::vector<float> dct2_ortho(int n_out, int n_in);
 constexpr int kDecimTaps = 383;
 std::vector<double> decimator_taps();
 
+// Rational resampler standing in for soxr_hq inside librosa.load (deep.py:44-50): the 2:1
+// decimator's specification (pass band to 0.913 x, stop band from 1.0 x the lower Nyquist,
+// 125 dB, linear phase, zero-extended edges) scaled to up/down = target/orig.  The prototype
+// low-pass runs at up x orig Hz with half-length round(95.5 * up * orig / min(orig, target)),
+// so 2:1 gives exactly decimator_taps().  poly[p][i] = up * g[p + up * i]  (float32, rows padded to
+// a multiple of 4 taps):
+//   y[m] = sum_i poly[(m*down + half_len) % up][i] * x[(m*down + half_len) / up - i]
+struct ResamplerDesign {
+    int up = 1, down = 1;        // target/orig in lowest terms
+    int half_len = 0;            // centre of the prototype (taps = 2 * half_len + 1)
+    int taps_per_phase = 0;      // K, multiple of 4
+    std::vector<float> poly;     // [up][K]
+};
+constexpr int kResampleMaxUp = 4096;
+bool design_resampler(int orig_sr, int target_sr, ResamplerDesign* d, const char** err);
+
 // ---- CQT plan (librosa.cqt = vqt(gamma=0, intervals="equal")) ---------------------------
 struct CqtOctave {
     int n_fft = 0;          // power of two >= longest wavelet of this octave

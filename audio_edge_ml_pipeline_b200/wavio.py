@@ -4,8 +4,9 @@
 What is covered: RIFF/WAVE PCM 8/16/24/32-bit and IEEE float 32/64, WAVE_FORMAT_EXTENSIBLE,
 offset/duration slicing in native frames, channel mean.  Mono PCM16 is returned as int16 (the
 GPU path applies the exact /32768); everything else as float32 scaled like libsndfile.
-What is NOT covered yet: files whose rate differs from ``sample_rate`` (librosa
-resamples with soxr_hq) and non-WAV containers — both raise, and the caller skips the sample the
+Files whose rate differs from ``sample_rate`` are resampled on the GPU (``resample_audio``; the
+reference uses soxr_hq, see DESIGN.md for the stand-in's specification).  What is NOT covered
+(SURVEY 8f N2): non-WAV containers — these raise, and the caller skips the sample the
 way the reference skips any failing sample (base.py:204-206).
 """
 
@@ -113,12 +114,19 @@ def load_segment(path, sample_rate: int, start_time, end_time, min_duration: flo
         raise AudioDecodeError(f"unsupported container {Path(path).suffix!r} (WAV only; SURVEY 8f N2)")
     audio, sr = decode_wav(path, offset, duration)
     if sr != sample_rate:
-        raise AudioDecodeError(
-            f"file rate {sr} != sample_rate {sample_rate}: resampling (soxr_hq in the reference) is not "
-            "implemented on this path yet (SURVEY 8f N2)")
+        audio = resample_audio(audio, sr, sample_rate)      # librosa.load resamples here (soxr_hq)
     if len(audio) < min_samples:
         audio = np.pad(audio, (0, min_samples - len(audio)))
     return audio
+
+
+def resample_audio(audio: np.ndarray, orig_sr: int, target_sr: int, device: int = 0) -> np.ndarray:
+    """What ``librosa.load(..., sr=target_sr)`` does to a file recorded at another rate
+    (deep.py:44-50): float32 mono at ``target_sr``, ``ceil(n * target / orig)`` samples.  Runs on the
+    GPU (``b2a_resampler_*``; no CPU path: without a device this raises and the sample is skipped
+    like any failing sample, base.py:204-206)."""
+    from . import _lib
+    return _lib.resample(audio, orig_sr, target_sr, device)
 
 
 def pad_or_trim(audio: np.ndarray, target_len: int) -> np.ndarray:

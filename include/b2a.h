@@ -130,6 +130,30 @@ int b2a_decode_wav_pcm16_batch(const char* const* paths, int64_t n_files, int32_
                                const double* offset_s, const double* duration_s, int32_t n_samples,
                                int16_t* dst, int32_t* status, int32_t n_threads);
 
+/* Rational resampler for files whose rate differs from `sample_rate` — what librosa.load does
+ * with soxr_hq inside `_load_segment` (deep.py:44-50) before any extractor sees the samples.
+ * Zero-phase Kaiser-sinc low-pass (pass band to 0.913 x, stop band from 1.0 x the lower Nyquist,
+ * 125 dB: the CQT decimator's specification), zero-extended edges, output length
+ * ceil(n_in * target / orig) as librosa.resample fixes it, float32 out (int16 input is scaled by
+ * 1/32768 like librosa.load).  One signal per call; `in_dtype` is B2A_IN_I16 or B2A_IN_F32.
+ * A resampler belongs to one (device, orig, target) and one thread at a time; no CPU path.
+ * b2a_resampler_geometry exposes up/down (target/orig in lowest terms), the prototype's half
+ * length and the polyphase table [up][taps_per_phase] for verification. */
+typedef struct b2a_resampler b2a_resampler;
+int b2a_resampler_create(int32_t orig_sr, int32_t target_sr, int32_t device, b2a_resampler** out);
+int b2a_resampler_destroy(b2a_resampler* r);
+int64_t b2a_resampler_out_len(const b2a_resampler* r, int64_t n_in);
+int b2a_resampler_geometry(const b2a_resampler* r, int32_t* up, int32_t* down, int32_t* half_len,
+                           int32_t* taps_per_phase, float* poly);
+/* The same design without a device (host only): query sizes with poly == NULL, then pass a buffer
+ * of up * taps_per_phase floats. */
+int b2a_resampler_design(int32_t orig_sr, int32_t target_sr, int32_t* up, int32_t* down, int32_t* half_len,
+                         int32_t* taps_per_phase, float* poly, int64_t poly_capacity);
+int b2a_resampler_run_host(b2a_resampler* r, const void* in, int32_t in_dtype, int64_t n_in, float* out);
+int b2a_resampler_run_device(b2a_resampler* r, const void* d_in, int32_t in_dtype, int64_t n_in,
+                             float* d_out, void* stream);
+const char* b2a_resampler_last_error(void);
+
 /* Number of CUDA kernel launches the last b2a_run_* call on this handle enqueued. */
 int64_t b2a_last_launch_count(const b2a_handle* h);
 

@@ -267,6 +267,43 @@ def decimate2(y: np.ndarray) -> np.ndarray:
     return (out * np.sqrt(2.0)).astype(np.float32)
 
 
+def resampler_prototype(orig_sr: int, target_sr: int):
+    """(up, down, half_len, g): the rational resampler's prototype low-pass, float64, unity DC
+    gain, running at up x orig_sr.  Same specification as halfband_taps() scaled to the ratio
+    (2:1 reproduces it exactly); the CUDA library evaluates the same closed form
+    (csrc/tables.cpp: design_resampler)."""
+    from math import gcd
+    g_ = gcd(int(orig_sr), int(target_sr))
+    up, down = int(target_sr) // g_, int(orig_sr) // g_
+    lo = float(min(orig_sr, target_sr))
+    fs_up = float(up) * float(orig_sr)
+    half = int(np.floor(95.5 * fs_up / lo + 0.5))
+    beta = 0.1102 * (HALFBAND_ATTEN_DB - 8.7)
+    fc = 0.5 * (HALFBAND_PASS + HALFBAND_STOP) * 0.5 * lo / fs_up
+    m = np.arange(-half, half + 1, dtype=np.float64)
+    h = 2.0 * fc * np.sinc(2.0 * fc * m)
+    w = np.i0(beta * np.sqrt(np.maximum(0.0, 1.0 - (m / half) ** 2))) / np.i0(beta)
+    h = h * w
+    h /= h.sum()
+    return up, down, half, h
+
+
+def resample_restated(y: np.ndarray, orig_sr: int, target_sr: int) -> np.ndarray:
+    """Stand-in for ``librosa.resample(y, orig_sr=, target_sr=, res_type="soxr_hq")`` as
+    ``librosa.load`` applies it (deep.py:44-50): zero-phase FIR, zero-extended edges, output length
+    ceil(n * target / orig).  Parity against libsoxr itself is unpinned (absent offline).
+    Taps are float32-rounded (what the GPU holds), arithmetic float64 through scipy's own
+    polyphase engine (an independent check of the indexing), output float32."""
+    import scipy.signal
+    y = np.asarray(y, dtype=np.float32)
+    if int(orig_sr) == int(target_sr):
+        return y.copy()
+    up, down, _half, g = resampler_prototype(orig_sr, target_sr)
+    g32 = (g * up).astype(np.float32).astype(np.float64) / up       # resample_poly multiplies by `up` itself
+    out = scipy.signal.resample_poly(y.astype(np.float64), up, down, window=g32, padtype="constant")
+    return out.astype(np.float32)
+
+
 # --------------------------------------------------------------------------------------
 # librosa 0.11.0: cqt = vqt(gamma=0, intervals='equal')
 # --------------------------------------------------------------------------------------
