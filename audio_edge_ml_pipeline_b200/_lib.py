@@ -303,6 +303,11 @@ class Resampler:
                                                    out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def run_device(self, d_in: int, in_dtype: int, n_in: int, d_out: int, stream: int = 0) -> None:
+        """Device pointers, asynchronous on `stream`; d_out must hold out_len(n_in) floats."""
+        _check_rs(self._lib.b2a_resampler_run_device(self._h, C.c_void_p(d_in), in_dtype, n_in,
+                                                     C.c_void_p(d_out), C.c_void_p(stream)))
+
     def close(self) -> None:
         if self._h:
             self._lib.b2a_resampler_destroy(self._h)

@@ -30,3 +30,27 @@ run(B.KIND_MEL, 20000, n_samples=80000, n_fft=256, hop_length=128, n_mels=40)
 run(B.KIND_MFCC, 20000, n_samples=80000, sample_rate=16000, n_fft=512, hop_length=160, n_mels=40, n_mfcc=13)
 run(B.KIND_MFCC, 10000, n_samples=110250)          # reference defaults 22050/1024/512/128 -> 40
 run(B.KIND_CQT, 4096, n_samples=110250)
+
+
+def run_resampler(orig, target, seconds=5.0, reps=200):
+    n = int(seconds * orig)
+    x = (torch.randn(n, device="cuda") * 3276.8).round().clamp(-32768, 32767).to(torch.int16)
+    with B.Resampler(orig, target) as r:
+        out = torch.empty(r.out_len(n), dtype=torch.float32, device="cuda")
+        st = torch.cuda.current_stream().cuda_stream
+        for _ in range(5): r.run_device(x.data_ptr(), B.IN_I16, n, out.data_ptr(), st)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps): r.run_device(x.data_ptr(), B.IN_I16, n, out.data_ptr(), st)
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        up, down, half, poly = B.resampler_design(orig, target)
+    macs = r.out_len(n) * poly.shape[1] if False else int(np.ceil(n * target / orig)) * poly.shape[1]
+    print(json.dumps(dict(resampler=f"{orig}->{target}", clip_s=seconds, us_per_clip=ms * 1e3, clips_per_s=1e3 / ms,
+                          taps_per_output=int(poly.shape[1]), gmac_per_s=macs / ms / 1e6)), flush=True)
+
+run_resampler(44100, 16000)
+run_resampler(48000, 16000)
+run_resampler(22050, 16000)
+run_resampler(44100, 22050)
