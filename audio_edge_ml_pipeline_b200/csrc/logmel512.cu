@@ -286,6 +286,16 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     for (int t = 8; t < 16; ++t) mst[(t - 8) * 16] = v[t];
                     mst[8 * 16] = v[0];                                // "row 16": Z[256] == Z[0] for lane 0
                     __syncwarp();
+                    // all eight mirror operands in flight at once (v[9..15] are dead by now): left to
+                    // itself ptxas loads them one per split step and every step eats the latency
+                    float2 Bm[8];
+                    {
+                        const uint32_t ma = smem_u32(mld);
+#define B2A_LDM(R2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" \
+                                 : "=f"(Bm[R2].x), "=f"(Bm[R2].y) : "r"(ma), "n"((7 - (R2)) * 16 * 8))
+                        B2A_LDM(0); B2A_LDM(1); B2A_LDM(2); B2A_LDM(3); B2A_LDM(4); B2A_LDM(5); B2A_LDM(6); B2A_LDM(7);
+#undef B2A_LDM
+                    }
                     if (!pow_free) {                                   // the mel warps are done with this slot
                         mbar_wait(bar_pow_empty + pb, ((it / NPOW) & 1) ^ 1);
                         pow_free = true;
@@ -295,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     float* pn = pw + ((NC - j) >> 1) * PROW + 2 * f + (j & 1);          // bin 256 - j - 16 r2
 #pragma unroll
                     for (int r2 = 0; r2 < 8; ++r2) {
-                        const float2 B = mld[(7 - r2) * 16];
+                        const float2 B = Bm[r2];
                         float4 w4;
                         if ((r2 & 1) == 0) w4 = t2[16 * (r2 >> 1)];
                         const float2 w = (r2 & 1) ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);
