@@ -303,17 +303,28 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     // element (bin k, frame f) lives at word (k>>1)*PROW + 2f + (k&1)
                     float* pk = pw + (j >> 1) * PROW + 2 * f + (j & 1);                 // bin j + 16 r2
                     float* pn = pw + ((NC - j) >> 1) * PROW + 2 * f + (j & 1);          // bin 256 - j - 16 r2
+                    // split twiddles, two per 128-bit load, fetched one pair of steps ahead
+                    const uint32_t ta = smem_u32(t2);
+                    float4 w4, w4n;
+#define B2A_LDT(DST, P) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" \
+                                     : "=f"(DST.x), "=f"(DST.y), "=f"(DST.z), "=f"(DST.w) : "r"(ta), "n"((P) * 16 * 16))
+                    B2A_LDT(w4n, 0);
 #pragma unroll
                     for (int r2 = 0; r2 < 8; ++r2) {
                         const float2 B = Bm[r2];
-                        float4 w4;
-                        if ((r2 & 1) == 0) w4 = t2[16 * (r2 >> 1)];
+                        if ((r2 & 1) == 0) {
+                            w4 = w4n;
+                            if (r2 == 0) B2A_LDT(w4n, 1);
+                            if (r2 == 2) B2A_LDT(w4n, 2);
+                            if (r2 == 4) B2A_LDT(w4n, 3);
+                        }
                         const float2 w = (r2 & 1) ? make_float2(w4.z, w4.w) : make_float2(w4.x, w4.y);
                         float2 xk, xnk;
                         rfft_split(v[r2], B, w, xk, xnk);              // 2 X[k], 2 X[256-k]
                         pk[8 * r2 * PROW] = xk.x * xk.x + xk.y * xk.y;         // 4|X|^2: the 1/4 lives
                         pn[-8 * r2 * PROW] = xnk.x * xnk.x + xnk.y * xnk.y;    // in the mel weights
                     }
+#undef B2A_LDT
                     if (j == 0) pw[(NC / 4) * PROW + 2 * f] = 4.0f * (v[8].x * v[8].x + v[8].y * v[8].y);
                     __syncwarp();
                 }
