@@ -265,8 +265,17 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     if constexpr (I16) {
                         // one 32-bit word = one packed complex point (two int16 samples)
                         const uint32_t* a = reinterpret_cast<const uint32_t*>(cur) + ((f * hop) >> 1) + j;
+                        // all sixteen words in flight before the first conversion
+                        uint32_t rw[16];
+                        {
+                            const uint32_t ra = smem_u32(a);
+#define B2A_LDR(T) asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(rw[T]) : "r"(ra), "n"((T) * 64))
+                            B2A_LDR(0); B2A_LDR(1); B2A_LDR(2); B2A_LDR(3); B2A_LDR(4); B2A_LDR(5); B2A_LDR(6); B2A_LDR(7);
+                            B2A_LDR(8); B2A_LDR(9); B2A_LDR(10); B2A_LDR(11); B2A_LDR(12); B2A_LDR(13); B2A_LDR(14); B2A_LDR(15);
+#undef B2A_LDR
+                        }
 #pragma unroll
-                        for (int t = 0; t < 16; ++t) v[t] = __fmul2_rn(cvt_pcm2(a[16 * t]), win[t]);
+                        for (int t = 0; t < 16; ++t) v[t] = __fmul2_rn(cvt_pcm2(rw[t]), win[t]);
                     } else {
                         const float* a = cur + f * hop + 2 * j;
 #pragma unroll
