@@ -49,7 +49,10 @@ constexpr int kMelThreads = 32 * kMelWarps;
 constexpr int kFftRegs = 104, kMelRegs = 64;    // 512*112 + 128*32 = 640*96 (the launch allocation)
 constexpr int NC = 256, NFFT = 512, F = 32;     // complex points, frame length, frames per tile
 constexpr int ROUNDS = F / (2 * kFftWarps);     // rounds of 2 frames per FFT warp per tile
-constexpr int NRAW = 4;                         // ring depth of raw PCM tiles
+// ring depth of raw PCM tiles: 4 for int16; float32 input doubles a slot, so 3 (mel) / 2 (mfcc, which
+// also carries the dB tile, the DCT basis and the partial sums) keep the CTA inside 227 KB
+__host__ __device__ constexpr int nraw(bool i16, bool mfcc) { return i16 ? 4 : (mfcc ? 2 : 3); }
+constexpr int kMaxRaw = 4;
 // ring depth of power tiles: 3 absorbs the mel warps' per-clip normalisation pause; float32 input
 // doubles the raw ring, leaving room for 2
 __host__ __device__ constexpr int npow(bool i16) { return i16 ? 2 : 2; }
@@ -150,14 +153,14 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     L.raw_bytes = (L.chunk * (i16 ? 2 : 4) + 15) & ~15;
-    L.off_raw = take(NRAW * L.raw_bytes);             // ring of raw PCM tiles, read directly by pass 1
+    L.off_raw = take(nraw(i16, mfcc) * L.raw_bytes);  // ring of raw PCM tiles, read directly by pass 1
     L.off_xch = take(2 * kFftWarps * XSLOT * 8);      // one exchange slot per half-warp
     L.off_pow = take(npow(i16) * PROWS * PROW * 4);   // ring of power tiles
     L.off_tw2 = take(8 * 16 * 8);
     L.off_melw = take(mel_wpad * 4);
     L.off_melk = take(n_mels * 16);
     L.off_red = take((64 + 2 * kZFast) * 4);          // per-warp max/min, then (mean, sd) per coefficient
-    L.off_bar = take((NRAW + 2 * 3) * 8);
+    L.off_bar = take((kMaxRaw + 2 * 3) * 8);
     L.off_db = take(mfcc ? n_mels * 32 * 4 : 0);      // mfcc: [n_mels][32] dB tile feeding the in-tile DCT
     L.off_part = take(mfcc && n_mfcc <= kZFast ? 2 * kMelWarps * n_mfcc * 32 * 4 : 0);   // generated DCT: partial sums
     L.gp = 4 * ((((n_mfcc + kMelWarps - 1) / kMelWarps) + 3) / 4);
@@ -182,10 +185,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
     float* const s_dct = reinterpret_cast<float*>(smem + L.off_dct);
     float* const s_part = reinterpret_cast<float*>(smem + L.off_part);
     uint64_t* const bar_raw_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    uint64_t* const bar_pow_full = bar_raw_full + NRAW;
+    uint64_t* const bar_pow_full = bar_raw_full + kMaxRaw;
     uint64_t* const bar_pow_empty = bar_pow_full + 3;
 
     constexpr int NPOW = npow(I16);
+    constexpr int NRAW = nraw(I16, KIND >= 1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int hop = p.hop, n_mels = p.n_mels, chunk = L.chunk;
     using E = typename std::conditional<I16, int16_t, float>::type;

@@ -9,6 +9,8 @@ def run(kind, n_clips, **kw):
     for k, v in kw.items(): setattr(cfg, k, v)
     e = B.Engine(cfg, 0)
     x = (torch.randn((n_clips, cfg.n_samples), device="cuda") * 3276.8).round().clamp(-32768, 32767).to(torch.int16)
+    if cfg.input_dtype == B.IN_F32:
+        x = x.to(torch.float32) / 32768.0
     out = torch.empty((n_clips, e.rows, e.frames), dtype=torch.float32, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     for _ in range(3): e.run_device(x.data_ptr(), n_clips, out.data_ptr(), st)
@@ -24,6 +26,7 @@ def run(kind, n_clips, **kw):
     e.close()
 
 run(B.KIND_MEL, 20000, n_samples=80000)
+run(B.KIND_MEL, 20000, n_samples=80000, input_dtype=B.IN_F32)
 run(B.KIND_MEL, 20000, n_samples=80000, n_fft=1024, hop_length=256, n_mels=64)
 run(B.KIND_MEL, 10000, n_samples=110250, sample_rate=22050, n_fft=2048, hop_length=512, n_mels=128)
 run(B.KIND_MEL, 20000, n_samples=80000, n_fft=256, hop_length=128, n_mels=40)
