@@ -57,6 +57,10 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     tgt = CSRC / "gen" / "mel_special.inc"
     if not tgt.exists() or tgt.read_text() != inc:
         tgt.write_text(inc)
+    inc2 = subprocess.run([str(gen), "decim"], check=True, capture_output=True, text=True).stdout
+    tgt2 = CSRC / "gen" / "decim_taps.inc"
+    if not tgt2.exists() or tgt2.read_text() != inc2:
+        tgt2.write_text(inc2)
     flags = list(NVCC_FLAGS) + os.environ.get("B2A_NVCC_EXTRA", "").split()
     procs = []
     objs = []

@@ -11,9 +11,12 @@
 // below the peak, so it runs on the CUDA cores as a banded complex dot product, not on tcgen05.
 #include "cqt.h"
 #include "fft_core.cuh"
+#include "gen/decim_taps.inc"   // build-time generated decimator taps (gen_mel.cpp decim)
 
 #include <algorithm>
 #include <cmath>
+#include <cstdint>
+#include <type_traits>
 
 namespace b2a {
 
@@ -35,35 +38,76 @@ constexpr int kDecLocal = kDecTile + kDecHalf;  // staged polyphase samples per 
 __device__ __forceinline__ int dpad(int q) { return q + (q >> 5); }
 
 template <bool I16>
-__global__ void __launch_bounds__(kDecThreads) cqt_decimate_kernel(
+__global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
     const void* __restrict__ in, size_t in_stride, int in_len, float* __restrict__ out,
     size_t out_stride, int out_len, const float* __restrict__ taps) {
     __shared__ float sA[kDecLocal + kDecLocal / 32 + 2];
     __shared__ float sB[kDecLocal + kDecLocal / 32 + 2];
-    __shared__ float sh[2 * kDecHalf];
+    static_assert(kDecimTapsGen == kDecimTaps, "regenerate gen/decim_taps.inc");
+    (void)taps;                                   // the taps are compile-time constants now
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * kDecTile;
     const size_t clip = blockIdx.y;
-    // contiguous input range feeding this tile: n = nstart + idx, idx in [0, 2*kDecLocal)
+    // contiguous input range feeding this tile: n = nstart + idx, idx in [0, 2*kDecLocal); even idx
+    // feeds B (odd taps), odd idx feeds A.  nstart is even, so one 32-bit (int16) / 64-bit (float)
+    // load brings the pair (B[l], A[l]); the loads of a batch are all issued before the first
+    // conversion (one DRAM round trip per batch instead of one per sample — staging was a third
+    // of this kernel's time).
     const int nstart = 2 * (m0 - (kDecHalf - 1)) + 190;
-    for (int idx = tid; idx < 2 * kDecLocal; idx += kDecThreads) {
-        const int nn = nstart + idx;
-        float v = 0.f;
-        if (nn >= 0 && nn < in_len) {
-            if (I16) v = (float)((const int16_t*)in)[clip * in_stride + nn] * (1.0f / 32768.0f);
-            else v = ((const float*)in)[clip * in_stride + nn];
+    {
+        using PairT = typename std::conditional<I16, uint32_t, float2>::type;
+        const unsigned char* base = (const unsigned char*)in + (clip * in_stride) * (I16 ? 2 : 4);
+        const bool pair_ok = (reinterpret_cast<uintptr_t>(base) & (sizeof(PairT) - 1)) == 0;
+        constexpr int kBatch = 9;
+        constexpr int kIters = (kDecLocal + kDecThreads - 1) / kDecThreads;      // 18
+#pragma unroll 1
+        for (int k0 = 0; k0 < kIters; k0 += kBatch) {
+            PairT raw[kBatch];
+            int state[kBatch];                       // 0: outside the tile, 1: pair load, 2: edge / unaligned
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int l = tid + (k0 + u) * kDecThreads;
+                const int nn = nstart + 2 * l;
+                state[u] = (k0 + u < kIters && l < kDecLocal) ? ((pair_ok && nn >= 0 && nn + 1 < in_len) ? 1 : 2) : 0;
+                if (state[u] == 1) raw[u] = __ldg(reinterpret_cast<const PairT*>(base + (size_t)nn * (I16 ? 2 : 4)));
+            }
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (state[u] == 0) continue;
+                const int l = tid + (k0 + u) * kDecThreads;
+                const int nn = nstart + 2 * l;
+                float vb, va;
+                if (state[u] == 1) {
+                    if constexpr (I16) {
+                        const uint32_t w = raw[u];
+                        vb = __int2float_rn((int)(short)(w & 0xffffu)) * (1.0f / 32768.0f);
+                        va = __int2float_rn((int)w >> 16) * (1.0f / 32768.0f);
+                    } else {
+                        vb = raw[u].x; va = raw[u].y;
+                    }
+                } else {
+                    auto one = [&](int n1) -> float {
+                        if (n1 < 0 || n1 >= in_len) return 0.f;
+                        if (I16) return __int2float_rn((int)((const int16_t*)base)[n1]) * (1.0f / 32768.0f);
+                        return ((const float*)base)[n1];
+                    };
+                    vb = one(nn); va = one(nn + 1);
+                }
+                sB[dpad(l)] = vb;
+                sA[dpad(l)] = va;
+            }
         }
-        const int l = idx >> 1;
-        if (idx & 1) sA[dpad(l)] = v; else sB[dpad(l)] = v;
     }
-    for (int i = tid; i < 2 * kDecHalf; i += kDecThreads) sh[i] = (i < kDecimTaps) ? taps[i] : 0.f;
     __syncthreads();
 
     // Accumulation order and precision matter here: six cascaded stages feed CQT bins that sit
     // 80 dB below the clip's peak.  The 32 taps around the centre carry almost all of the filter's
-    // energy and are accumulated in fp64 (B200 issues DFMA at half the FFMA rate); the 351 small
+    // energy and are accumulated in fp64 (B200 issues DFMA at ~0.64 of the FFMA rate, tools/ubench/dfma.cu); the 351 small
     // outer taps run in fp32 from the tails inwards so their running sums stay small.  The oracle
     // accumulates everything in float64 (oracle/librosa_restated.py: decimate2).
+    // The taps come from constant memory through the uniform datapath (gen/decim_taps.inc), indexed by
+    // the loop-uniform chunk: the shared-memory pipe only carries the samples (with the taps staged
+    // next to them it was 97 % busy).
     float acc[kDecR];
     double accd[kDecR];
 #pragma unroll
@@ -78,7 +122,7 @@ __global__ void __launch_bounds__(kDecThreads) cqt_decimate_kernel(
         for (int d = 0; d < kDecR + kDecU - 1; ++d) { xa[d] = sA[dpad(l0 + d)]; xb[d] = sB[dpad(l0 + d)]; }
 #pragma unroll
         for (int u = 0; u < kDecU; ++u) {
-            const float he = sh[2 * (i0 + u)], ho = sh[2 * (i0 + u) + 1];
+            const float he = kDecTapF[2 * (i0 + u)], ho = kDecTapF[2 * (i0 + u) + 1];
 #pragma unroll
             for (int r = 0; r < kDecR; ++r) {
                 acc[r] = fmaf(he, xa[r - u + kDecU - 1], acc[r]);
@@ -100,7 +144,7 @@ __global__ void __launch_bounds__(kDecThreads) cqt_decimate_kernel(
         for (int d = 0; d < kDecR + kDecU - 1; ++d) { xa[d] = (double)sA[dpad(l0 + d)]; xb[d] = (double)sB[dpad(l0 + d)]; }
 #pragma unroll
         for (int u = 0; u < kDecU; ++u) {
-            const double he = (double)sh[2 * (i0 + u)], ho = (double)sh[2 * (i0 + u) + 1];
+            const double he = (double)kDecTapF[2 * (i0 + u)], ho = (double)kDecTapF[2 * (i0 + u) + 1];
 #pragma unroll
             for (int r = 0; r < kDecR; ++r) {
                 accd[r] = fma(he, xa[r - u + kDecU - 1], accd[r]);
