@@ -557,6 +557,14 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                             if (i < nq_n4) nq[i] = nrm4(nx[k]);
                         }
                         nq_done += NPF * kMelThreads;
+                        // more bands than the prefetched slices cover per tile (n_mels > 48): the rest of
+                        // this tile's share goes without prefetch, so the backlog never reaches the
+                        // end-of-clip flush
+                        for (int more = (n_mels * (F / 4) + kMelThreads - 1) / kMelThreads - NPF; more > 0; --more) {
+                            const int i = nq_done + mtid;
+                            if (i < nq_n4) nq[i] = nrm4(nq[i]);
+                            nq_done += kMelThreads;
+                        }
                     } else {
 #pragma unroll
                         for (int k = 0; k < NPZ; ++k) {
@@ -564,6 +572,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                             if (i < nq_n4) nz[i] = zs1(zx[k], i);
                         }
                         nq_done += NPZ * kMelThreads;
+                        for (int more = (p.n_mfcc * F + kMelThreads - 1) / kMelThreads - NPZ; more > 0; --more) {
+                            const int i = nq_done + mtid;
+                            if (i < nq_n4) nz[i] = zs1(nz[i], i);
+                            nq_done += kMelThreads;
+                        }
                     }
                     if (tile + 1 == tiles) nq_finish();            // short clip after a long one
                 }
