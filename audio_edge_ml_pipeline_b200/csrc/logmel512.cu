@@ -560,10 +560,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                         // more bands than the prefetched slices cover per tile (n_mels > 48): the rest of
                         // this tile's share goes without prefetch, so the backlog never reaches the
                         // end-of-clip flush
-                        for (int more = (n_mels * (F / 4) + kMelThreads - 1) / kMelThreads - NPF; more > 0; --more) {
-                            const int i = nq_done + mtid;
-                            if (i < nq_n4) nq[i] = nrm4(nq[i]);
-                            nq_done += kMelThreads;
+                        if constexpr (!SPEC) {       // (the generated configuration has 40 bands: nothing left)
+                            for (int more = (n_mels * (F / 4) + kMelThreads - 1) / kMelThreads - NPF; more > 0; --more) {
+                                const int i = nq_done + mtid;
+                                if (i < nq_n4) nq[i] = nrm4(nq[i]);
+                                nq_done += kMelThreads;
+                            }
                         }
                     } else {
 #pragma unroll
@@ -572,10 +574,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                             if (i < nq_n4) nz[i] = zs1(zx[k], i);
                         }
                         nq_done += NPZ * kMelThreads;
-                        for (int more = (p.n_mfcc * F + kMelThreads - 1) / kMelThreads - NPZ; more > 0; --more) {
-                            const int i = nq_done + mtid;
-                            if (i < nq_n4) nz[i] = zs1(nz[i], i);
-                            nq_done += kMelThreads;
+                        if constexpr (KIND != 2) {   // (13 coefficients x 32 frames = 4 slices: nothing left)
+                            for (int more = (p.n_mfcc * F + kMelThreads - 1) / kMelThreads - NPZ; more > 0; --more) {
+                                const int i = nq_done + mtid;
+                                if (i < nq_n4) nz[i] = zs1(nz[i], i);
+                                nq_done += kMelThreads;
+                            }
                         }
                     }
                     if (tile + 1 == tiles) nq_finish();            // short clip after a long one
