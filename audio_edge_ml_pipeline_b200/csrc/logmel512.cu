@@ -1,28 +1,30 @@
 // logmel512.cu — the headline kernel: n_fft = 512 fused log-mel / MFCC front end, sm_100a only.
 //
 // One persistent, warp-specialised CTA per SM (640 threads):
-//   * 16 FFT warps (setmaxnreg 112).  One half-warp per frame, 16 complex points per lane in
+//   * 16 FFT warps (setmaxnreg 104).  One half-warp per frame, 16 complex points per lane in
 //     registers for both radix-16 passes of the 256-point packed FFT, all complex arithmetic in
 //     packed FP32 (FADD2 / FMUL2 / FFMA2, fft_core.cuh).  Pass 1 reads the packed int16 pairs
 //     straight from the raw PCM tile (one 32-bit word = one complex point) and widens them in
 //     registers, the exact 1/32768 riding on the window; pass-2 results never leave registers —
 //     only the 8 rows the mirror lane needs go through shared memory (X[k] needs Z[k] and
 //     Z[256-k], which lives in lane 16-j).  4|X|^2 goes to a [bin pair][frame] power tile.
+//     Raw words, mirror operands and split twiddles are issued as explicit batches of loads.
 //     These warps never touch global memory and never meet a CTA-wide barrier.
-//   * 4 mel warps (setmaxnreg 32).  Warp 0's lane 0 is the TMA producer: one cp.async.bulk per
-//     32-frame tile of raw PCM into a 3-deep ring, issued three tiles ahead (also across clip
-//     boundaries).  All four consume power tiles (2-deep ring): lane = frame, band warp-uniform;
-//     for the headline configuration the band sweep is generated at build time (gen_mel.cpp)
-//     with the 490 filter weights as FFMA immediates and every power pair loaded once.  Raw dB
-//     goes to the output buffer (L2-resident), per-clip max/min stay in registers, and after a
-//     clip's last tile the same warps normalise it in place (mfcc: in-tile DCT-II, recomputed
-//     from an L2 scratch only when the top_db clip engages, then a z-score per row).
+//   * 4 mel warps (setmaxnreg 64).  Warp 0 is also the TMA producer: one cp.async.bulk per
+//     32-frame tile of raw PCM into a ring (4 slots for int16 clips), issued a ring ahead (also
+//     across clip boundaries).  All four consume power tiles (2-deep ring): lane = frame, band
+//     warp-uniform; for the headline configuration the band sweep is generated at build time
+//     (gen_mel.cpp) with the 490 filter weights as FFMA immediates and every power pair loaded
+//     once.  Raw dB goes to the output buffer (L2-resident), per-clip max/min stay in registers,
+//     and a clip is normalised in place during the NEXT clip's tiles, a prefetched slice per tile
+//     (mfcc: in-tile DCT-II, recomputed from an L2 scratch only when the top_db clip engages,
+//     z-score statistics from running sums, rows rewritten by the same deferred pass).
 //   * Hand-off by mbarriers only: raw_full (TMA tx bytes) -> FFT; pow_full (16 warp arrivals)
 //     -> mel; pow_empty (4 warp arrivals) -> FFT.  pow_full of tile i also tells the producer
-//     that raw slot i % 3 is free again.
-// The FFT phase is FMA-pipe bound; mel, dB, normalisation, staging and every global access now
-// overlap it instead of alternating with it (profiles/: the phase-alternating predecessor spent
-// 58 % of its time in the FFT rounds).
+//     that the raw slot of tile i is free again.
+// The FFT warps are bound by the FMA and shared-memory pipes; mel, dB, normalisation, staging and
+// every global access overlap them instead of alternating with them (the phase-alternating
+// predecessor spent 58 % of its time in the FFT rounds).
 //
 // Reference arithmetic: deep.py:126-134 (mel), :318-328 (mfcc) via librosa 0.11.0.
 #include "frontend.h"
