@@ -56,6 +56,9 @@ int ilog2(int x) {
 
 }  // namespace
 
+// other translation units of the library (resample.cu) report through the same thread-local text
+void b2a_internal_set_error(const char* msg) { g_err = msg ? msg : ""; }
+
 struct b2a_handle {
     b2a_config cfg{};
     int device = 0, sm_count = 0;

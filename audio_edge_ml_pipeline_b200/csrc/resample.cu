@@ -24,6 +24,8 @@
 
 #include "tables.h"
 
+void b2a_internal_set_error(const char* msg);      // api.cu
+
 namespace {
 
 constexpr int kThreads = 256;
@@ -80,7 +82,11 @@ struct b2a_resampler {
 
 namespace {
 
-int rs_fail(int code, const std::string& msg) { g_rs_err = msg; return code; }
+int rs_fail(int code, const std::string& msg) {
+    g_rs_err = msg;
+    b2a_internal_set_error(msg.c_str());          // b2a_last_error() sees it too
+    return code;
+}
 
 #define RS_TRY(expr)                                                                      \
     do {                                                                                  \

@@ -152,7 +152,7 @@ int b2a_resampler_design(int32_t orig_sr, int32_t target_sr, int32_t* up, int32_
 int b2a_resampler_run_host(b2a_resampler* r, const void* in, int32_t in_dtype, int64_t n_in, float* out);
 int b2a_resampler_run_device(b2a_resampler* r, const void* d_in, int32_t in_dtype, int64_t n_in,
                              float* d_out, void* stream);
-const char* b2a_resampler_last_error(void);
+const char* b2a_resampler_last_error(void);   /* same text b2a_last_error() returns after a resampler call */
 
 /* Number of CUDA kernel launches the last b2a_run_* call on this handle enqueued. */
 int64_t b2a_last_launch_count(const b2a_handle* h);
