@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
         const bool zfast = MFCC && p.n_mfcc <= kZFast;
         auto zs1 = [&](float x, int i) {
             const int k = __float2int_rd(((float)i + 0.5f) * nz_inv);    // row of element i (never near an integer)
-            return __fdiv_rn(x - s_zs[2 * k], s_zs[2 * k + 1]);
+            return (x - s_zs[2 * k]) * s_zs[2 * k + 1];                   // s_zs = (mean, 1 / (sd + 1e-8))
         };
         auto nq_finish = [&]() {                                 // whatever is left of the previous clip
             if constexpr (!MFCC) {
@@ -730,7 +730,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                         if (lane == 0 && k < p.n_mfcc) {
                             const float md = __fdiv_rn(S, fn);
                             s_zs[2 * k] = zx0[g] + md;
-                            s_zs[2 * k + 1] = sqrtf(fmaxf(fmaf(-md, md, __fdiv_rn(Q, fn)), 0.f)) + 1e-8f;
+                            s_zs[2 * k + 1] = __fdiv_rn(1.0f, sqrtf(fmaxf(fmaf(-md, md, __fdiv_rn(Q, fn)), 0.f)) + 1e-8f);
                         }
                         zS[g] = 0.f; zQ[g] = 0.f;
                     }
