@@ -26,40 +26,45 @@ constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------------------------------
 // 2:1 decimator:  out[m] = sqrt(2) * sum_j h[j] y[2m + 191 - j],  j = 0..382, zero-extended.
-// Polyphase: A[q] = y[2q+191] meets the even taps, B[q] = y[2q+190] the odd taps.
+// Polyphase: A[q] = y[2q+191] meets the even taps, B[q] = y[2q+190] the odd taps.  (B[q], A[q]) are
+// neighbours in the input, so the staged tile is a plain copy of the signal as float2 pairs and
+// ONE packed FFMA2 advances both polyphase sums of an output: acc2 += (B, A) * (h_odd, h_even).
 // ------------------------------------------------------------------------------------------
 constexpr int kDecThreads = 128;
-constexpr int kDecR = 16;                       // consecutive outputs per thread
+constexpr int kDecR = 17;                       // consecutive outputs per thread; odd, so the 64-bit window
+                                                // loads of a half-warp (pair stride 17) hit 16 distinct bank
+                                                // pairs with no padding and constant offsets in the loop
 constexpr int kDecTile = kDecThreads * kDecR;   // outputs per CTA
-constexpr int kDecU = 8;                        // taps per register-window step
-constexpr int kDecHalf = 192;                   // taps per phase (odd phase zero-padded)
-constexpr int kDecLocal = kDecTile + kDecHalf;  // staged polyphase samples per phase
-
-__device__ __forceinline__ int dpad(int q) { return q + (q >> 5); }
+#ifndef B2A_DEC_U
+#define B2A_DEC_U 8
+#endif
+constexpr int kDecU = B2A_DEC_U;                // tap pairs per register-window step (8 or 11)
+constexpr int kDecHalf = 192;                   // tap pairs (the odd phase is zero-padded)
+constexpr int kDecMid = 16;                     // centre tap pairs accumulated in fp64: pairs [88, 104)
+constexpr int kDecOuter = (kDecHalf - kDecMid) / 2;   // 88 pairs on either side
+constexpr int kDecLocal = kDecTile + kDecHalf;  // staged sample pairs
+static_assert(kDecOuter % kDecU == 0, "outer taps must split into whole window steps");
 
 template <bool I16>
 __global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
     const void* __restrict__ in, size_t in_stride, int in_len, float* __restrict__ out,
     size_t out_stride, int out_len, const float* __restrict__ taps) {
-    __shared__ float sA[kDecLocal + kDecLocal / 32 + 2];
-    __shared__ float sB[kDecLocal + kDecLocal / 32 + 2];
+    __shared__ __align__(16) float2 s2[kDecLocal];      // s2[l] = (y[nstart + 2l], y[nstart + 2l + 1])
     static_assert(kDecimTapsGen == kDecimTaps, "regenerate gen/decim_taps.inc");
     (void)taps;                                   // the taps are compile-time constants now
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * kDecTile;
     const size_t clip = blockIdx.y;
-    // contiguous input range feeding this tile: n = nstart + idx, idx in [0, 2*kDecLocal); even idx
-    // feeds B (odd taps), odd idx feeds A.  nstart is even, so one 32-bit (int16) / 64-bit (float)
-    // load brings the pair (B[l], A[l]); the loads of a batch are all issued before the first
-    // conversion (one DRAM round trip per batch instead of one per sample — staging was a third
-    // of this kernel's time).
+    // contiguous input range feeding this tile: n = nstart + 2l (+1).  nstart is even, so one 32-bit
+    // (int16) / 64-bit (float) load brings a pair; the loads of a batch are all issued before the
+    // first conversion (one DRAM round trip per batch instead of one per sample).
     const int nstart = 2 * (m0 - (kDecHalf - 1)) + 190;
     {
         using PairT = typename std::conditional<I16, uint32_t, float2>::type;
         const unsigned char* base = (const unsigned char*)in + (clip * in_stride) * (I16 ? 2 : 4);
         const bool pair_ok = (reinterpret_cast<uintptr_t>(base) & (sizeof(PairT) - 1)) == 0;
-        constexpr int kBatch = 9;
-        constexpr int kIters = (kDecLocal + kDecThreads - 1) / kDecThreads;      // 18
+        constexpr int kBatch = 10;
+        constexpr int kIters = (kDecLocal + kDecThreads - 1) / kDecThreads;      // 19
 #pragma unroll 1
         for (int k0 = 0; k0 < kIters; k0 += kBatch) {
             PairT raw[kBatch];
@@ -93,8 +98,7 @@ __global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
                     };
                     vb = one(nn); va = one(nn + 1);
                 }
-                sB[dpad(l)] = vb;
-                sA[dpad(l)] = va;
+                s2[l] = make_float2(vb, va);
             }
         }
     }
@@ -102,62 +106,68 @@ __global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
 
     // Accumulation order and precision matter here: six cascaded stages feed CQT bins that sit
     // 80 dB below the clip's peak.  The 32 taps around the centre carry almost all of the filter's
-    // energy and are accumulated in fp64 (B200 issues DFMA at ~0.64 of the FFMA rate, tools/ubench/dfma.cu); the 351 small
-    // outer taps run in fp32 from the tails inwards so their running sums stay small.  The oracle
-    // accumulates everything in float64 (oracle/librosa_restated.py: decimate2).
-    // The taps come from constant memory through the uniform datapath (gen/decim_taps.inc), indexed by
-    // the loop-uniform chunk: the shared-memory pipe only carries the samples (with the taps staged
-    // next to them it was 97 % busy).
-    float acc[kDecR];
-    double accd[kDecR];
+    // energy and are accumulated in fp64 (B200 issues DFMA at ~0.64 of the FFMA rate,
+    // tools/ubench/dfma.cu); the 351 small outer taps run in packed fp32 from the tails inwards so
+    // their running sums stay small.  The oracle accumulates everything in float64
+    // (oracle/librosa_restated.py: decimate2).
+    // Tap pairs come from constant memory, indexed by the loop-uniform step: the shared-memory
+    // pipe only carries the samples.
+    const int lb = tid * kDecR + (kDecHalf - 1);     // local index of the pair (B[m_0], A[m_0]) of output r = 0
+    float2 acc2[kDecR];
 #pragma unroll
-    for (int r = 0; r < kDecR; ++r) { acc[r] = 0.f; accd[r] = 0.0; }
-    const int lb = tid * kDecR + (kDecHalf - 1);     // local index of A[m_0], B[m_0]
-    constexpr int kChunks = kDecHalf / kDecU;        // 24
-    constexpr int kMidLo = 11, kMidHi = 13;          // chunks [11,13) = taps j in [176, 208)
-    auto chunk_f32 = [&](int i0) {
-        float xa[kDecR + kDecU - 1], xb[kDecR + kDecU - 1];
-        const int l0 = lb - i0 - (kDecU - 1);
+    for (int r = 0; r < kDecR; ++r) acc2[r] = make_float2(0.f, 0.f);
+    auto step_f32 = [&](int i0) {                    // tap pairs [i0, i0 + kDecU)
+        float2 x[kDecR + kDecU - 1];
+        const float2* w = s2 + (lb - i0 - (kDecU - 1));
 #pragma unroll
-        for (int d = 0; d < kDecR + kDecU - 1; ++d) { xa[d] = sA[dpad(l0 + d)]; xb[d] = sB[dpad(l0 + d)]; }
+        for (int d = 0; d < kDecR + kDecU - 1; ++d) x[d] = w[d];
 #pragma unroll
         for (int u = 0; u < kDecU; ++u) {
-            const float he = kDecTapF[2 * (i0 + u)], ho = kDecTapF[2 * (i0 + u) + 1];
+            const float2 h = kDecTapP[i0 + u];
 #pragma unroll
-            for (int r = 0; r < kDecR; ++r) {
-                acc[r] = fmaf(he, xa[r - u + kDecU - 1], acc[r]);
-                acc[r] = fmaf(ho, xb[r - u + kDecU - 1], acc[r]);
-            }
+            for (int r = 0; r < kDecR; ++r) acc2[r] = __ffma2_rn(x[r - u + kDecU - 1], h, acc2[r]);
         }
     };
 #pragma unroll 1
-    for (int c = 0; c < kMidLo; ++c) {
-        chunk_f32(c * kDecU);
-        chunk_f32((kChunks - 1 - c) * kDecU);
+    for (int c = 0; c < kDecOuter / kDecU; ++c) {
+        step_f32(c * kDecU);
+        step_f32(kDecHalf - (c + 1) * kDecU);
     }
+    float acc[kDecR];
+    double accd[kDecR];
+#pragma unroll
+    for (int r = 0; r < kDecR; ++r) { acc[r] = acc2[r].x + acc2[r].y; accd[r] = 0.0; }
+    // centre pairs [88, 104) in fp64, one polyphase component at a time (a window of doubles for both
+    // would not fit the register budget); the 32-bit loads of a phase are 2-way bank conflicted,
+    // which this short pass can afford.
+    constexpr int kMidU = 8;
+    const float* s1 = reinterpret_cast<const float*>(s2);
 #pragma unroll 1
-    for (int c = kMidLo; c < kMidHi; ++c) {
-        const int i0 = c * kDecU;
-        double xa[kDecR + kDecU - 1], xb[kDecR + kDecU - 1];
-        const int l0 = lb - i0 - (kDecU - 1);
+    for (int i0 = kDecOuter; i0 < kDecOuter + kDecMid; i0 += kMidU) {
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {             // 0: odd taps on B, 1: even taps on A
+            double x[kDecR + kMidU - 1];
+            const float* w = s1 + 2 * (lb - i0 - (kMidU - 1)) + ph;
 #pragma unroll
-        for (int d = 0; d < kDecR + kDecU - 1; ++d) { xa[d] = (double)sA[dpad(l0 + d)]; xb[d] = (double)sB[dpad(l0 + d)]; }
+            for (int d = 0; d < kDecR + kMidU - 1; ++d) x[d] = (double)w[2 * d];
 #pragma unroll
-        for (int u = 0; u < kDecU; ++u) {
-            const double he = (double)kDecTapF[2 * (i0 + u)], ho = (double)kDecTapF[2 * (i0 + u) + 1];
+            for (int u = 0; u < kMidU; ++u) {
+                const double h = (double)kDecTapF[2 * (i0 + u) + 1 - ph];
 #pragma unroll
-            for (int r = 0; r < kDecR; ++r) {
-                accd[r] = fma(he, xa[r - u + kDecU - 1], accd[r]);
-                accd[r] = fma(ho, xb[r - u + kDecU - 1], accd[r]);
+                for (int r = 0; r < kDecR; ++r) accd[r] = fma(h, x[r - u + kMidU - 1], accd[r]);
             }
         }
     }
-    float* o = out + clip * out_stride;
+    // results leave through shared memory so that the global stores are coalesced
+    __syncthreads();
+    float* so = reinterpret_cast<float*>(s2);
 #pragma unroll
-    for (int r = 0; r < kDecR; ++r) {
-        const int m = m0 + tid * kDecR + r;
-        if (m < out_len) o[m] = (float)((accd[r] + (double)acc[r]) * 1.41421356237309504880);
-    }
+    for (int r = 0; r < kDecR; ++r)
+        so[tid * kDecR + r] = (float)((accd[r] + (double)acc[r]) * 1.41421356237309504880);
+    __syncthreads();
+    float* o = out + clip * out_stride + m0;
+    const int n_valid = min(kDecTile, out_len - m0);
+    for (int i = tid; i < n_valid; i += kDecThreads) o[i] = so[i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -228,27 +238,62 @@ __global__ void __launch_bounds__(kThreads) cqt_octave_kernel(OctParams p) {
     const int t0 = blockIdx.x * F;
     const int n = p.in_len;
     // ---- stage samples (zero outside [0, n)) ---------------------------------------------------
-    if (per_frame) {
-        for (int i = tid; i < F * NFFT; i += kThreads) {
-            const int f = i / NFFT, o = i % NFFT;
-            const int s = (t0 + f) * p.hop - NFFT / 2 + o;
-            float v = 0.f;
-            if (s >= 0 && s < n) {
-                if (I16) v = (float)((const int16_t*)p.in)[clip * p.in_stride + s] * (1.0f / 32768.0f);
-                else v = ((const float*)p.in)[clip * p.in_stride + s];
-            }
-            s_audio[i] = v;
-        }
-    } else {
+    // Vector groups (4 floats / 2 int16) with all the loads of a batch issued before the first
+    // conversion: one DRAM round trip per batch of eight instead of one per sample (this loop, not
+    // the FFT, set the octave kernels' time).  Segment starts are multiples of 8 samples, so a group
+    // is either inside [0, n) and aligned, or it takes the scalar edge path.
+    {
+        using VecT = typename std::conditional<I16, uint32_t, float4>::type;
+        constexpr int V = I16 ? 2 : 4;
+        constexpr int kBatch = 8;
+        const int seg_len = per_frame ? NFFT : cl;                 // samples per contiguous segment
+        const int gps = seg_len / V;                               // groups per segment
+        const int total = (per_frame ? F : 1) * gps;
+        const unsigned char* base = (const unsigned char*)p.in + (clip * p.in_stride) * (I16 ? 2 : 4);
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(base) & (sizeof(VecT) - 1)) == 0;
         const int c0 = t0 * p.hop - NFFT / 2;
-        for (int i = tid; i < cl; i += kThreads) {
-            const int s = c0 + i;
-            float v = 0.f;
-            if (s >= 0 && s < n) {
-                if (I16) v = (float)((const int16_t*)p.in)[clip * p.in_stride + s] * (1.0f / 32768.0f);
-                else v = ((const float*)p.in)[clip * p.in_stride + s];
+#pragma unroll 1
+        for (int g0 = tid; g0 < total; g0 += kBatch * kThreads) {
+            VecT raw[kBatch];
+            int src[kBatch], state[kBatch];                        // 0: past the end, 1: vector load, 2: edge / unaligned
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                const int g = g0 + u * kThreads;
+                const int f = per_frame ? g / (NFFT / V) : 0;
+                const int o = (per_frame ? g % (NFFT / V) : g) * V;
+                src[u] = c0 + f * p.hop + o;
+                const bool al = vec_ok && ((src[u] * (I16 ? 2 : 4)) & (int)(sizeof(VecT) - 1)) == 0;   // odd hops
+                state[u] = g < total ? ((al && src[u] >= 0 && src[u] + V <= n) ? 1 : 2) : 0;
+                if (state[u] == 1) raw[u] = __ldg(reinterpret_cast<const VecT*>(base + (size_t)src[u] * (I16 ? 2 : 4)));
             }
-            s_audio[i] = v;
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) {
+                if (state[u] == 0) continue;
+                const int g = g0 + u * kThreads;
+                float* dst = s_audio + g * V;                      // per_frame: f * NFFT + o == g * V as well
+                float v[V];
+                if (state[u] == 1) {
+                    if constexpr (I16) {
+                        const uint32_t w = raw[u];
+                        v[0] = __int2float_rn((int)(short)(w & 0xffffu)) * (1.0f / 32768.0f);
+                        v[1] = __int2float_rn((int)w >> 16) * (1.0f / 32768.0f);
+                    } else {
+                        v[0] = raw[u].x; v[1] = raw[u].y; v[2] = raw[u].z; v[3] = raw[u].w;
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const int s1 = src[u] + e;
+                        v[e] = 0.f;
+                        if (s1 >= 0 && s1 < n) {
+                            if (I16) v[e] = __int2float_rn((int)((const int16_t*)base)[s1]) * (1.0f / 32768.0f);
+                            else v[e] = ((const float*)base)[s1];
+                        }
+                    }
+                }
+                if constexpr (I16) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
+                else *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            }
         }
     }
     __syncthreads();
