@@ -93,6 +93,11 @@ __device__ __forceinline__ float warp_min(float v) {
     for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
 }
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -493,9 +498,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     const float2* pl = reinterpret_cast<const float2*>(s_pow + pb * (PROWS * PROW)) + lane;
                     if constexpr (SPEC) {
                         const uint32_t pla = smem_u32(pl);
-                        float dacc[KIND == 2 ? B2A_DCTSPEC_NMFCC : 1];     // this warp's bands' share of each coefficient
-#pragma unroll
-                        for (int k = 0; k < (KIND == 2 ? B2A_DCTSPEC_NMFCC : 1); ++k) dacc[k] = 0.f;
 #define B2A_LDS2(DST, ADDR, OFF) \
     asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(DST.x), "=f"(DST.y) : "r"(ADDR), "n"(OFF))
                         // headline configuration: every band unrolled, weights are FFMA immediates
@@ -503,7 +505,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
     {                                                                               \
         const float vv = db10(VAL);                                                 \
         if (KIND == 1) s_db[(M) * 32 + lane] = vv;                                  \
-        if (KIND == 2) B2A_DCT_BAND_##M(vv, dacc)                                   \
         if (valid) outp[(M) * nfr] = vv;      /* predicated store: the band sweep stays one basic block */ \
         vmax = fmaxf(vmax, valid ? vv : vmax);                                      \
         vmin = fminf(vmin, valid ? vv : vmin);                                      \
@@ -516,11 +517,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                         }
 #undef B2A_EMIT
 #undef B2A_LDS2
-                        if constexpr (KIND == 2) {
-                            float* const pp = s_part + ((it & 1) * kMelWarps + mw) * (B2A_DCTSPEC_NMFCC * 32) + lane;
-#pragma unroll
-                            for (int k = 0; k < B2A_DCTSPEC_NMFCC; ++k) pp[k * 32] = dacc[k];
-                        }
                     } else {
                         // per 4-bin step one 128-bit broadcast weight load and two 64-bit power
                         // loads (bands padded with zero weights)
@@ -585,28 +581,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                         }
                     }
                     if (tile + 1 == tiles) nq_finish();            // short clip after a long one
-                }
-                if constexpr (KIND == 2) {
-                    // generated DCT: the four warps' partial sums meet in shared memory (double
-                    // buffered by tile parity: one barrier per tile); warp mw finishes k = mw + 4 g
-                    mel_sync();
-                    const int t = t0 + lane;
-                    const bool valid = t < nfr;
-                    const float* const pp = s_part + (it & 1) * (kMelWarps * B2A_DCTSPEC_NMFCC * 32) + lane;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        const int k = mw + kMelWarps * g;
-                        float ag = 0.f;
-                        if (k < B2A_DCTSPEC_NMFCC) {
-                            ag = (pp[k * 32] + pp[(B2A_DCTSPEC_NMFCC + k) * 32]) +
-                                 (pp[(2 * B2A_DCTSPEC_NMFCC + k) * 32] + pp[(3 * B2A_DCTSPEC_NMFCC + k) * 32]);
-                            if (valid) outb[(size_t)k * nfr + t] = ag;
-                        }
-                        if (tile == 0) zx0[g] = __shfl_sync(0xffffffffu, ag, 0);
-                        const float dd = valid ? ag - zx0[g] : 0.f;
-                        zS[g] += dd;
-                        zQ[g] = fmaf(dd, dd, zQ[g]);
-                    }
                 }
                 if constexpr (KIND == 1) {
                     // DCT-II of this tile straight from shared memory, assuming the top_db clip
@@ -693,6 +667,72 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                     for (int i = mtid; i < total; i += kMelThreads) inter[i] = nrm(inter[i]);
                     nq_n4 = nq_done = 0;
                 }
+            } else if constexpr (KIND == 2) {
+                // Headline mfcc: the DCT of the whole clip runs HERE, once, from the raw-dB scratch (L2
+                // resident), one frame per thread: the top_db threshold is known by now (no recompute
+                // path), the 520 immediate-weight FFMAs are fetched once per clip instead of once per
+                // tile (in the tile loop they pushed the hot code past the 32 KB instruction cache and
+                // the mel warps, not the FFT warps, set the pace: 2.6 M clips/s), and the per-row
+                // statistics of the z-score (deep.py:326-328) are float64 sums taken on the way.
+                // The FFT warps run ahead into the next clip meanwhile (two power tiles of slack).
+                float* const outc = outb;
+                const float thr = vmax - p.top_db;
+                nq_finish();                                          // the previous clip's z-score, if any is left
+                mel_sync();                                           // ... by every warp, before s_zs changes
+                double* const s_zd = reinterpret_cast<double*>(s_part);   // [mel warp][coefficient][S, Q]
+#define B2A_DCT_LD(M) fmaxf(src[(size_t)(M) * nfr], thr)
+#define B2A_DCT_PASS(G)                                                                            \
+    {                                                                                              \
+        constexpr int NK = B2A_DCT_GROUP##G##_NK, K0 = B2A_DCT_GROUP##G##_K0;                      \
+        double S[NK], Q[NK];                                                                       \
+        _Pragma("unroll") for (int k = 0; k < NK; ++k) { S[k] = 0.0; Q[k] = 0.0; }                 \
+        _Pragma("unroll 1") for (int t = mtid; t < nfr; t += kMelThreads) {                        \
+            float a[NK];                                                                           \
+            _Pragma("unroll") for (int k = 0; k < NK; ++k) a[k] = 0.f;                             \
+            const float* const src = inter + t;                                                    \
+            B2A_DCT_GROUP##G(B2A_DCT_LD, a)                                                        \
+            _Pragma("unroll") for (int k = 0; k < NK; ++k) {                                       \
+                outc[(size_t)(K0 + k) * nfr + t] = a[k];                                           \
+                const double ad = (double)a[k];                                                    \
+                S[k] += ad;                                                                        \
+                Q[k] = fma(ad, ad, Q[k]);                                                          \
+            }                                                                                      \
+        }                                                                                          \
+        _Pragma("unroll") for (int k = 0; k < NK; ++k) {                                           \
+            const double Sw = warp_sum_d(S[k]), Qw = warp_sum_d(Q[k]);                             \
+            if (lane == 0) { s_zd[(mw * B2A_DCTSPEC_NMFCC + K0 + k) * 2] = Sw; s_zd[(mw * B2A_DCTSPEC_NMFCC + K0 + k) * 2 + 1] = Qw; } \
+        }                                                                                          \
+    }
+                B2A_DCT_PASS(0)
+#if B2A_DCT_NGROUPS > 1
+                B2A_DCT_PASS(1)
+#endif
+#if B2A_DCT_NGROUPS > 2
+                B2A_DCT_PASS(2)
+#endif
+#undef B2A_DCT_PASS
+#undef B2A_DCT_LD
+                mel_sync();
+                if (mtid < B2A_DCTSPEC_NMFCC) {
+                    double S = 0.0, Q = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kMelWarps; ++w) {
+                        S += s_zd[(w * B2A_DCTSPEC_NMFCC + mtid) * 2];
+                        Q += s_zd[(w * B2A_DCTSPEC_NMFCC + mtid) * 2 + 1];
+                    }
+                    // constant rows (silence): S = n c exactly, so the mean is c and every z is exactly 0
+                    const double mean = S / (double)nfr;
+                    const double var = fmax(Q / (double)nfr - mean * mean, 0.0);
+                    s_zs[2 * mtid] = (float)mean;
+                    s_zs[2 * mtid + 1] = __fdiv_rn(1.0f, sqrtf((float)var) + 1e-8f);
+                }
+                nz = outc;
+                nz_nfr = nfr;
+                nz_inv = __fdiv_rn(1.0f, (float)nfr);
+                nq_n4 = B2A_DCTSPEC_NMFCC * nfr;
+                nq_done = 0;
+                mel_sync();                                           // s_zs and the DCT rows are visible to every mel warp
+                continue;
             } else {
                 float* outc = outb;
                 const float thr = vmax - p.top_db;

@@ -10,9 +10,14 @@
 //
 //   y[m] = sum_i poly[(m*down + half) % up][i] * x[(m*down + half) / up - i]
 //
-// One CTA produces 256 consecutive outputs: the input window they share is staged once in shared
-// memory (int16 widened there), every thread walks its own phase row with 128-bit tap loads (the
-// table, <= a few hundred KB, stays in L1/L2) and four independent accumulators.
+// Two kernels.  resample_phase_kernel (up >= 8, down odd — 44.1 -> 16 kHz is 160/441): the 32 lanes
+// of a warp take outputs m, m + up, m + 2 up, ..., which all use the SAME phase row, so a 128-bit
+// tap load is one broadcast wavefront instead of 32, and their input positions are `down` samples
+// apart — odd, hence 32 distinct shared-memory banks.  A CTA stages the 32 * down + K input samples
+// once and its eight warps take eight phases; blockIdx.y walks the rest.  resample_kernel (everything
+// else: up < 8 shares rows between lanes anyway; an even `down` would put every lane on one bank):
+// one CTA produces 256 consecutive outputs from a staged window, every thread walks its own phase
+// row.  Both: int16 widened while staging, four independent accumulators, identical tap order.
 #include "../../include/b2a.h"
 
 #include <cuda_runtime.h>
@@ -68,6 +73,51 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(const void* __restri
     out[m] = (a0 + a1) + (a2 + a3);
 }
 
+constexpr int kPhWarps = kThreads / 32;
+
+template <bool I16>
+__global__ void __launch_bounds__(kThreads) resample_phase_kernel(const void* __restrict__ in, long long n_in,
+                                                                  float* __restrict__ out, long long n_out,
+                                                                  const float* __restrict__ poly, int up, int down,
+                                                                  int K, int half_len, int win) {
+    extern __shared__ __align__(16) float s_x[];
+    const long long mb = (long long)blockIdx.x * 32 * up;          // first output of this block of 32 * up
+    const long long k_lo = (mb * down + half_len) / up - (K - 1);   // oldest sample the block touches
+    constexpr int kBatch = 8;
+#pragma unroll 1
+    for (int i0 = threadIdx.x; i0 < win; i0 += kBatch * kThreads) {
+        float v[kBatch];
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b) {
+            const long long k = k_lo + i0 + b * kThreads;
+            v[b] = 0.f;
+            if (i0 + b * kThreads < win && k >= 0 && k < n_in)
+                v[b] = I16 ? (float)__ldg((const int16_t*)in + k) * (1.0f / 32768.0f) : __ldg((const float*)in + k);
+        }
+#pragma unroll
+        for (int b = 0; b < kBatch; ++b)
+            if (i0 + b * kThreads < win) s_x[i0 + b * kThreads] = v[b];
+    }
+    __syncthreads();
+    const int j = blockIdx.y * kPhWarps + (threadIdx.x >> 5);      // which of the block's `up` residues
+    if (j >= up) return;
+    const long long m = mb + j + (long long)up * (threadIdx.x & 31);
+    if (m >= n_out) return;
+    const long long u = m * down + half_len;                        // u % up is the same for all 32 lanes
+    const float* xs = s_x + (int)(u / up - k_lo);                   // lanes are `down` samples apart
+    const float4* h4 = reinterpret_cast<const float4*>(poly + (size_t)(u % up) * K);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int i = 0; i < K / 4; ++i) {
+        const float4 h = __ldg(h4 + i);
+        a0 = fmaf(h.x, xs[-4 * i], a0);
+        a1 = fmaf(h.y, xs[-4 * i - 1], a1);
+        a2 = fmaf(h.z, xs[-4 * i - 2], a2);
+        a3 = fmaf(h.w, xs[-4 * i - 3], a3);
+    }
+    out[m] = (a0 + a1) + (a2 + a3);
+}
+
 }  // namespace
 
 struct b2a_resampler {
@@ -100,6 +150,24 @@ int rs_launch(b2a_resampler* r, const void* d_in, int in_dtype, long long n_in, 
     const long long n_out = b2a_resampler_out_len(r, n_in);
     if (n_out <= 0) return B2A_OK;
     const int K = r->d.taps_per_phase;
+    const int up = r->d.up, down = r->d.down;
+    // phase-aligned kernel: 32 lanes x `down` samples + the filter must fit shared memory
+    const long long win_ph = 32LL * down + K + 2;
+    if (up >= 8 && (down & 1) && win_ph * (long long)sizeof(float) <= 200 * 1024) {
+        const size_t smem = (size_t)win_ph * sizeof(float);
+        const dim3 grid((unsigned)((n_out + 32LL * up - 1) / (32LL * up)), (unsigned)((up + kPhWarps - 1) / kPhWarps));
+        if (in_dtype == B2A_IN_I16) {
+            auto k = resample_phase_kernel<true>;
+            RS_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, up, down, K, r->d.half_len, (int)win_ph);
+        } else {
+            auto k = resample_phase_kernel<false>;
+            RS_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, up, down, K, r->d.half_len, (int)win_ph);
+        }
+        RS_TRY(cudaGetLastError());
+        return B2A_OK;
+    }
     // input samples spanned by 256 consecutive outputs, plus the filter length
     const int win = K + (int)(((long long)(kThreads - 1) * r->d.down + r->d.up - 1) / r->d.up) + 2;
     const size_t smem = (size_t)win * sizeof(float);

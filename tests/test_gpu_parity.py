@@ -10,7 +10,7 @@ Tolerances (BASELINE.json north_star; "stated per extract
                   z errors no fp32 FFT avoids: pocketfft in float32 in place of ours gives 9e-4 z on the
                   same clips (tools/tolerance_evidence.py).  4e-3 MFCC units is the mel tolerance seen
                   through the DCT: 1e-4 of the 80 dB range is 8e-3 dB per band.  2025 clips: 1.4e-3 z
-                  worst, p99 6.9e-4; rows with sd < 1: 6.9e-4 MFCC units worst.
+                  worst (row sd ~1.4: 1.9e-3 MFCC units), p99 6.9e-4, 4.2e-4 on rows with sd >= 2.
   audio_cqt       max-abs <= 2.5e-4 in [0,1] space (oracle and kernel share decimator taps).  Bins 80 dB
                   below a tonal clip's peak are this sensitive: rounding each decimated signal to
                   float32 once (which librosa does too) already moves the oracle's own features by
