@@ -65,7 +65,12 @@ constexpr int PROWS = 132;                      // bin pairs (0,1)..(256,257) + 
 constexpr int kZFast = 16;                      // mfcc: up to this many coefficients take the one-sweep z-score
 static_assert(ROUNDS >= 1 && ROUNDS * 2 * kFftWarps == F, "tile must be a whole number of rounds");
 static_assert(B2A_MELSPEC_WARPS == kMelWarps, "regenerate gen/mel_special.inc for this warp count");
-static_assert(B2A_DCTSPEC_NMFCC <= kZFast && kMelWarps == 4, "generated DCT: coefficients k = warp + 4 g, g < 4");
+static_assert(B2A_DCTSPEC_NMFCC <= kZFast && kMelWarps == 4, "generated DCT: one-sweep z-score, four mel warps");
+// KIND 2 overlays [n_mels][128] float columns + [4][n_mfcc][2] doubles on the dB tile, partial-sum and basis regions
+static_assert(B2A_MELSPEC_NMELS * 32 * 4 + (2 * 4 * B2A_DCTSPEC_NMFCC * 32 * 4 + 512) +
+                      B2A_MELSPEC_NMELS * 4 * (4 * ((((B2A_DCTSPEC_NMFCC + 3) / 4) + 3) / 4)) * 4 >=
+                  B2A_MELSPEC_NMELS * 128 * 4 + 4 * B2A_DCTSPEC_NMFCC * 16,
+              "generated DCT: the per-thread dB columns do not fit the regions they overlay");
 
 __device__ __forceinline__ float db10(float s) {
     // 10*log10(max(amin, s)); the argument is >= 1e-10, never denormal -> lg2.approx.ftz
@@ -169,7 +174,7 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.off_red = take((64 + 2 * kZFast) * 4);          // per-warp max/min, then (mean, sd) per coefficient
     L.off_bar = take((kMaxRaw + 2 * 3) * 8);
     L.off_db = take(mfcc ? n_mels * 32 * 4 : 0);      // mfcc: [n_mels][32] dB tile feeding the in-tile DCT
-    L.off_part = take(mfcc && n_mfcc <= kZFast ? 2 * kMelWarps * n_mfcc * 32 * 4 : 0);   // generated DCT: partial sums
+    L.off_part = take(mfcc && n_mfcc <= kZFast ? 2 * kMelWarps * n_mfcc * 32 * 4 + 512 : 0);   // (reserve: with off_db and off_dct, KIND 2's [n_mels][128] columns + sums)
     L.gp = 4 * ((((n_mfcc + kMelWarps - 1) / kMelWarps) + 3) / 4);
     L.off_dct = take(mfcc ? n_mels * kMelWarps * L.gp * 4 : 0);   // mfcc: DCT-II basis as [mel][mel warp][gp]
     L.total = o;
@@ -679,8 +684,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                 const float thr = vmax - p.top_db;
                 nq_finish();                                          // the previous clip's z-score, if any is left
                 mel_sync();                                           // ... by every warp, before s_zs changes
-                double* const s_zd = reinterpret_cast<double*>(s_part);   // [mel warp][coefficient][S, Q]
-#define B2A_DCT_LD(M) fmaxf(src[(size_t)(M) * nfr], thr)
+                // A frame's 40 raw dB come from L2 by cp.async, all in flight at once and without holding
+                // registers (plain loads in batches of eight made this phase a chain of L2 round trips:
+                // 31 k cycles per clip), into a column of shared memory private to the thread — no
+                // barrier, the thread only reads what it copied itself.  KIND 2 has no other use for the
+                // dB tile / partial-sum / basis regions, which the columns overlay.
+                float* const s_col = reinterpret_cast<float*>(smem + L.off_db) + mtid;           // [n_mels][128]
+                double* const s_zd = reinterpret_cast<double*>(smem + L.off_db + B2A_MELSPEC_NMELS * kMelThreads * 4);   // [mel warp][coefficient][S, Q]
+                const uint32_t s_col_a = smem_u32(s_col);
+#define B2A_DCT_LD(M) fmaxf(s_col[(M) * kMelThreads], thr)
 #define B2A_DCT_PASS(G)                                                                            \
     {                                                                                              \
         constexpr int NK = B2A_DCT_GROUP##G##_NK, K0 = B2A_DCT_GROUP##G##_K0;                      \
@@ -689,7 +701,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
         _Pragma("unroll 1") for (int t = mtid; t < nfr; t += kMelThreads) {                        \
             float a[NK];                                                                           \
             _Pragma("unroll") for (int k = 0; k < NK; ++k) a[k] = 0.f;                             \
-            const float* const src = inter + t;                                                    \
+            {                                                                                      \
+                const float* src = inter + t;                                                      \
+                _Pragma("unroll") for (int m = 0; m < B2A_MELSPEC_NMELS; ++m, src += nfr)          \
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_col_a + m * kMelThreads * 4), "l"(src) : "memory"); \
+                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");      \
+            }                                                                                      \
             B2A_DCT_GROUP##G(B2A_DCT_LD, a)                                                        \
             _Pragma("unroll") for (int k = 0; k < NK; ++k) {                                       \
                 outc[(size_t)(K0 + k) * nfr + t] = a[k];                                           \
