@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
 #define B2A_DCT_LD(M) fmaxf(s_col[(M) * kMelThreads], thr)
 #define B2A_DCT_PASS(G)                                                                            \
     {                                                                                              \
-        constexpr int NK = B2A_DCT_GROUP##G##_NK, K0 = B2A_DCT_GROUP##G##_K0;                      \
+        constexpr int NK = B2A_DCT_GROUP##G##_NK;                                                  \
         double S[NK], Q[NK];                                                                       \
         _Pragma("unroll") for (int k = 0; k < NK; ++k) { S[k] = 0.0; Q[k] = 0.0; }                 \
         _Pragma("unroll 1") for (int t = mtid; t < nfr; t += kMelThreads) {                        \
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
             }                                                                                      \
             B2A_DCT_GROUP##G(B2A_DCT_LD, a)                                                        \
             _Pragma("unroll") for (int k = 0; k < NK; ++k) {                                       \
-                outc[(size_t)(K0 + k) * nfr + t] = a[k];                                           \
+                outc[(size_t)B2A_DCT_GROUP##G##_KOF(k) * nfr + t] = a[k];                          \
                 const double ad = (double)a[k];                                                    \
                 S[k] += ad;                                                                        \
                 Q[k] = fma(ad, ad, Q[k]);                                                          \
@@ -717,16 +717,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
         }                                                                                          \
         _Pragma("unroll") for (int k = 0; k < NK; ++k) {                                           \
             const double Sw = warp_sum_d(S[k]), Qw = warp_sum_d(Q[k]);                             \
-            if (lane == 0) { s_zd[(mw * B2A_DCTSPEC_NMFCC + K0 + k) * 2] = Sw; s_zd[(mw * B2A_DCTSPEC_NMFCC + K0 + k) * 2 + 1] = Qw; } \
+            if (lane == 0) { s_zd[(mw * B2A_DCTSPEC_NMFCC + B2A_DCT_GROUP##G##_KOF(k)) * 2] = Sw; s_zd[(mw * B2A_DCTSPEC_NMFCC + B2A_DCT_GROUP##G##_KOF(k)) * 2 + 1] = Qw; } \
         }                                                                                          \
     }
                 B2A_DCT_PASS(0)
-#if B2A_DCT_NGROUPS > 1
                 B2A_DCT_PASS(1)
-#endif
-#if B2A_DCT_NGROUPS > 2
-                B2A_DCT_PASS(2)
-#endif
 #undef B2A_DCT_PASS
 #undef B2A_DCT_LD
                 mel_sync();
