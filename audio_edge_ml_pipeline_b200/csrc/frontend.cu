@@ -55,36 +55,67 @@ __device__ __forceinline__ float load_sample(const void* clip, int s, int n, int
     return ((const float*)clip)[s];
 }
 
-// Stage samples [c0, c0+len) of one clip into smem as fp32.
+// Stage samples [c0, c0+len) of one clip into smem as fp32.  16-byte global loads on the clip's own
+// 16-byte grid: the first `head` samples (up to the next boundary) and the tail go one by one, so a
+// clip whose start is not a multiple of 8 samples (110 250-sample clips: three out of four) still
+// streams through vector loads — only the shared-memory stores narrow to the alignment that is left.
+// The loads of a batch are issued before the first conversion (one L2/DRAM round trip per batch).
 template <bool I16>
 __device__ __forceinline__ void stage_audio(float* __restrict__ dst, const void* __restrict__ clip,
                                             long long clip_elem0, int c0, int len, int n, int pad_mode,
                                             bool base_aligned) {
     constexpr int V = I16 ? 8 : 4;               // elements per 16-byte load
-    const bool aligned = base_aligned && (((clip_elem0 + c0) & (V - 1)) == 0);
-    const int groups = (len + V - 1) / V;
-    for (int g = threadIdx.x; g < groups; g += kThreads) {
-        const int i = g * V, s = c0 + i;
-        if (aligned && s >= 0 && s + V <= n && i + V <= len) {
-            if (I16) {
-                const int4 raw = __ldg(reinterpret_cast<const int4*>((const int16_t*)clip + s));
-                const int r[4] = {raw.x, raw.y, raw.z, raw.w};
-                float f[8];
+    constexpr int kBatch = 4;
+    // samples [c0 + head, ...) start on a 16-byte boundary of the batch (base_aligned: the batch itself does)
+    const int head = base_aligned ? (int)((V - ((clip_elem0 + c0) & (V - 1))) & (V - 1)) : len;
+    const int hl = head < len ? head : len;
+    for (int i = threadIdx.x; i < hl; i += kThreads) dst[i] = load_sample<I16>(clip, c0 + i, n, pad_mode);
+    const int groups = len > hl ? (len - hl + V - 1) / V : 0;
+#pragma unroll 1
+    for (int g0 = threadIdx.x; g0 < groups; g0 += kBatch * kThreads) {
+        int4 raw[kBatch];
+        int state[kBatch];                       // 0: none, 1: vector load, 2: edge (clip boundary, padding, tail)
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            const int g = g0 + u * kThreads, i = hl + g * V, sidx = c0 + i;
+            state[u] = g < groups ? ((sidx >= 0 && sidx + V <= n && i + V <= len) ? 1 : 2) : 0;
+            if (state[u] == 1)
+                raw[u] = __ldg(reinterpret_cast<const int4*>(I16 ? (const void*)((const int16_t*)clip + sidx)
+                                                                 : (const void*)((const float*)clip + sidx)));
+        }
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            if (state[u] == 0) continue;
+            const int g = g0 + u * kThreads, i = hl + g * V, sidx = c0 + i;
+            if (state[u] == 2) {
+#pragma unroll
+                for (int e = 0; e < V; ++e)
+                    if (i + e < len) dst[i + e] = load_sample<I16>(clip, sidx + e, n, pad_mode);
+                continue;
+            }
+            float f[V];
+            if constexpr (I16) {
+                const int r[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     f[2 * e] = (float)(short)(r[e] & 0xffff) * (1.0f / 32768.0f);
                     f[2 * e + 1] = (float)(r[e] >> 16) * (1.0f / 32768.0f);
                 }
-                *reinterpret_cast<float4*>(dst + i) = make_float4(f[0], f[1], f[2], f[3]);
-                *reinterpret_cast<float4*>(dst + i + 4) = make_float4(f[4], f[5], f[6], f[7]);
             } else {
-                *reinterpret_cast<float4*>(dst + i) =
-                    __ldg(reinterpret_cast<const float4*>((const float*)clip + s));
+                f[0] = __int_as_float(raw[u].x); f[1] = __int_as_float(raw[u].y);
+                f[2] = __int_as_float(raw[u].z); f[3] = __int_as_float(raw[u].w);
             }
-        } else {
+            float* d = dst + i;
+            if ((hl & 3) == 0) {
 #pragma unroll
-            for (int e = 0; e < V; ++e)
-                if (i + e < len) dst[i + e] = load_sample<I16>(clip, s + e, n, pad_mode);
+                for (int e = 0; e < V; e += 4) *reinterpret_cast<float4*>(d + e) = make_float4(f[e], f[e + 1], f[e + 2], f[e + 3]);
+            } else if ((hl & 1) == 0) {
+#pragma unroll
+                for (int e = 0; e < V; e += 2) *reinterpret_cast<float2*>(d + e) = make_float2(f[e], f[e + 1]);
+            } else {
+#pragma unroll
+                for (int e = 0; e < V; ++e) d[e] = f[e];
+            }
         }
     }
 }
@@ -330,9 +361,20 @@ __global__ void __launch_bounds__(kThreads, FrontCfg<LOG2NC>::MINB) front_kernel
             float* s_l = s_pow;                       // [n_mels][32] tile of clipped dB
             for (int t0 = 0; t0 < nfr; t0 += 32) {
                 __syncthreads();
-                for (int i = tid; i < n_mels * 32; i += kThreads) {
-                    const int m = i >> 5, f = i & 31, t = t0 + f;
-                    s_l[i] = (t < nfr) ? fmaxf(inter[(size_t)m * nfr + t], thr) : 0.f;
+                // raw dB come back from L2: eight loads in flight per thread, not one round trip each
+#pragma unroll 1
+                for (int i0 = tid; i0 < n_mels * 32; i0 += 8 * kThreads) {
+                    float v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * kThreads, m = i >> 5, t = t0 + (i & 31);
+                        v[u] = (i < n_mels * 32 && t < nfr) ? inter[(size_t)m * nfr + t] : -3.0e38f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int i = i0 + u * kThreads;
+                        if (i < n_mels * 32) s_l[i] = (t0 + (i & 31) < nfr) ? fmaxf(v[u], thr) : 0.f;
+                    }
                 }
                 __syncthreads();
                 constexpr int KB = 5;                                                  // coefficients per warp and block
