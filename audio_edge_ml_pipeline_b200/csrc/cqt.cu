@@ -189,11 +189,6 @@ template <int LOG2NC> struct OctCfg {
     static constexpr int FR = kThreads / G::T;
     static constexpr int ROUNDS = F / FR;
     static constexpr int SSTRIDE = G::NC + 1;        // float2 per frame in the spectrum tile
-    // One FFT round per tile (n_fft 256: every frame keeps its own exchange slot): the split step writes
-    // the spectrum over the slot it reads — bins k and NC-k belong to the same thread — plus one extra
-    // element for bin NC, and the separate spectrum tile (33 KB, a third of the CTA) goes away.
-    static constexpr bool INPLACE = (F / FR) == 1;
-    static constexpr int XS1 = G::XSTRIDE + (INPLACE ? 1 : 0);   // float2 per exchange slot
 };
 
 static size_t oct_smem_bytes(int log2nc, int hop, int n_rows, int nnz) {
@@ -202,19 +197,15 @@ static size_t oct_smem_bytes(int log2nc, int hop, int n_rows, int nnz) {
     const size_t fstride = hop >= n_fft ? (size_t)n_fft : (size_t)hop;
     size_t cl = fstride * (F - 1) + n_fft;
     cl = (cl + 7) & ~(size_t)7;
-    const bool inplace = F / FR == 1;
-    size_t b = cl * 4 + (size_t)FR * (NC + NC / 16 + (inplace ? 1 : 0)) * 8 + (inplace ? 0 : (size_t)F * (NC + 1) * 8);
+    size_t b = cl * 4 + (size_t)FR * (NC + NC / 16) * 8 + (size_t)F * (NC + 1) * 8;
     b = (b + 15) & ~(size_t)15;
     const int R1 = log2nc >= 8 ? 16 : (1 << (log2nc - 4));
     b += (size_t)NC * 8 + (size_t)(NC / 2 + 1) * 8 + (size_t)(16 / R1) * (R1 - 1) * T * 8 + (size_t)nnz * 8 + (size_t)n_rows * 12 + 128 * 4;
     return b + 64;
 }
 
-#ifndef B2A_OCT_MINB
-#define B2A_OCT_MINB 4          // CTAs per SM the n_fft-256 octave kernel is compiled for (register cap 64)
-#endif
 template <int LOG2NC, bool I16>
-__global__ void __launch_bounds__(kThreads, LOG2NC == 7 ? B2A_OCT_MINB : 1) cqt_octave_kernel(OctParams p) {
+__global__ void __launch_bounds__(kThreads) cqt_octave_kernel(OctParams p) {
     using G = FftGeom<LOG2NC>;
     using C = OctCfg<LOG2NC>;
     constexpr int NC = G::NC, NFFT = G::NFFT, T = G::T, F = C::F, FR = C::FR;
@@ -225,8 +216,8 @@ __global__ void __launch_bounds__(kThreads, LOG2NC == 7 ? B2A_OCT_MINB : 1) cqt_
     const int cl = (fstride * (F - 1) + NFFT + 7) & ~7;
     float* s_audio = reinterpret_cast<float*>(smem_raw);
     float2* s_xch = reinterpret_cast<float2*>(s_audio + cl);
-    float2* s_spec = s_xch + FR * C::XS1;
-    const int off_tw = ((cl * 4 + FR * C::XS1 * 8 + (C::INPLACE ? 0 : F * C::SSTRIDE * 8)) + 15) & ~15;   // no integer round trip
+    float2* s_spec = s_xch + FR * G::XSTRIDE;
+    const int off_tw = ((cl * 4 + FR * G::XSTRIDE * 8 + F * C::SSTRIDE * 8) + 15) & ~15;   // no integer round trip
     float2* s_tw = reinterpret_cast<float2*>(smem_raw + off_tw);
     float2* s_tw2 = s_tw + NC;
     float2* s_twp = s_tw2 + NC / 2 + 1;
@@ -313,7 +304,7 @@ __global__ void __launch_bounds__(kThreads, LOG2NC == 7 ? B2A_OCT_MINB : 1) cqt_
 #pragma unroll 1
     for (int r = 0; r < C::ROUNDS; ++r) {
         const int f = r * FR + slot;
-        float2* xb = s_xch + slot * C::XS1;
+        float2* xb = s_xch + slot * G::XSTRIDE;
         {
             float2 v[16];
             const float* a = s_audio + f * fstride + 2 * j;
@@ -331,19 +322,18 @@ __global__ void __launch_bounds__(kThreads, LOG2NC == 7 ? B2A_OCT_MINB : 1) cqt_
         frame_sync<T>();
         fft_tail_passes<LOG2NC, false>(xb, s_tw, nullptr, s_twp, j);
         {
-            float2* sp = C::INPLACE ? xb : s_spec + f * C::SSTRIDE;
-            auto si = [](int k) { return C::INPLACE ? xpad(k) : k; };       // spectrum index of bin k
+            float2* sp = s_spec + f * C::SSTRIDE;
 #pragma unroll
             for (int r2 = 0; r2 < 8; ++r2) {
                 const int k = j + T * r2;
                 float2 xk, xnk;
                 rfft_split(xb[xpad(k)], xb[xpad((NC - k) & (NC - 1))], s_tw2[k], xk, xnk);
-                sp[si(k)] = make_float2(0.5f * xk.x, 0.5f * xk.y);
-                sp[si(NC - k)] = make_float2(0.5f * xnk.x, 0.5f * xnk.y);
+                sp[k] = make_float2(0.5f * xk.x, 0.5f * xk.y);
+                sp[NC - k] = make_float2(0.5f * xnk.x, 0.5f * xnk.y);
             }
             if (j == 0) {
                 const float2 A = xb[xpad(NC / 2)];
-                sp[si(NC / 2)] = make_float2(A.x, -A.y);
+                sp[NC / 2] = make_float2(A.x, -A.y);
             }
         }
         frame_sync<T>();
@@ -354,13 +344,12 @@ __global__ void __launch_bounds__(kThreads, LOG2NC == 7 ? B2A_OCT_MINB : 1) cqt_
     float vmax = 0.f, vmin = 3.0e38f;
     for (int i = tid; i < p.n_rows * F; i += kThreads) {
         const int b = i / F, f = i % F;
-        const float2* x = C::INPLACE ? s_xch + f * C::XS1 : s_spec + f * C::SSTRIDE + s_k0[b];
-        const int kb0 = s_k0[b];
+        const float2* x = s_spec + f * C::SSTRIDE + s_k0[b];
         const float2* g = s_basis + s_off[b];
         const int cnt = s_cnt[b];
         float ar = 0.f, ai = 0.f;
         for (int qk = 0; qk < cnt; ++qk) {
-            const float2 gg = g[qk], xx = C::INPLACE ? x[xpad(kb0 + qk)] : x[qk];
+            const float2 gg = g[qk], xx = x[qk];
             ar = fmaf(gg.x, xx.x, ar); ar = fmaf(-gg.y, xx.y, ar);
             ai = fmaf(gg.x, xx.y, ai); ai = fmaf(gg.y, xx.x, ai);
         }
