@@ -81,6 +81,22 @@ def test_mel_other_shapes(n_fft, hop, n_mels, sr, n):
     assert np.abs(got - ref).max() <= MEL_TOL
 
 
+@pytest.mark.parametrize("dtype", [B.IN_I16, B.IN_F32])
+@pytest.mark.parametrize("n,pad", [(20011, B.PAD_CONSTANT), (20011, B.PAD_REFLECT), (44102, B.PAD_CONSTANT), (16005, B.PAD_CONSTANT)])
+def test_generic_kernel_staging_alignment(dtype, n, pad):
+    """n_fft 1024 runs on the generic kernel, whose 16-byte staging follows each clip's own alignment:
+    with these lengths clip i starts i * n samples into the batch, i.e. on every residue modulo 8
+    (odd ones included), so the scalar head, the narrowed shared-memory stores and the tail all run;
+    reflect padding keeps the clip edges on the one-sample path."""
+    pcm = synth.make_suite(21, 16000, n, seed=11)
+    x = pcm if dtype == B.IN_I16 else L.pcm16_to_float(pcm)
+    with _engine(B.KIND_MEL, n, dtype, n_fft=1024, hop_length=256, n_mels=64, sample_rate=16000, pad_mode=pad) as e:
+        got = e.run_host(x)
+    ref = _mel_oracle(pcm, sample_rate=16000, n_fft=1024, hop_length=256, n_mels=64,
+                      pad_mode="reflect" if pad == B.PAD_REFLECT else "constant")
+    assert np.abs(got - ref).max() <= MEL_TOL
+
+
 def test_mel_reflect_padding_option():
     pcm = synth.make_suite(7, 16000, 16000, seed=3)
     with _engine(B.KIND_MEL, 16000, pad_mode=B.PAD_REFLECT) as e:
