@@ -155,7 +155,7 @@ struct Layout {
     int chunk;          // samples staged per tile, multiple of 8
     int raw_bytes;      // bytes of one raw slot (multiple of 16)
     int gp;             // mfcc: DCT coefficients per mel warp, padded to a multiple of 4
-    int off_raw, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, off_db, off_dct, off_part, total;
+    int off_raw, off_xch, off_pow, off_tw2, off_melw, off_melk, off_red, off_bar, off_db, off_dct, off_part, off_zq, total;
 };
 
 __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc) {
@@ -177,6 +177,9 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.off_part = take(mfcc && n_mfcc <= kZFast ? 2 * kMelWarps * n_mfcc * 32 * 4 + 512 : 0);   // (reserve: with off_db and off_dct, KIND 2's [n_mels][128] columns + sums)
     L.gp = 4 * ((((n_mfcc + kMelWarps - 1) / kMelWarps) + 3) / 4);
     L.off_dct = take(mfcc ? n_mels * kMelWarps * L.gp * 4 : 0);   // mfcc: DCT-II basis as [mel][mel warp][gp]
+    // headline mfcc shape: [2 * odd coefficients][128 threads] float64 running sums of the per-clip DCT phase
+    L.off_zq = take(mfcc && n_mfcc == B2A_DCTSPEC_NMFCC && n_mels == B2A_MELSPEC_NMELS
+                        ? 2 * B2A_DCT_GROUP1_NK * kMelThreads * 8 : 0);
     L.total = o;
     return L;
 }
@@ -693,36 +696,63 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                 double* const s_zd = reinterpret_cast<double*>(smem + L.off_db + B2A_MELSPEC_NMELS * kMelThreads * 4);   // [mel warp][coefficient][S, Q]
                 const uint32_t s_col_a = smem_u32(s_col);
 #define B2A_DCT_LD(M) fmaxf(s_col[(M) * kMelThreads], thr)
-#define B2A_DCT_PASS(G)                                                                            \
-    {                                                                                              \
-        constexpr int NK = B2A_DCT_GROUP##G##_NK;                                                  \
-        double S[NK], Q[NK];                                                                       \
-        _Pragma("unroll") for (int k = 0; k < NK; ++k) { S[k] = 0.0; Q[k] = 0.0; }                 \
-        _Pragma("unroll 1") for (int t = mtid; t < nfr; t += kMelThreads) {                        \
-            float a[NK];                                                                           \
-            _Pragma("unroll") for (int k = 0; k < NK; ++k) a[k] = 0.f;                             \
-            {                                                                                      \
-                const float* src = inter + t;                                                      \
-                _Pragma("unroll") for (int m = 0; m < B2A_MELSPEC_NMELS; ++m, src += nfr)          \
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_col_a + m * kMelThreads * 4), "l"(src) : "memory"); \
-                asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");      \
-            }                                                                                      \
-            B2A_DCT_GROUP##G(B2A_DCT_LD, a)                                                        \
-            _Pragma("unroll") for (int k = 0; k < NK; ++k) {                                       \
-                outc[(size_t)B2A_DCT_GROUP##G##_KOF(k) * nfr + t] = a[k];                          \
-                const double ad = (double)a[k];                                                    \
-                S[k] += ad;                                                                        \
-                Q[k] = fma(ad, ad, Q[k]);                                                          \
-            }                                                                                      \
-        }                                                                                          \
-        _Pragma("unroll") for (int k = 0; k < NK; ++k) {                                           \
-            const double Sw = warp_sum_d(S[k]), Qw = warp_sum_d(Q[k]);                             \
-            if (lane == 0) { s_zd[(mw * B2A_DCTSPEC_NMFCC + B2A_DCT_GROUP##G##_KOF(k)) * 2] = Sw; s_zd[(mw * B2A_DCTSPEC_NMFCC + B2A_DCT_GROUP##G##_KOF(k)) * 2 + 1] = Qw; } \
-        }                                                                                          \
-    }
-                B2A_DCT_PASS(0)
-                B2A_DCT_PASS(1)
-#undef B2A_DCT_PASS
+                // One staged column serves both coefficient groups: the even group's float64 sums live in
+                // registers across the frames, the odd group's in shared memory next to the thread's
+                // column (both sets in registers would not fit the 64-register role; a second pass over
+                // the frames cost a second L2 round trip per frame).
+                constexpr int NK0 = B2A_DCT_GROUP0_NK, NK1 = B2A_DCT_GROUP1_NK;
+                double* const zq = reinterpret_cast<double*>(smem + L.off_zq) + mtid;          // [2 NK1][128]
+                double S0[NK0], Q0[NK0];
+#pragma unroll
+                for (int k = 0; k < NK0; ++k) { S0[k] = 0.0; Q0[k] = 0.0; }
+#pragma unroll
+                for (int k = 0; k < 2 * NK1; ++k) zq[k * kMelThreads] = 0.0;
+#pragma unroll 1
+                for (int t = mtid; t < nfr; t += kMelThreads) {
+                    {
+                        const float* src = inter + t;
+#pragma unroll
+                        for (int m = 0; m < B2A_MELSPEC_NMELS; ++m, src += nfr)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s_col_a + m * kMelThreads * 4), "l"(src) : "memory");
+                        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+                    }
+                    {
+                        float a[NK0];
+#pragma unroll
+                        for (int k = 0; k < NK0; ++k) a[k] = 0.f;
+                        B2A_DCT_GROUP0(B2A_DCT_LD, a)
+#pragma unroll
+                        for (int k = 0; k < NK0; ++k) {
+                            outc[(size_t)B2A_DCT_GROUP0_KOF(k) * nfr + t] = a[k];
+                            const double ad = (double)a[k];
+                            S0[k] += ad;
+                            Q0[k] = fma(ad, ad, Q0[k]);
+                        }
+                    }
+                    {
+                        float a[NK1];
+#pragma unroll
+                        for (int k = 0; k < NK1; ++k) a[k] = 0.f;
+                        B2A_DCT_GROUP1(B2A_DCT_LD, a)
+#pragma unroll
+                        for (int k = 0; k < NK1; ++k) {
+                            outc[(size_t)B2A_DCT_GROUP1_KOF(k) * nfr + t] = a[k];
+                            const double ad = (double)a[k];
+                            zq[(2 * k) * kMelThreads] += ad;
+                            zq[(2 * k + 1) * kMelThreads] = fma(ad, ad, zq[(2 * k + 1) * kMelThreads]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NK0; ++k) {
+                    const double Sw = warp_sum_d(S0[k]), Qw = warp_sum_d(Q0[k]);
+                    if (lane == 0) { s_zd[(mw * B2A_DCTSPEC_NMFCC + B2A_DCT_GROUP0_KOF(k)) * 2] = Sw; s_zd[(mw * B2A_DCTSPEC_NMFCC + B2A_DCT_GROUP0_KOF(k)) * 2 + 1] = Qw; }
+                }
+#pragma unroll
+                for (int k = 0; k < NK1; ++k) {
+                    const double Sw = warp_sum_d(zq[(2 * k) * kMelThreads]), Qw = warp_sum_d(zq[(2 * k + 1) * kMelThreads]);
+                    if (lane == 0) { s_zd[(mw * B2A_DCTSPEC_NMFCC + B2A_DCT_GROUP1_KOF(k)) * 2] = Sw; s_zd[(mw * B2A_DCTSPEC_NMFCC + B2A_DCT_GROUP1_KOF(k)) * 2 + 1] = Qw; }
+                }
 #undef B2A_DCT_LD
                 mel_sync();
                 if (mtid < B2A_DCTSPEC_NMFCC) {
