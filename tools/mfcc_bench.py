@@ -1,6 +1,6 @@
-"""audio_mfcc_seq (config 2) and audio_mel_spec device-resident throughput — profiling aid.
-   python tools/mfcc_bench.py            (B2A_MFCC_TILE_DCT=1 selects the dB-tile DCT for the headline shape)"""
-import sys, json, os
+"""audio_mfcc_seq (config 2: per-clip DCT; 12 coefficients: per-tile DCT) and audio_mel_spec
+device-resident throughput, with a 42-clip parity check — profiling aid.   python tools/mfcc_bench.py"""
+import sys, json
 import numpy as np, torch
 sys.path.insert(0, str(__import__("pathlib").Path(__file__).resolve().parents[1]))
 from audio_edge_ml_pipeline_b200 import _lib as B
@@ -28,11 +28,10 @@ def run(kind, n_clips, **kw):
             got = e.run_host(pcm)
             ref = np.stack([L.audio_mfcc_seq(L.pcm16_to_float(c), 16000, kw["n_mfcc"], 512, 160, 5.0, n_mels=40) for c in pcm])
             err = float(np.abs(got - ref).max())
-    print(json.dumps(dict(kind=kind, cfg=kw, tile_dct=bool(os.environ.get("B2A_MFCC_TILE_DCT")), clips_per_s=n_clips / ms * 1e3,
+    print(json.dumps(dict(kind=kind, cfg=kw, clips_per_s=n_clips / ms * 1e3,
                           ms=ms, max_abs_42=err)), flush=True)
 
 
 run(B.KIND_MFCC, 40000, n_samples=80000, sample_rate=16000, n_fft=512, hop_length=160, n_mels=40, n_mfcc=13)
-if not os.environ.get("B2A_MFCC_TILE_DCT"):
-    run(B.KIND_MFCC, 40000, n_samples=80000, sample_rate=16000, n_fft=512, hop_length=160, n_mels=40, n_mfcc=12)
-    run(B.KIND_MEL, 40000, n_samples=80000)
+run(B.KIND_MFCC, 40000, n_samples=80000, sample_rate=16000, n_fft=512, hop_length=160, n_mels=40, n_mfcc=12)
+run(B.KIND_MEL, 40000, n_samples=80000)
