@@ -65,6 +65,39 @@ __global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
         const bool pair_ok = (reinterpret_cast<uintptr_t>(base) & (sizeof(PairT) - 1)) == 0;
         constexpr int kBatch = 10;
         constexpr int kIters = (kDecLocal + kDecThreads - 1) / kDecThreads;      // 19
+        // Interior tiles (all but a clip's first and last): no bounds logic, every load of the tile in
+        // flight before the first conversion — the general path below spent a third of the kernel's
+        // time on index arithmetic and two DRAM round trips.
+        const bool interior = pair_ok && nstart >= 0 && nstart + 2 * kDecLocal <= in_len;    // CTA-uniform
+        if (interior && (I16 || (reinterpret_cast<uintptr_t>(base + (size_t)nstart * 4) & 15) == 0)) {
+            if constexpr (I16) {
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(base + (size_t)nstart * 2) + tid;
+                uint32_t raw[kIters];
+#pragma unroll
+                for (int u = 0; u < kIters; ++u)
+                    if (tid + u * kDecThreads < kDecLocal) raw[u] = __ldg(src + u * kDecThreads);
+#pragma unroll
+                for (int u = 0; u < kIters; ++u) {
+                    const int l = tid + u * kDecThreads;
+                    if (l < kDecLocal)
+                        s2[l] = make_float2(__int2float_rn((int)(short)(raw[u] & 0xffffu)) * (1.0f / 32768.0f),
+                                            __int2float_rn((int)raw[u] >> 16) * (1.0f / 32768.0f));
+                }
+            } else {
+                static_assert(kDecLocal % 2 == 0, "two sample pairs per 128-bit load");
+                constexpr int kQuads = kDecLocal / 2, kIt4 = (kQuads + kDecThreads - 1) / kDecThreads;   // 1184, 10
+                const float4* src = reinterpret_cast<const float4*>(base + (size_t)nstart * 4) + tid;
+                float4 raw[kIt4];
+#pragma unroll
+                for (int u = 0; u < kIt4; ++u)
+                    if (tid + u * kDecThreads < kQuads) raw[u] = __ldg(src + u * kDecThreads);
+#pragma unroll
+                for (int u = 0; u < kIt4; ++u) {
+                    const int q = tid + u * kDecThreads;
+                    if (q < kQuads) *reinterpret_cast<float4*>(&s2[2 * q]) = raw[u];
+                }
+            }
+        } else
 #pragma unroll 1
         for (int k0 = 0; k0 < kIters; k0 += kBatch) {
             PairT raw[kBatch];
