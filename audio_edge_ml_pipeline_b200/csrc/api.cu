@@ -91,6 +91,7 @@ struct b2a_handle {
     b2a::CqtDevice cqtdev;
     // run_host resources
     cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev_kernels[2] = {nullptr, nullptr};   // chunk c's kernels done (mfcc / cqt share one scratch per handle)
     void* d_in[2] = {nullptr, nullptr};
     float* d_out[2] = {nullptr, nullptr};
     int64_t chunk_clips = 0;
@@ -131,6 +132,7 @@ int b2a_destroy(b2a_handle* h) {
     cudaSetDevice(h->device);
     for (int i = 0; i < 2; ++i) {
         if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); }
+        if (h->ev_kernels[i]) cudaEventDestroy(h->ev_kernels[i]);
         cudaFree(h->d_in[i]); cudaFree(h->d_out[i]);
     }
     cudaFree(h->d_window); cudaFree(h->d_tw); cudaFree(h->d_tw2);
@@ -350,6 +352,7 @@ int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out) 
         h->chunk_clips = cc;
         for (int i = 0; i < 2; ++i) {
             CU_TRY(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&h->ev_kernels[i], cudaEventDisableTiming));
             CU_TRY(cudaMalloc(&h->d_in[i], in_clip * cc));
             CU_TRY(cudaMalloc((void**)&h->d_out[i], out_clip * cc));
         }
@@ -363,8 +366,14 @@ int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out) 
         const unsigned char* src = (const unsigned char*)clips + (size_t)done * in_clip;
         float* dst = (float*)((unsigned char*)out + (size_t)done * out_clip);
         CU_TRY(cudaMemcpyAsync(h->d_in[s], src, in_clip * nb, cudaMemcpyHostToDevice, h->streams[s]));
+        // The two streams overlap copies with kernels, but the kernels of consecutive chunks must not
+        // overlap each other when they work in the handle's scratch (mfcc: raw-dB rows per CTA index;
+        // cqt: decimated signals and per-clip extrema): chunk c+1's kernels wait for chunk c's.
+        const bool shared_scratch = h->cfg.kind != B2A_KIND_MEL;
+        if (shared_scratch && c > 0) CU_TRY(cudaStreamWaitEvent(h->streams[s], h->ev_kernels[s ^ 1], 0));
         rc = run_device_impl(h, h->d_in[s], nb, h->d_out[s], h->streams[s], &h->last_launches);
         if (rc != B2A_OK) break;
+        if (shared_scratch) CU_TRY(cudaEventRecord(h->ev_kernels[s], h->streams[s]));
         CU_TRY(cudaMemcpyAsync(dst, h->d_out[s], out_clip * nb, cudaMemcpyDeviceToHost, h->streams[s]));
         done += nb;
     }

@@ -91,7 +91,9 @@ int b2a_out_shape(const b2a_handle* h, int32_t* rows, int32_t* frames);
 /* Device-resident path: d_clips and d_out are device pointers on the handle's device; the work
  * is enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and the call returns
  * without synchronising.  d_clips: [n_clips][n_samples] of input_dtype; d_out:
- * [n_clips][rows][frames] float32. */
+ * [n_clips][rows][frames] float32.  mfcc and cqt handles work in per-handle device scratch: two
+ * calls on the SAME handle must not run concurrently (use one stream, or order the streams with an
+ * event); different handles are independent. */
 int b2a_run_device(b2a_handle* h, const void* d_clips, int64_t n_clips, float* d_out,
                    void* stream);
 

@@ -310,6 +310,25 @@ def test_ragged_batch_matches_per_clip_oracle(kind, n_fft, hop):
         assert np.abs(g - ref).max() <= tol, (len(c), float(np.abs(g - ref).max()))
 
 
+@pytest.mark.parametrize("kind,sr,n,kw", [
+    (B.KIND_MFCC, 16000, 8000, dict(sample_rate=16000, n_fft=512, hop_length=160, n_mels=40, n_mfcc=13)),
+    (B.KIND_MFCC, 16000, 8000, dict(sample_rate=16000, n_fft=1024, hop_length=256, n_mels=64, n_mfcc=20)),
+    (B.KIND_CQT, 22050, 11025, dict()),
+])
+def test_host_batches_larger_than_one_chunk(kind, sr, n, kw):
+    """b2a_run_host cuts a batch into chunks on two streams.  mfcc and cqt kernels work in per-handle
+    scratch, so the kernels of consecutive chunks must not overlap: a batch of several chunks (every
+    clip repeated many times) must give, row for row, what the same clips give in a single chunk."""
+    base = synth.make_suite(35, sr, n, seed=21)
+    reps = 260                                   # 9100 clips: 3-6 chunks for these clip sizes
+    with _engine(kind, n, **kw) as e:
+        one = e.run_host(base)
+        many = e.run_host(np.tile(base, (reps, 1)))
+        assert e.last_launch_count > (1 if kind != B.KIND_CQT else 16)
+    assert many.shape == (35 * reps,) + one.shape[1:]
+    assert np.array_equal(many.reshape(reps, 35, *one.shape[1:]), np.broadcast_to(one, (reps,) + one.shape))
+
+
 def test_ragged_rejects_bad_lengths():
     with _engine(B.KIND_MEL, 16000) as e:
         with pytest.raises(B.B2AError):
