@@ -38,7 +38,7 @@ def run(name, kind, sr, n, fn, n_clips, **kw):
         row = np.abs(got - ref).max(axis=2)       # (clips, rows) z-score error
         extra = dict(z_err_by_min_sd={str(t): float(np.where(sd >= t, row, 0).max()) for t in (0.5, 1, 2, 4, 8, 16)},
                      mfcc_err_by_max_sd={str(t): float(np.where(sd < t, row * sd, 0).max()) for t in (0.5, 1, 2, 4, 8, 16)},
-                     worst_over_tolerance=float((row / np.maximum(1.0, 4.0 / np.maximum(sd, 1e-12))).max() / 1e-3))
+                     worst_over_tolerance=float((row / np.maximum(1.0, 1.0 / np.maximum(sd, 1e-12))).max() / 1e-3))
     err = np.abs(got - ref).reshape(n_clips, -1).max(axis=1)
     fam = [float(err[f::synth.N_FAMILIES].max()) for f in range(synth.N_FAMILIES)]
     print(json.dumps(dict(config=name, clips=n_clips, shape=list(got.shape[1:]), max_abs=float(err.max()),
