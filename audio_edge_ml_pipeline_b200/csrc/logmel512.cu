@@ -17,8 +17,11 @@
 //     (gen_mel.cpp) with the 490 filter weights as FFMA immediates and every power pair loaded
 //     once.  Raw dB goes to the output buffer (L2-resident), per-clip max/min stay in registers,
 //     and a clip is normalised in place during the NEXT clip's tiles, a prefetched slice per tile
-//     (mfcc: in-tile DCT-II, recomputed from an L2 scratch only when the top_db clip engages,
-//     z-score statistics from running sums, rows rewritten by the same deferred pass).
+//     (mfcc, headline shape: the DCT-II of the whole clip runs once at clip end from the raw-dB
+//     scratch in L2, one frame per thread through cp.async-staged columns, basis folded on its
+//     symmetry and generated as FFMA immediates, float64 z-score sums on the way; other mfcc
+//     shapes: in-tile table-driven DCT, recomputed from the scratch only when the top_db clip
+//     engages.  Either way the rows are z-scored by the same deferred pass).
 //   * Hand-off by mbarriers only: raw_full (TMA tx bytes) -> FFT; pow_full (16 warp arrivals)
 //     -> mel; pow_empty (4 warp arrivals) -> FFT.  pow_full of tile i also tells the producer
 //     that the raw slot of tile i is free again.
@@ -174,7 +177,8 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.off_red = take((64 + 2 * kZFast) * 4);          // per-warp max/min, then (mean, sd) per coefficient
     L.off_bar = take((kMaxRaw + 2 * 3) * 8);
     L.off_db = take(mfcc ? n_mels * 32 * 4 : 0);      // mfcc: [n_mels][32] dB tile feeding the in-tile DCT
-    L.off_part = take(mfcc && n_mfcc <= kZFast ? 2 * kMelWarps * n_mfcc * 32 * 4 + 512 : 0);   // (reserve: with off_db and off_dct, KIND 2's [n_mels][128] columns + sums)
+    L.off_part = take(mfcc && n_mfcc <= kZFast ? 2 * kMelWarps * n_mfcc * 32 * 4 + 512 : 0);   // reserve: with off_db and off_dct it holds
+                                                                                             // KIND 2's [n_mels][128] columns + per-warp sums
     L.gp = 4 * ((((n_mfcc + kMelWarps - 1) / kMelWarps) + 3) / 4);
     L.off_dct = take(mfcc ? n_mels * kMelWarps * L.gp * 4 : 0);   // mfcc: DCT-II basis as [mel][mel warp][gp]
     // headline mfcc shape: [2 * odd coefficients][128 threads] float64 running sums of the per-clip DCT phase
