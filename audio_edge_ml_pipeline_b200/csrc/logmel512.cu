@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
         if (KIND == 1) s_db[(M) * 32 + lane] = vv;                                  \
         if (valid) outp[(M) * nfr] = vv;      /* predicated store: the band sweep stays one basic block */ \
         vmax = fmaxf(vmax, valid ? vv : vmax);                                      \
-        vmin = fminf(vmin, valid ? vv : vmin);                                      \
+        if (KIND != 2) vmin = fminf(vmin, valid ? vv : vmin);   /* KIND 2 clamps at clip end and needs only the peak */ \
     }
                         switch (mw) {
                             case 0: B2A_MEL_WARP0(pla, B2A_EMIT) break;
