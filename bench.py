@@ -187,7 +187,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -344,7 +344,7 @@ def run_ours(args):
         }
         if world == 1 and not args.no_cpu and args.extractor == "mel":
             line["cpu_baseline"] = cpu_baseline_serial(args.cpu_clips)
-        print(json.dumps(line), flush=True)
+        _emit(line)
     pin_in.close()
     pin_out.close()
     ext.close()
@@ -352,6 +352,18 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+_REAL_STDOUT = None
+
+
+def _emit(line: dict) -> None:
+    """The ONE JSON line, on the process's real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -367,6 +379,12 @@ def main():
     ap.add_argument("--extractor", default="mel", choices=["mel", "mfcc", "cqt"],
                     help="mel = the headline metric; mfcc / cqt = BASELINE configs 2 / 3 at scale")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print on fd 1 while the
+    # bench runs (NCCL writes its version banner there when the box sets NCCL_DEBUG) goes to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
