@@ -8,13 +8,16 @@ fails loudly when the library or a CUDA device is missing.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import threading
 from pathlib import Path
 from typing import Optional
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libb2a.so"
+# B2A_LIBRARY: another build of the same library (build.build_variant: numerics A/B experiments)
+LIB_PATH = Path(os.environ["B2A_LIBRARY"]) if os.environ.get("B2A_LIBRARY") else PKG / "libb2a.so"
 
 KIND_MEL, KIND_MFCC, KIND_CQT = 0, 1, 2
 IN_I16, IN_F32 = 0, 1
@@ -23,7 +26,7 @@ TABLE_WINDOW, TABLE_MEL_DENSE, TABLE_DCT, TABLE_DECIM_TAPS, TABLE_CQT_LENGTHS, T
 
 EXPORTED_SYMBOLS = [
     "b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
-    "b2a_run_host", "b2a_run_host_ragged", "b2a_run_device_ragged", "b2a_last_launch_count", "b2a_alloc_pinned", "b2a_free_pinned",
+    "b2a_run_host", "b2a_run_host_copy_only", "b2a_run_host_ragged", "b2a_run_device_ragged", "b2a_last_launch_count", "b2a_alloc_pinned", "b2a_free_pinned",
     "b2a_decode_wav_pcm16_batch", "b2a_get_table", "b2a_cqt_geometry", "b2a_last_error", "b2a_abi_version", "b2a_device_count",
     "b2a_resampler_create", "b2a_resampler_destroy", "b2a_resampler_out_len", "b2a_resampler_geometry",
     "b2a_resampler_design", "b2a_resampler_run_host", "b2a_resampler_run_device", "b2a_resampler_last_error",
@@ -66,6 +69,8 @@ def load_library() -> C.CDLL:
     lib.b2a_out_shape.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     lib.b2a_run_device.argtypes = [vp, vp, i64, vp, vp]
     lib.b2a_run_host.argtypes = [vp, vp, i64, vp]
+    lib.b2a_run_host_copy_only.argtypes = [vp, vp, i64, vp]
+    lib.b2a_run_host_copy_only.restype = C.c_int
     lib.b2a_run_host_ragged.argtypes = [vp, vp, i64, vp, vp, vp, i64, vp, i64]
     lib.b2a_run_device_ragged.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
     lib.b2a_decode_wav_pcm16_batch.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp, i32]
@@ -208,6 +213,11 @@ class Engine:
         _check(self._lib.b2a_run_host(self._h, clips.ctypes.data, n, out.ctypes.data))
         return out
 
+    def run_host_copy_only(self, clips: np.ndarray, out: np.ndarray) -> None:
+        """run_host's H2D / D2H schedule without the kernels (transfer ceiling; `out` is garbage)."""
+        assert clips.flags.c_contiguous and out.flags.c_contiguous and clips.dtype == self.in_dtype
+        _check(self._lib.b2a_run_host_copy_only(self._h, clips.ctypes.data, clips.shape[0], out.ctypes.data))
+
     def run_host_ragged(self, clips: list) -> list:
         """Variable-length clips (each 1-D, dtype = the engine's input dtype, n_fft <= len <=
         cfg.n_samples) -> list of (rows, 1 + len // hop) float32 arrays, one launch."""
@@ -327,12 +337,20 @@ class Resampler:
 
 
 _resamplers: dict = {}
+_resamplers_lock = threading.Lock()
+
+
+def get_resampler(orig_sr: int, target_sr: int, device: int = 0) -> "Resampler":
+    """The process-wide resampler of (orig, target, device); creation is serialised (decode workers
+    race here), use is serialised inside the library (b2a_resampler_run_host holds the handle's mutex)."""
+    key = (int(orig_sr), int(target_sr), int(device))
+    with _resamplers_lock:
+        r = _resamplers.get(key)
+        if r is None:
+            r = _resamplers[key] = Resampler(*key)
+        return r
 
 
 def resample(y: np.ndarray, orig_sr: int, target_sr: int, device: int = 0) -> np.ndarray:
     """librosa.resample(y, orig_sr, target_sr, res_type="soxr_hq") stand-in (see Resampler)."""
-    key = (int(orig_sr), int(target_sr), int(device))
-    r = _resamplers.get(key)
-    if r is None:
-        r = _resamplers[key] = Resampler(*key)
-    return r.run_host(y)
+    return get_resampler(orig_sr, target_sr, device).run_host(y)

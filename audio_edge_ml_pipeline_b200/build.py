@@ -39,17 +39,28 @@ def _fingerprint() -> str:
     return h.hexdigest()
 
 
-def build_lib(force: bool = False, verbose: bool = False) -> Path:
+def build_variant(tag: str, defines: list, verbose: bool = False) -> Path:
+    """An experimental build with extra -D flags (numerics A/B runs, tools/mfcc_floor.py) as
+    build/libb2a_<tag>.so; loaded instead of the product library through the B2A_LIBRARY variable."""
+    return build_lib(force=True, verbose=verbose, extra=[f"-D{d}" for d in defines],
+                     lib=PKG / "build" / f"libb2a_{tag}.so", objdir=PKG / "build" / f"obj_{tag}")
+
+
+def build_lib(force: bool = False, verbose: bool = False, extra: list = (), lib: Path = LIB,
+              objdir: Path = None) -> Path:
     """Compile (if sources changed) and return the path of libb2a.so."""
+    product = lib == LIB
     stamp = PKG / ".libb2a.stamp"
     fp = _fingerprint()
-    if not force and LIB.exists() and stamp.exists() and stamp.read_text() == fp:
+    if product and not force and LIB.exists() and stamp.exists() and stamp.read_text() == fp:
         return LIB
     nvcc = _nvcc()
-    objdir = PKG / "build"
+    gendir = PKG / "build"
+    gendir.mkdir(exist_ok=True)
+    objdir = objdir or gendir
     objdir.mkdir(exist_ok=True)
     # build-time code generation: straight-line mel code for the headline configuration
-    gen = objdir / "gen_mel"
+    gen = gendir / "gen_mel"
     subprocess.run(["g++", "-O2", "-std=c++17", str(CSRC / "gen_mel.cpp"), str(CSRC / "tables.cpp"), "-o", str(gen)],
                    check=True)
     inc = subprocess.run([str(gen), "16000", "512", "40", "4", "13"], check=True, capture_output=True, text=True).stdout
@@ -61,7 +72,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
     tgt2 = CSRC / "gen" / "decim_taps.inc"
     if not tgt2.exists() or tgt2.read_text() != inc2:
         tgt2.write_text(inc2)
-    flags = list(NVCC_FLAGS) + os.environ.get("B2A_NVCC_EXTRA", "").split()
+    flags = list(NVCC_FLAGS) + os.environ.get("B2A_NVCC_EXTRA", "").split() + list(extra)
     procs = []
     objs = []
     for src in SOURCES:
@@ -77,10 +88,11 @@ def build_lib(force: bool = False, verbose: bool = False) -> Path:
             print(out.decode(errors="replace"))
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}")
-    subprocess.run([nvcc, "-shared", "-o", str(LIB), *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"],
+    subprocess.run([nvcc, "-shared", "-o", str(lib), *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"],
                    check=True)
-    stamp.write_text(fp)
-    return LIB
+    if product:
+        stamp.write_text(fp)
+    return lib
 
 
 if __name__ == "__main__":

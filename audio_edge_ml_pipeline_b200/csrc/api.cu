@@ -95,6 +95,11 @@ struct b2a_handle {
     void* d_in[2] = {nullptr, nullptr};
     float* d_out[2] = {nullptr, nullptr};
     int64_t chunk_clips = 0;
+    bool host_ready = false;                          // set only after every run_host resource exists
+    // run_host_ragged resources (grow-only, reused across calls)
+    cudaStream_t rag_stream = nullptr;
+    void* rag_in = nullptr; float* rag_out = nullptr; void* rag_meta = nullptr;
+    size_t rag_in_cap = 0, rag_out_cap = 0, rag_meta_cap = 0;
 };
 
 extern "C" {
@@ -135,6 +140,8 @@ int b2a_destroy(b2a_handle* h) {
         if (h->ev_kernels[i]) cudaEventDestroy(h->ev_kernels[i]);
         cudaFree(h->d_in[i]); cudaFree(h->d_out[i]);
     }
+    if (h->rag_stream) { cudaStreamSynchronize(h->rag_stream); cudaStreamDestroy(h->rag_stream); }
+    cudaFree(h->rag_in); cudaFree(h->rag_out); cudaFree(h->rag_meta);
     cudaFree(h->d_window); cudaFree(h->d_tw); cudaFree(h->d_tw2);
     cudaFree(h->d_k0); cudaFree(h->d_cnt); cudaFree(h->d_off); cudaFree(h->d_w);
     cudaFree(h->d_wq); cudaFree(h->d_k0e); cudaFree(h->d_cnt4); cudaFree(h->d_off4); cudaFree(h->d_order);
@@ -317,7 +324,7 @@ static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, 
     p.n_mfcc = h->cfg.n_mfcc; p.pad_mode = h->cfg.pad_mode; p.top_db = h->cfg.top_db;
     p.mel_wq = h->d_wq; p.mel_k0e = h->d_k0e; p.mel_cnt4 = h->d_cnt4; p.mel_off4 = h->d_off4; p.mel_order = h->d_order;
     p.mel_wpad = h->mel_wpad;
-    p.mel_special = (h->use512 && !h->cfg.reserved[0] && b2a::logmel512_has_special(h->cfg.sample_rate, h->cfg.n_mels)) ? 1 : 0;
+    p.mel_special = (h->use512 && b2a::logmel512_has_special(h->cfg.sample_rate, h->cfg.n_mels)) ? 1 : 0;
     const int grid = (int)std::min<int64_t>(n_clips, h->grid_cap);
     const bool i16 = h->cfg.input_dtype == B2A_IN_I16;
     const int kind = h->cfg.kind == B2A_KIND_MFCC ? 1 : 0;
@@ -336,7 +343,56 @@ int b2a_run_device(b2a_handle* h, const void* d_clips, int64_t n_clips, float* d
     return run_device_impl(h, d_clips, n_clips, d_out, (cudaStream_t)stream, &h->last_launches);
 }
 
+// Frees whatever a failed lazy init of the run_host resources left behind, so the next call retries.
+static void host_teardown(b2a_handle* h) {
+    for (int i = 0; i < 2; ++i) {
+        if (h->streams[i]) { cudaStreamSynchronize(h->streams[i]); cudaStreamDestroy(h->streams[i]); h->streams[i] = nullptr; }
+        if (h->ev_kernels[i]) { cudaEventDestroy(h->ev_kernels[i]); h->ev_kernels[i] = nullptr; }
+        cudaFree(h->d_in[i]); h->d_in[i] = nullptr;
+        cudaFree(h->d_out[i]); h->d_out[i] = nullptr;
+    }
+    h->host_ready = false;
+}
+
+static int host_init(b2a_handle* h, size_t in_clip, size_t out_clip) {
+    // ~64 MiB of input per chunk, two chunks in flight.  mel / mfcc kernels are persistent (one clip
+    // per CTA at a time, grid = min(n, grid_cap)): a chunk is a whole number of waves of grid_cap clips.
+    int64_t cc = (int64_t)((64u << 20) / in_clip);
+    cc = std::max<int64_t>(1, std::min<int64_t>(cc, 4096));
+    if (h->cfg.kind == B2A_KIND_CQT) cc = std::max<int64_t>(cc, 1024);   // one full CQT chunk per copy
+    else if (h->grid_cap > 0 && cc > h->grid_cap) cc = ((cc + h->grid_cap - 1) / h->grid_cap) * h->grid_cap;
+    h->chunk_clips = cc;
+    cudaError_t e = cudaSuccess;
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_kernels[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_in[i], in_clip * cc);
+        if (e == cudaSuccess) e = cudaMalloc((void**)&h->d_out[i], out_clip * cc);
+    }
+    if (e != cudaSuccess) {
+        host_teardown(h);            // the handle stays usable: the next call starts from scratch
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA,
+                    std::string("run_host resources: ") + cudaGetErrorString(e));
+    }
+    h->host_ready = true;
+    return B2A_OK;
+}
+
+static int run_host_impl(b2a_handle* h, const void* clips, int64_t n_clips, float* out, bool copy_only);
+
 int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out) {
+    return run_host_impl(h, clips, n_clips, out, false);
+}
+
+// Diagnostic: b2a_run_host's exact copy schedule (same chunks, streams, device buffers) with the kernels
+// left out; `out` receives whatever the device buffers hold.  The time of this call is the host<->device
+// transfer ceiling of the host path on this box (bench.py reports e2e against it).
+int b2a_run_host_copy_only(b2a_handle* h, const void* clips, int64_t n_clips, float* out) {
+    return run_host_impl(h, clips, n_clips, out, true);
+}
+
+static int run_host_impl(b2a_handle* h, const void* clips, int64_t n_clips, float* out, bool copy_only) {
     if (!h) return fail(B2A_EINVAL, "handle is NULL");
     if (n_clips < 0) return fail(B2A_EINVAL, "n_clips < 0");
     if (n_clips == 0) { h->last_launches = 0; return B2A_OK; }
@@ -344,42 +400,41 @@ int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out) 
     CU_TRY(cudaSetDevice(h->device));
     const size_t in_clip = (size_t)h->cfg.n_samples * h->in_elem;
     const size_t out_clip = (size_t)h->rows * h->frames * sizeof(float);
-    if (!h->streams[0]) {
-        // ~64 MiB of input per chunk, two chunks in flight
-        int64_t cc = (int64_t)((64u << 20) / in_clip);
-        cc = std::max<int64_t>(1, std::min<int64_t>(cc, 4096));
-        if (h->cfg.kind == B2A_KIND_CQT) cc = std::max<int64_t>(cc, 1024);   // one full CQT chunk per copy
-        h->chunk_clips = cc;
-        for (int i = 0; i < 2; ++i) {
-            CU_TRY(cudaStreamCreateWithFlags(&h->streams[i], cudaStreamNonBlocking));
-            CU_TRY(cudaEventCreateWithFlags(&h->ev_kernels[i], cudaEventDisableTiming));
-            CU_TRY(cudaMalloc(&h->d_in[i], in_clip * cc));
-            CU_TRY(cudaMalloc((void**)&h->d_out[i], out_clip * cc));
-        }
+    if (!h->host_ready) {
+        const int irc = host_init(h, in_clip, out_clip);
+        if (irc != B2A_OK) return irc;
     }
     h->last_launches = 0;
     int rc = B2A_OK;
+    cudaError_t ce = cudaSuccess;
+    const char* what = "";
+    // Every failure inside the loop leaves through the common exit below, which drains both streams:
+    // copies into the caller's `out` that were already enqueued must not outlive this call.
+#define CU_STEP(expr) { ce = (expr); if (ce != cudaSuccess) { what = #expr; break; } }
     int64_t done = 0;
     for (int c = 0; done < n_clips; ++c) {
         const int s = c & 1;
         const int64_t nb = std::min<int64_t>(h->chunk_clips, n_clips - done);
         const unsigned char* src = (const unsigned char*)clips + (size_t)done * in_clip;
         float* dst = (float*)((unsigned char*)out + (size_t)done * out_clip);
-        CU_TRY(cudaMemcpyAsync(h->d_in[s], src, in_clip * nb, cudaMemcpyHostToDevice, h->streams[s]));
+        CU_STEP(cudaMemcpyAsync(h->d_in[s], src, in_clip * nb, cudaMemcpyHostToDevice, h->streams[s]));
         // The two streams overlap copies with kernels, but the kernels of consecutive chunks must not
         // overlap each other when they work in the handle's scratch (mfcc: raw-dB rows per CTA index;
         // cqt: decimated signals and per-clip extrema): chunk c+1's kernels wait for chunk c's.
         const bool shared_scratch = h->cfg.kind != B2A_KIND_MEL;
-        if (shared_scratch && c > 0) CU_TRY(cudaStreamWaitEvent(h->streams[s], h->ev_kernels[s ^ 1], 0));
-        rc = run_device_impl(h, h->d_in[s], nb, h->d_out[s], h->streams[s], &h->last_launches);
+        if (shared_scratch && c > 0) CU_STEP(cudaStreamWaitEvent(h->streams[s], h->ev_kernels[s ^ 1], 0));
+        if (!copy_only) rc = run_device_impl(h, h->d_in[s], nb, h->d_out[s], h->streams[s], &h->last_launches);
         if (rc != B2A_OK) break;
-        if (shared_scratch) CU_TRY(cudaEventRecord(h->ev_kernels[s], h->streams[s]));
-        CU_TRY(cudaMemcpyAsync(dst, h->d_out[s], out_clip * nb, cudaMemcpyDeviceToHost, h->streams[s]));
+        if (shared_scratch) CU_STEP(cudaEventRecord(h->ev_kernels[s], h->streams[s]));
+        CU_STEP(cudaMemcpyAsync(dst, h->d_out[s], out_clip * nb, cudaMemcpyDeviceToHost, h->streams[s]));
         done += nb;
     }
-    cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
-    cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
-    if (rc != B2A_OK) return rc;
+#undef CU_STEP
+    const cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
+    const cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
+    if (rc != B2A_OK) return rc;                     // run_device_impl already set the message
+    if (ce != cudaSuccess)
+        return fail(ce == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA, std::string(what) + ": " + cudaGetErrorString(ce));
     CU_TRY(e0);
     CU_TRY(e1);
     return B2A_OK;
@@ -417,37 +472,46 @@ int b2a_run_host_ragged(b2a_handle* h, const void* clips, int64_t total_in, cons
         if (out_offsets[i] < 0 || out_offsets[i] + need > total_out) return fail(B2A_EINVAL, "output offset out of range");
     }
     CU_TRY(cudaSetDevice(h->device));
-    void* d_in = nullptr; float* d_out = nullptr; long long* d_io = nullptr; long long* d_oo = nullptr; int* d_len = nullptr;
+    // Per-handle scratch, grown on demand and kept (no allocation in the steady state), on the handle's
+    // own non-blocking stream.  Offsets and lengths travel in one block: [in_off | out_off | len].
+    if (!h->rag_stream) CU_TRY(cudaStreamCreateWithFlags(&h->rag_stream, cudaStreamNonBlocking));
+    auto grow = [](void** p, size_t* cap, size_t need) -> cudaError_t {
+        if (need <= *cap) return cudaSuccess;
+        cudaFree(*p); *p = nullptr; *cap = 0;
+        const size_t want = need + need / 4;
+        cudaError_t e = cudaMalloc(p, want);
+        if (e == cudaSuccess) *cap = want;
+        return e;
+    };
+    const size_t meta_bytes = (size_t)n_clips * (8 + 8 + 4);
+    CU_TRY(grow(&h->rag_in, &h->rag_in_cap, (size_t)total_in * h->in_elem));
+    CU_TRY(grow((void**)&h->rag_out, &h->rag_out_cap, (size_t)total_out * sizeof(float)));
+    CU_TRY(grow(&h->rag_meta, &h->rag_meta_cap, meta_bytes));
+    long long* const d_io = (long long*)h->rag_meta;
+    long long* const d_oo = d_io + n_clips;
+    int* const d_len = (int*)(d_oo + n_clips);
+    cudaStream_t st = h->rag_stream;
     int rc = B2A_OK;
-    cudaStream_t st = nullptr;
-    auto cleanup = [&]() { cudaFree(d_in); cudaFree(d_out); cudaFree(d_io); cudaFree(d_oo); cudaFree(d_len); };
-#define CU_TRY_R(expr)                                                                     \
-    do {                                                                                   \
-        cudaError_t e__ = (expr);                                                          \
-        if (e__ != cudaSuccess) {                                                          \
-            cleanup();                                                                     \
-            return fail(e__ == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA,         \
-                        std::string(#expr) + ": " + cudaGetErrorString(e__));              \
-        }                                                                                  \
-    } while (0)
-    CU_TRY_R(cudaMalloc(&d_in, (size_t)total_in * h->in_elem));
-    CU_TRY_R(cudaMalloc((void**)&d_out, (size_t)total_out * sizeof(float)));
-    CU_TRY_R(cudaMalloc((void**)&d_io, (size_t)n_clips * 8));
-    CU_TRY_R(cudaMalloc((void**)&d_oo, (size_t)n_clips * 8));
-    CU_TRY_R(cudaMalloc((void**)&d_len, (size_t)n_clips * 4));
-    CU_TRY_R(cudaMemcpyAsync(d_in, clips, (size_t)total_in * h->in_elem, cudaMemcpyHostToDevice, st));
-    CU_TRY_R(cudaMemcpyAsync(d_io, in_offsets, (size_t)n_clips * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY_R(cudaMemcpyAsync(d_oo, out_offsets, (size_t)n_clips * 8, cudaMemcpyHostToDevice, st));
-    CU_TRY_R(cudaMemcpyAsync(d_len, lengths, (size_t)n_clips * 4, cudaMemcpyHostToDevice, st));
-    h->last_launches = 0;
-    rc = run_device_impl(h, d_in, n_clips, d_out, st, &h->last_launches, d_io, d_len, d_oo);
-    if (rc == B2A_OK) {
-        CU_TRY_R(cudaMemcpyAsync(out, d_out, (size_t)total_out * sizeof(float), cudaMemcpyDeviceToHost, st));
-        CU_TRY_R(cudaStreamSynchronize(st));
-    }
-    cleanup();
-    return rc;
-#undef CU_TRY_R
+    cudaError_t ce = cudaSuccess;
+    const char* what = "";
+#define CU_STEP(expr) { ce = (expr); if (ce != cudaSuccess) { what = #expr; break; } }
+    do {
+        CU_STEP(cudaMemcpyAsync(h->rag_in, clips, (size_t)total_in * h->in_elem, cudaMemcpyHostToDevice, st));
+        CU_STEP(cudaMemcpyAsync(d_io, in_offsets, (size_t)n_clips * 8, cudaMemcpyHostToDevice, st));
+        CU_STEP(cudaMemcpyAsync(d_oo, out_offsets, (size_t)n_clips * 8, cudaMemcpyHostToDevice, st));
+        CU_STEP(cudaMemcpyAsync(d_len, lengths, (size_t)n_clips * 4, cudaMemcpyHostToDevice, st));
+        h->last_launches = 0;
+        rc = run_device_impl(h, h->rag_in, n_clips, h->rag_out, st, &h->last_launches, d_io, d_len, d_oo);
+        if (rc != B2A_OK) break;
+        CU_STEP(cudaMemcpyAsync(out, h->rag_out, (size_t)total_out * sizeof(float), cudaMemcpyDeviceToHost, st));
+    } while (0);
+#undef CU_STEP
+    const cudaError_t es = cudaStreamSynchronize(st);     // also on failure: nothing may still touch the caller's buffers
+    if (rc != B2A_OK) return rc;
+    if (ce != cudaSuccess)
+        return fail(ce == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+    CU_TRY(es);
+    return B2A_OK;
 }
 
 int b2a_alloc_pinned(size_t bytes, void** out) {

@@ -40,7 +40,10 @@ constexpr int kDecTile = kDecThreads * kDecR;   // outputs per CTA
 #endif
 constexpr int kDecU = B2A_DEC_U;                // tap pairs per register-window step (8 or 11)
 constexpr int kDecHalf = 192;                   // tap pairs (the odd phase is zero-padded)
-constexpr int kDecMid = 16;                     // centre tap pairs accumulated in fp64: pairs [88, 104)
+#ifndef B2A_AB_DECMID
+#define B2A_AB_DECMID 16
+#endif
+constexpr int kDecMid = B2A_AB_DECMID;          // centre tap pairs accumulated in fp64: pairs [88, 104)
 constexpr int kDecOuter = (kDecHalf - kDecMid) / 2;   // 88 pairs on either side
 constexpr int kDecLocal = kDecTile + kDecHalf;  // staged sample pairs
 static_assert(kDecOuter % kDecU == 0, "outer taps must split into whole window steps");

@@ -14,6 +14,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#ifndef B2A_AB_EXACT_BFLY
+#define B2A_AB_EXACT_BFLY 0
+#endif
+
 namespace b2a {
 
 // ---- packed FP32 (sm_100a FADD2 / FMUL2 / FFMA2) -----------------------------------------------
@@ -41,7 +45,11 @@ __device__ __forceinline__ float2 cmul_mi(float2 a) { return make_float2(a.y, -a
 // 2e - first (one extra rounding, ~1 ulp).
 __device__ __forceinline__ void bfly_w(float2 e, float2 o, float wr, float wi, float2& a, float2& b) {
     a = __ffma2_rn(make_float2(o.y, o.x), make_float2(-wi, wi), __ffma2_rn(o, bc2(wr), e));
+#if B2A_AB_EXACT_BFLY
+    b = __ffma2_rn(make_float2(o.y, o.x), make_float2(wi, -wi), __ffma2_rn(o, bc2(-wr), e));
+#else
     b = __ffma2_rn(e, bc2(2.0f), make_float2(-a.x, -a.y));
+#endif
 }
 // w = s(1 - i):  w*o = s((o.x + o.y), (o.y - o.x))
 __device__ __forceinline__ void bfly_p(float2 e, float2 o, float2& a, float2& b) {
@@ -224,7 +232,14 @@ __device__ __forceinline__ void rfft_split(float2 A, float2 Bz, float2 w, float2
     const float2 E = __fadd2_rn(A, make_float2(Bz.x, -Bz.y));
     const float2 O = __fadd2_rn(make_float2(A.y, -A.x), make_float2(Bz.y, Bz.x));
     xk = __ffma2_rn(make_float2(O.y, O.x), make_float2(-w.y, w.y), __ffma2_rn(O, bc2(w.x), E));   // E + w*O
+#if B2A_AB_EXACT_BFLY
+    {   // conj(E - w*O), each half from its own FMA chain
+        const float2 d = __ffma2_rn(make_float2(O.y, O.x), make_float2(w.y, -w.y), __ffma2_rn(O, bc2(-w.x), E));
+        xnk = make_float2(d.x, -d.y);
+    }
+#else
     xnk = __ffma2_rn(make_float2(E.x, -E.y), bc2(2.0f), make_float2(-xk.x, xk.y));   // conj(E - w*O) = conj(2E - xk)
+#endif
 }
 
 }  // namespace b2a

@@ -34,6 +34,23 @@
 #include "fft_core.cuh"
 #include "gen/mel_special.inc"   // build-time generated straight-line mel code (gen_mel.cpp)
 
+// arithmetic of the generated per-clip DCT (KIND 2): float64 accumulation of the 20 folded terms
+#ifndef B2A_AB_DCT64
+#define B2A_AB_DCT64 0
+#endif
+#ifndef B2A_AB_LOG2F
+#define B2A_AB_LOG2F 0
+#endif
+#if B2A_AB_DCT64
+#define B2A_DCT_T double
+#define B2A_DCT_CVT(x) ((double)(x))
+#define B2A_DCT_FMA(cf, cd, f, a) fma((cd), (f), (a))
+#else
+#define B2A_DCT_T float
+#define B2A_DCT_CVT(x) (x)
+#define B2A_DCT_FMA(cf, cd, f, a) fmaf((cf), (f), (a))
+#endif
+
 #include <cstdint>
 #include <type_traits>
 
@@ -77,9 +94,13 @@ static_assert(B2A_MELSPEC_NMELS * 32 * 4 + (2 * 4 * B2A_DCTSPEC_NMFCC * 32 * 4 +
 
 __device__ __forceinline__ float db10(float s) {
     // 10*log10(max(amin, s)); the argument is >= 1e-10, never denormal -> lg2.approx.ftz
+#if B2A_AB_LOG2F
+    return 3.01029995663981195f * log2f(fmaxf(s, 1e-10f));
+#else
     float l;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(fmaxf(s, 1e-10f)));
     return 3.01029995663981195f * l;
+#endif
 }
 // two packed int16 PCM samples -> two integer-valued floats (the 1/32768 rides on the window).
 // Sign-extend on the ALU (PRMT / SHF) then I2FP.F32.S32: cvt.f32.s16 (I2F.S16) runs on the
@@ -721,27 +742,29 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
                         asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
                     }
                     {
-                        float a[NK0];
+                        B2A_DCT_T a[NK0];
 #pragma unroll
-                        for (int k = 0; k < NK0; ++k) a[k] = 0.f;
+                        for (int k = 0; k < NK0; ++k) a[k] = 0;
                         B2A_DCT_GROUP0(B2A_DCT_LD, a)
 #pragma unroll
                         for (int k = 0; k < NK0; ++k) {
-                            outc[(size_t)B2A_DCT_GROUP0_KOF(k) * nfr + t] = a[k];
-                            const double ad = (double)a[k];
+                            const float af = (float)a[k];
+                            outc[(size_t)B2A_DCT_GROUP0_KOF(k) * nfr + t] = af;
+                            const double ad = (double)af;      // statistics of the stored float32 row (deep.py:326-328)
                             S0[k] += ad;
                             Q0[k] = fma(ad, ad, Q0[k]);
                         }
                     }
                     {
-                        float a[NK1];
+                        B2A_DCT_T a[NK1];
 #pragma unroll
-                        for (int k = 0; k < NK1; ++k) a[k] = 0.f;
+                        for (int k = 0; k < NK1; ++k) a[k] = 0;
                         B2A_DCT_GROUP1(B2A_DCT_LD, a)
 #pragma unroll
                         for (int k = 0; k < NK1; ++k) {
-                            outc[(size_t)B2A_DCT_GROUP1_KOF(k) * nfr + t] = a[k];
-                            const double ad = (double)a[k];
+                            const float af = (float)a[k];
+                            outc[(size_t)B2A_DCT_GROUP1_KOF(k) * nfr + t] = af;
+                            const double ad = (double)af;
                             zq[(2 * k) * kMelThreads] += ad;
                             zq[(2 * k + 1) * kMelThreads] = fma(ad, ad, zq[(2 * k + 1) * kMelThreads]);
                         }

@@ -23,6 +23,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -128,6 +129,7 @@ struct b2a_resampler {
     float* d_out = nullptr;
     size_t cap_in = 0, cap_out = 0;          // bytes
     cudaStream_t stream = nullptr;
+    std::mutex mu;                           // run_host works in the handle's own buffers and stream: one call at a time
 };
 
 namespace {
@@ -279,6 +281,9 @@ int b2a_resampler_run_host(b2a_resampler* r, const void* in, int32_t in_dtype, i
     if (in_dtype != B2A_IN_I16 && in_dtype != B2A_IN_F32) return rs_fail(B2A_EINVAL, "unknown input dtype");
     if (n_in == 0) return B2A_OK;
     if (!in || !out) return rs_fail(B2A_EINVAL, "NULL buffer");
+    // Callers decode files on a thread pool (extractors.py) and share one resampler per (orig, target,
+    // device): serialise here rather than trusting every caller to.
+    std::lock_guard<std::mutex> guard(r->mu);
     RS_TRY(cudaSetDevice(r->device));
     const size_t in_bytes = (size_t)n_in * (in_dtype == B2A_IN_I16 ? 2 : 4);
     const size_t out_bytes = (size_t)b2a_resampler_out_len(r, n_in) * sizeof(float);

@@ -312,6 +312,20 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = world * ne * e2e_steps / float(e2e_s.item())
     checksum = float(pin_out.array[0].sum())
+    # copy-only ceiling: the same call path (b2a_run_host's chunks, streams and device buffers) with the
+    # kernels left out — what the host<->device links of this box give N ranks moving the same bytes
+    eng_h = ext._engine(N_SAMPLES, np.int16, local)
+    for _ in range(2):
+        eng_h.run_host_copy_only(pin_in.array, pin_out.array)
+    fence()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng_h.run_host_copy_only(pin_in.array, pin_out.array)
+    torch.cuda.synchronize()
+    cc_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(cc_s, op=dist.ReduceOp.MAX)
+    copy_ceiling = world * ne * e2e_steps / float(cc_s.item())
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -333,17 +347,27 @@ def run_ours(args):
                          "frac": achieved / peak, "peak_source": peak_src,
                          "bytes_per_clip": BYTES_PER_CLIP, "kernel": kernel_name,
                          "traffic": (traffic["dram_bytes_per_clip"] * n) if (traffic and args.extractor == "mel") else None,
+                         "traffic_source": "static profile (profiles/traffic.json: one ncu --set full capture, scaled per clip); not sampled in this run",
                          "traffic_note": (traffic or {}).get("note") if traffic else "no ncu capture committed yet",
                          "frac_of_nominal_8TBs": achieved / 8000.0},
             "e2e": {"value": e2e_val, "unit": "clips/s", "h2d_bytes_per_step": ne * N_SAMPLES * 2,
                     "d2h_bytes_per_step": ne * N_MELS * N_FRAMES * 4, "clips_per_step": ne,
-                    "steps": e2e_steps, "cpu_cores_bound_to_gpu_numa": numa, "api": f"get('{ext_name}')(...).extract_batch -> b2a_run_host (pinned host buffers)",
+                    "steps": e2e_steps, "cpu_cores_bound_to_gpu_numa": numa,
+                    "copy_ceiling": {"value": copy_ceiling, "unit": "clips/s",
+                                     "what": "b2a_run_host_copy_only: same pinned buffers, chunks and streams, no kernels",
+                                     "h2d_GBps_total": copy_ceiling * N_SAMPLES * 2 / 1e9,
+                                     "d2h_GBps_total": copy_ceiling * N_MELS * N_FRAMES * 4 / 1e9},
+                    "frac_of_copy_ceiling": e2e_val / copy_ceiling, "api": f"get('{ext_name}')(...).extract_batch -> b2a_run_host (pinned host buffers)",
                     "checksum": checksum},
             "gpu_launches": launches,
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu and args.extractor == "mel":
             line["cpu_baseline"] = cpu_baseline_serial(args.cpu_clips)
+        if world == 1 and args.extractor == "mel" and not args.no_extra:
+            del d_in, d_out
+            torch.cuda.empty_cache()
+            line["extra"] = _secondary(torch, dev, local, peak)
         _emit(line)
     pin_in.close()
     pin_out.close()
@@ -352,6 +376,67 @@ def run_ours(args):
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _secondary(torch, dev, local, peak):
+    """Driver-visible secondary numbers (N = 1 only): the other two extractors device-resident at their
+    BASELINE shapes, the reference-default mfcc shape (generic kernel), and config 5 end to end."""
+    import audio_edge_ml_pipeline_b200 as P
+    out = {}
+    stream = torch.cuda.current_stream().cuda_stream
+    jobs = [("mfcc", EXTRA["mfcc"], 50000), ("cqt", EXTRA["cqt"], 16384),
+            ("mfcc_reference_defaults", dict(sr=22050, n=110250, rows=40, hop=512, bytes=110250 * 2 + 40 * 216 * 4,
+                                             name="audio_mfcc_seq", params=dict(duration=5.0),
+                                             workload="audio_mfcc_seq reference defaults 22050/1024/512/128 mels -> 40 (generic kernel)"),
+             20000)]
+    for key, x, n in jobs:
+        try:
+            ext = P.get(x["name"])(**x["params"], devices=[local])
+            eng = ext._engine(x["n"], np.int16, local)
+            g = torch.Generator(device=dev)
+            g.manual_seed(99)
+            d_in = torch.empty((n, x["n"]), dtype=torch.int16, device=dev)
+            for a in range(0, n, 4096):
+                b = min(n, a + 4096)
+                d_in[a:b] = (torch.randn((b - a, x["n"]), generator=g, device=dev) * (0.1 * 32768.0)).round_() \
+                    .clamp_(-32768, 32767).to(torch.int16)
+            d_out = torch.empty((n, eng.rows, eng.frames), dtype=torch.float32, device=dev)
+            for _ in range(3):
+                eng.run_device(d_in.data_ptr(), n, d_out.data_ptr(), stream)
+            torch.cuda.synchronize()
+            sampler = ClockSampler(local)
+            sampler.start()
+            time.sleep(0.25)
+            steps = 5
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0 = time.time()
+            ev0.record()
+            launches = 0
+            for _ in range(steps):
+                eng.run_device(d_in.data_ptr(), n, d_out.data_ptr(), stream)
+                launches += eng.last_launch_count
+            ev1.record()
+            torch.cuda.synchronize()
+            t1 = time.time()
+            ms = ev0.elapsed_time(ev1) / steps
+            val = n / (ms * 1e-3)
+            ach = val * x["bytes"] / 1e9
+            out[key] = {"value": val, "unit": "clips/s", "ms_per_step": ms, "clips_per_step": n, "steps": steps,
+                        "workload": x["workload"], "gpu_launches": launches,
+                        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                     "bytes_per_clip": x["bytes"]},
+                        "clocks": sampler.stop(t0, t1)}
+            del d_in, d_out
+            ext.close()
+            torch.cuda.empty_cache()
+        except Exception as exc:  # noqa: BLE001 — a secondary number must not take the headline line down
+            out[key] = {"error": repr(exc)}
+    try:
+        import bench_stage2
+        out["config5"] = bench_stage2.run(devices=str(local), repeat=2)
+    except Exception as exc:  # noqa: BLE001
+        out["config5"] = {"error": repr(exc)}
+    return out
 
 
 _REAL_STDOUT = None
@@ -376,6 +461,7 @@ def main():
     ap.add_argument("--e2e-clips", type=int, default=16384, help="clips per end-to-end step (host buffers)")
     ap.add_argument("--cpu-clips", type=int, default=6000, help="clips in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary workloads (mfcc, cqt, config 5) at N=1")
     ap.add_argument("--extractor", default="mel", choices=["mel", "mfcc", "cqt"],
                     help="mel = the headline metric; mfcc / cqt = BASELINE configs 2 / 3 at scale")
     args = ap.parse_args()

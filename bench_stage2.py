@@ -23,15 +23,9 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--classes", type=int, default=27)
-    ap.add_argument("--per-class", type=int, default=260)
-    ap.add_argument("--devices", default="all")
-    ap.add_argument("--dir", default="/dev/shm/b2a_stage2")
-    ap.add_argument("--repeat", type=int, default=3)
-    args = ap.parse_args()
-
+def run(classes: int = 27, per_class: int = 260, devices: str = "all", dir: str = "/dev/shm/b2a_stage2",
+        repeat: int = 3) -> dict:
+    args = argparse.Namespace(classes=classes, per_class=per_class, devices=devices, dir=dir, repeat=repeat)
     import audio_edge_ml_pipeline_b200 as P
     from audio_edge_ml_pipeline_b200 import _lib as B
     from audio_edge_ml_pipeline_b200 import synth, wavio
@@ -77,9 +71,20 @@ def main():
         "dataset": f"{args.classes} classes x {args.per_class} PCM16 5 s 16 kHz WAVs on {root}",
         "dataset_write_s": gen_s, "device_count_visible": B.device_count(),
     }
-    print(json.dumps(line), flush=True)
     ext.close()
     shutil.rmtree(root, ignore_errors=True)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--classes", type=int, default=27)
+    ap.add_argument("--per-class", type=int, default=260)
+    ap.add_argument("--devices", default="all")
+    ap.add_argument("--dir", default="/dev/shm/b2a_stage2")
+    ap.add_argument("--repeat", type=int, default=3)
+    a = ap.parse_args()
+    print(json.dumps(run(a.classes, a.per_class, a.devices, a.dir, a.repeat)), flush=True)
 
 
 if __name__ == "__main__":

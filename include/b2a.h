@@ -101,6 +101,11 @@ int b2a_run_device(b2a_handle* h, const void* d_clips, int64_t n_clips, float* d
  * overlaps H2D / kernels / D2H on its own streams and returns when `out` is complete. */
 int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out);
 
+/* Diagnostic twin of b2a_run_host: the same chunked H2D / D2H schedule on the same streams and device
+ * buffers with the kernels left out (`out` receives unspecified data).  Its duration is the transfer
+ * ceiling of the host path on this machine; bench.py reports the end-to-end rate against it. */
+int b2a_run_host_copy_only(b2a_handle* h, const void* clips, int64_t n_clips, float* out);
+
 /* Ragged batches (`duration=None` in the reference: every clip keeps its own length and frame
  * count; deep.py:122-124 is skipped).  mel and mfcc handles only.  Clip i has lengths[i] samples,
  * n_fft <= lengths[i] <= cfg.n_samples (the handle's n_samples is the MAXIMUM length), stored at
@@ -138,7 +143,9 @@ int b2a_decode_wav_pcm16_batch(const char* const* paths, int64_t n_files, int32_
  * 125 dB: the CQT decimator's specification), zero-extended edges, output length
  * ceil(n_in * target / orig) as librosa.resample fixes it, float32 out (int16 input is scaled by
  * 1/32768 like librosa.load).  One signal per call; `in_dtype` is B2A_IN_I16 or B2A_IN_F32.
- * A resampler belongs to one (device, orig, target) and one thread at a time; no CPU path.
+ * A resampler belongs to one (device, orig, target); b2a_resampler_run_host may be called from several
+ * threads (calls on one handle are serialised inside the library), run_device is the caller's to order;
+ * no CPU path.
  * b2a_resampler_geometry exposes up/down (target/orig in lowest terms), the prototype's half
  * length and the polyphase table [up][taps_per_phase] for verification. */
 typedef struct b2a_resampler b2a_resampler;

@@ -15,6 +15,10 @@ SRC = r'''
 #include <cmath>
 #include <cstdio>
 #include "gen/mel_special.inc"
+// the arithmetic is the includer's choice (logmel512.cu): float32 FMAs here, as in the product build
+#define B2A_DCT_T float
+#define B2A_DCT_CVT(x) (x)
+#define B2A_DCT_FMA(cf, cd, f, a) std::fmaf((cf), (f), (a))
 int main() {
     float v[B2A_MELSPEC_NMELS];
     for (int m = 0; m < B2A_MELSPEC_NMELS; ++m) if (std::scanf("%f", &v[m]) != 1) return 2;

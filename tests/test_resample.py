@@ -155,3 +155,21 @@ def test_gpu_mixed_rate_dataset_goes_through_the_resampler(tmp_path):
             y = L.resample_restated(y, sr, 16000)
         ref = L.audio_mel_spec(y, 16000, 40, 512, 160, 1.0)
         assert np.abs(row - ref).max() <= 1e-4, (meta["filename"], float(np.abs(row - ref).max()))
+
+
+@pytest.mark.gpu
+def test_shared_resampler_is_safe_from_many_threads():
+    """extract_dataset decodes on a thread pool and every worker whose file is at another rate goes
+    through the process-wide resampler of that (orig, target, device): concurrent run_host calls on one
+    handle must each return what a serial call returns (the library serialises them)."""
+    from concurrent.futures import ThreadPoolExecutor
+    rng = np.random.default_rng(11)
+    clips = [np.clip(np.round(0.3 * rng.standard_normal(20000 + 3001 * k) * 32768), -32768, 32767).astype(np.int16)
+             for k in range(12)]
+    serial = [B.resample(c, 44100, 16000) for c in clips]
+    for _ in range(3):
+        with ThreadPoolExecutor(max_workers=12) as pool:
+            got = list(pool.map(lambda c: B.resample(c, 44100, 16000), clips))
+        for g, s in zip(got, serial):
+            assert g.shape == s.shape and np.array_equal(g, s)
+    assert len([k for k in B._resamplers if k[:2] == (44100, 16000)]) == 1
