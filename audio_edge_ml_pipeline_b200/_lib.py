@@ -27,9 +27,10 @@ TABLE_WINDOW, TABLE_MEL_DENSE, TABLE_DCT, TABLE_DECIM_TAPS, TABLE_CQT_LENGTHS, T
 EXPORTED_SYMBOLS = [
     "b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
     "b2a_run_host", "b2a_run_host_copy_only", "b2a_run_host_ragged", "b2a_run_device_ragged", "b2a_last_launch_count", "b2a_alloc_pinned", "b2a_free_pinned",
-    "b2a_decode_wav_pcm16_batch", "b2a_get_table", "b2a_cqt_geometry", "b2a_last_error", "b2a_abi_version", "b2a_device_count",
+    "b2a_decode_wav_pcm16_batch", "b2a_probe_wav_batch", "b2a_decode_wav_batch", "b2a_get_table", "b2a_cqt_geometry", "b2a_last_error", "b2a_abi_version", "b2a_device_count",
     "b2a_resampler_create", "b2a_resampler_destroy", "b2a_resampler_out_len", "b2a_resampler_geometry",
     "b2a_resampler_design", "b2a_resampler_run_host", "b2a_resampler_run_device", "b2a_resampler_last_error",
+    "b2a_resampler_run_device_batch", "b2a_resampler_rates", "b2a_run_host_resampled",
 ]
 
 
@@ -75,6 +76,16 @@ def load_library() -> C.CDLL:
     lib.b2a_run_device_ragged.argtypes = [vp, vp, vp, vp, vp, i64, vp, vp]
     lib.b2a_decode_wav_pcm16_batch.argtypes = [vp, i64, i32, vp, vp, i32, vp, vp, i32]
     lib.b2a_decode_wav_pcm16_batch.restype = C.c_int
+    lib.b2a_probe_wav_batch.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp, i32]
+    lib.b2a_probe_wav_batch.restype = C.c_int
+    lib.b2a_decode_wav_batch.argtypes = [vp, i64, vp, vp, i64, i32, vp, i64, vp, vp, vp, i32]
+    lib.b2a_decode_wav_batch.restype = C.c_int
+    lib.b2a_resampler_run_device_batch.argtypes = [vp, vp, i32, i64, i64, vp, vp, i64, i64, vp]
+    lib.b2a_resampler_run_device_batch.restype = C.c_int
+    lib.b2a_resampler_rates.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+    lib.b2a_resampler_rates.restype = C.c_int
+    lib.b2a_run_host_resampled.argtypes = [vp, vp, vp, i32, i64, vp, i64, vp]
+    lib.b2a_run_host_resampled.restype = C.c_int
     lib.b2a_last_launch_count.argtypes = [vp]
     lib.b2a_last_launch_count.restype = i64
     lib.b2a_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(vp)]
@@ -138,6 +149,47 @@ def decode_wav_pcm16_batch(paths, sample_rate: int, n_samples: int, out: np.ndar
                                           None if dur is None else dur.ctypes.data,
                                           int(n_samples), out.ctypes.data, status.ctypes.data, int(n_threads)))
     return status
+
+
+def _path_array(paths):
+    n = len(paths)
+    return (C.c_char_p * n)(*[str(p).encode() for p in paths])
+
+
+def probe_wav_batch(paths, n_threads: int = 0) -> dict:
+    """Header probe of many RIFF/WAVE files (native, threaded): arrays rate / channels / bits / format_tag /
+    n_frames / status (B2A_DEC_*; non-WAV files report DEC_EFORMAT)."""
+    lib = load_library()
+    n = len(paths)
+    out = {k: np.zeros(n, dtype=np.int32) for k in ("rate", "channels", "bits", "format_tag", "status")}
+    out["n_frames"] = np.zeros(n, dtype=np.int64)
+    if n:
+        _check(lib.b2a_probe_wav_batch(C.cast(_path_array(paths), C.c_void_p), n, out["rate"].ctypes.data,
+                                       out["channels"].ctypes.data, out["bits"].ctypes.data,
+                                       out["format_tag"].ctypes.data, out["n_frames"].ctypes.data,
+                                       out["status"].ctypes.data, int(n_threads)))
+    return out
+
+
+def decode_wav_batch(paths, max_frames: int, out: np.ndarray, offsets=None, durations=None, n_threads: int = 0):
+    """Native threaded decode of RIFF/WAVE files AT THEIR OWN RATE into ``out[:len(paths), :max_frames]``
+    (int16: mono PCM16 only; float32: every supported PCM / float format, channel mean).  Rows are zero-filled
+    past the decoded frames.  Returns (rate, n_out, status) arrays."""
+    lib = load_library()
+    n = len(paths)
+    rate, n_out, status = (np.zeros(n, dtype=np.int32) for _ in range(3))
+    if n == 0:
+        return rate, n_out, status
+    assert out.dtype in (np.int16, np.float32) and out.ndim == 2 and out.strides[1] == out.itemsize
+    assert out.shape[0] >= n and out.shape[1] >= max_frames
+    off = None if offsets is None else np.ascontiguousarray(offsets, dtype=np.float64)
+    dur = None if durations is None else np.ascontiguousarray(durations, dtype=np.float64)
+    _check(lib.b2a_decode_wav_batch(C.cast(_path_array(paths), C.c_void_p), n,
+                                    None if off is None else off.ctypes.data, None if dur is None else dur.ctypes.data,
+                                    int(max_frames), IN_I16 if out.dtype == np.int16 else IN_F32, out.ctypes.data,
+                                    out.strides[0] // out.itemsize, rate.ctypes.data, n_out.ctypes.data,
+                                    status.ctypes.data, int(n_threads)))
+    return rate, n_out, status
 
 
 class PinnedArray:
@@ -211,6 +263,29 @@ class Engine:
         elif out.shape != (n, self.rows, self.frames) or out.dtype != np.float32 or not out.flags.c_contiguous:
             raise ValueError("out must be C-contiguous float32 (N, rows, frames)")
         _check(self._lib.b2a_run_host(self._h, clips.ctypes.data, n, out.ctypes.data))
+        return out
+
+    def run_host_resampled(self, resampler: "Resampler", clips: np.ndarray, lengths: np.ndarray,
+                           out: Optional[np.ndarray] = None) -> np.ndarray:
+        """Clips at the files' rate, (N, in_stride) int16/float32 with ``lengths[i]`` valid samples each ->
+        resampled on the device to this engine's rate, padded / trimmed to its n_samples, extracted:
+        (N, rows, frames) float32.  The engine must take float32 input."""
+        clips = np.ascontiguousarray(clips)
+        if clips.dtype != np.int16:
+            clips = clips.astype(np.float32, copy=False)
+        if clips.ndim != 2:
+            raise ValueError("clips must be (N, in_stride)")
+        n = clips.shape[0]
+        lengths = np.ascontiguousarray(lengths, dtype=np.int32)
+        if lengths.shape != (n,):
+            raise ValueError("lengths must be (N,)")
+        if out is None:
+            out = np.empty((n, self.rows, self.frames), dtype=np.float32)
+        elif out.shape != (n, self.rows, self.frames) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be C-contiguous float32 (N, rows, frames)")
+        _check(self._lib.b2a_run_host_resampled(self._h, resampler._h, clips.ctypes.data,
+                                                IN_I16 if clips.dtype == np.int16 else IN_F32, clips.shape[1],
+                                                lengths.ctypes.data, n, out.ctypes.data))
         return out
 
     def run_host_copy_only(self, clips: np.ndarray, out: np.ndarray) -> None:

@@ -100,6 +100,10 @@ struct b2a_handle {
     cudaStream_t rag_stream = nullptr;
     void* rag_in = nullptr; float* rag_out = nullptr; void* rag_meta = nullptr;
     size_t rag_in_cap = 0, rag_out_cap = 0, rag_meta_cap = 0;
+    // run_host_resampled resources: raw clips at the files' rate + their lengths, one set per stream
+    void* rs_raw[2] = {nullptr, nullptr};
+    int* rs_len[2] = {nullptr, nullptr};
+    size_t rs_raw_cap[2] = {0, 0};
 };
 
 extern "C" {
@@ -142,6 +146,7 @@ int b2a_destroy(b2a_handle* h) {
     }
     if (h->rag_stream) { cudaStreamSynchronize(h->rag_stream); cudaStreamDestroy(h->rag_stream); }
     cudaFree(h->rag_in); cudaFree(h->rag_out); cudaFree(h->rag_meta);
+    for (int i = 0; i < 2; ++i) { cudaFree(h->rs_raw[i]); cudaFree(h->rs_len[i]); }
     cudaFree(h->d_window); cudaFree(h->d_tw); cudaFree(h->d_tw2);
     cudaFree(h->d_k0); cudaFree(h->d_cnt); cudaFree(h->d_off); cudaFree(h->d_w);
     cudaFree(h->d_wq); cudaFree(h->d_k0e); cudaFree(h->d_cnt4); cudaFree(h->d_off4); cudaFree(h->d_order);
@@ -433,6 +438,80 @@ static int run_host_impl(b2a_handle* h, const void* clips, int64_t n_clips, floa
     const cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
     const cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
     if (rc != B2A_OK) return rc;                     // run_device_impl already set the message
+    if (ce != cudaSuccess)
+        return fail(ce == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA, std::string(what) + ": " + cudaGetErrorString(ce));
+    CU_TRY(e0);
+    CU_TRY(e1);
+    return B2A_OK;
+}
+
+// Files recorded at another rate (deep.py:44-50: librosa.load resamples, then deep.py:52-61 pads / trims):
+// raw clips at the file rate -> H2D -> batched resampler writing [chunk][n_samples] float32 rows (trimmed or
+// zero-padded to the handle's n_samples) -> the extractor's kernels -> D2H, chunked over the two streams
+// exactly like b2a_run_host.  The intermediate rows live in the handle's own input buffers.
+int b2a_run_host_resampled(b2a_handle* h, b2a_resampler* r, const void* clips, int32_t in_dtype, int64_t in_stride,
+                           const int32_t* in_len, int64_t n_clips, float* out) {
+    if (!h || !r) return fail(B2A_EINVAL, "handle/resampler is NULL");
+    if (h->cfg.input_dtype != B2A_IN_F32) return fail(B2A_EINVAL, "run_host_resampled needs a float32-input handle (the resampler's output type)");
+    if (in_dtype != B2A_IN_I16 && in_dtype != B2A_IN_F32) return fail(B2A_EINVAL, "in_dtype");
+    if (n_clips < 0 || in_stride <= 0) return fail(B2A_EINVAL, "bad batch geometry");
+    int32_t orig = 0, target = 0, rdev = 0;
+    b2a_resampler_rates(r, &orig, &target, &rdev);
+    if (target != h->cfg.sample_rate || rdev != h->device)
+        return fail(B2A_EINVAL, "resampler target rate / device do not match the handle");
+    if (n_clips == 0) { h->last_launches = 0; return B2A_OK; }
+    if (!clips || !in_len || !out) return fail(B2A_EINVAL, "NULL buffer");
+    for (int64_t i = 0; i < n_clips; ++i)
+        if (in_len[i] < 0 || in_len[i] > in_stride) return fail(B2A_EINVAL, "in_len outside [0, in_stride]");
+    CU_TRY(cudaSetDevice(h->device));
+    const size_t mid_clip = (size_t)h->cfg.n_samples * sizeof(float);
+    const size_t out_clip = (size_t)h->rows * h->frames * sizeof(float);
+    const size_t raw_elem = in_dtype == B2A_IN_I16 ? 2 : 4;
+    if (!h->host_ready) {
+        const int irc = host_init(h, mid_clip, out_clip);
+        if (irc != B2A_OK) return irc;
+    }
+    // raw chunks of <= 128 MiB: not more clips than the intermediate buffers hold
+    int64_t cc = std::max<int64_t>(1, (int64_t)((128u << 20) / ((size_t)in_stride * raw_elem)));
+    cc = std::min<int64_t>(cc, h->chunk_clips);
+    for (int i = 0; i < 2; ++i) {
+        const size_t need = (size_t)cc * in_stride * raw_elem;
+        if (need > h->rs_raw_cap[i]) {
+            cudaFree(h->rs_raw[i]); h->rs_raw[i] = nullptr; h->rs_raw_cap[i] = 0;
+            CU_TRY(cudaMalloc(&h->rs_raw[i], need));
+            h->rs_raw_cap[i] = need;
+        }
+        if (!h->rs_len[i]) CU_TRY(cudaMalloc((void**)&h->rs_len[i], (size_t)h->chunk_clips * sizeof(int)));
+    }
+    h->last_launches = 0;
+    int rc = B2A_OK;
+    cudaError_t ce = cudaSuccess;
+    const char* what = "";
+#define CU_STEP(expr) { ce = (expr); if (ce != cudaSuccess) { what = #expr; break; } }
+    int64_t done = 0;
+    for (int c = 0; done < n_clips; ++c) {
+        const int s = c & 1;
+        const int64_t nb = std::min<int64_t>(cc, n_clips - done);
+        const unsigned char* src = (const unsigned char*)clips + (size_t)done * in_stride * raw_elem;
+        float* dst = (float*)((unsigned char*)out + (size_t)done * out_clip);
+        CU_STEP(cudaMemcpyAsync(h->rs_raw[s], src, (size_t)nb * in_stride * raw_elem, cudaMemcpyHostToDevice, h->streams[s]));
+        CU_STEP(cudaMemcpyAsync(h->rs_len[s], in_len + done, (size_t)nb * sizeof(int), cudaMemcpyHostToDevice, h->streams[s]));
+        rc = b2a_resampler_run_device_batch(r, h->rs_raw[s], in_dtype, nb, in_stride, h->rs_len[s], (float*)h->d_in[s],
+                                            h->cfg.n_samples, h->cfg.n_samples, h->streams[s]);
+        if (rc != B2A_OK) break;
+        h->last_launches += 1;
+        const bool shared_scratch = h->cfg.kind != B2A_KIND_MEL;
+        if (shared_scratch && c > 0) CU_STEP(cudaStreamWaitEvent(h->streams[s], h->ev_kernels[s ^ 1], 0));
+        rc = run_device_impl(h, h->d_in[s], nb, h->d_out[s], h->streams[s], &h->last_launches);
+        if (rc != B2A_OK) break;
+        if (shared_scratch) CU_STEP(cudaEventRecord(h->ev_kernels[s], h->streams[s]));
+        CU_STEP(cudaMemcpyAsync(dst, h->d_out[s], out_clip * nb, cudaMemcpyDeviceToHost, h->streams[s]));
+        done += nb;
+    }
+#undef CU_STEP
+    const cudaError_t e0 = cudaStreamSynchronize(h->streams[0]);
+    const cudaError_t e1 = cudaStreamSynchronize(h->streams[1]);
+    if (rc != B2A_OK) return rc;
     if (ce != cudaSuccess)
         return fail(ce == cudaErrorMemoryAllocation ? B2A_ENOMEM : B2A_ECUDA, std::string(what) + ": " + cudaGetErrorString(ce));
     CU_TRY(e0);

@@ -6,9 +6,16 @@
 // y_{o+1} = sqrt(2) * decimate2(y_o).  The decimator is this project's stand-in for soxr_hq
 // (tables.h: decimator_taps; DESIGN.md "CQT decimator").
 //
-// The basis product is a 12 x 129 complex matrix with ~147 non-zeros against [129 x frames]: as a
-// dense GEMM it would be 10x the flops of the banded form and needs fp32-grade accuracy 80 dB
-// below the peak, so it runs on the CUDA cores as a banded complex dot product, not on tcgen05.
+// The octave response is evaluated in the TIME domain: basis_o . STFT(y_o) == sum_n y_o[t hop + n - N/2] b_o[r][n]
+// with b_o[r][n] = sum_k basis_o[r][k] exp(-2 pi i k n / N) built on the host in double precision from the
+// same sparsified complex64 basis librosa multiplies with — a dense [frames x N] . [N x 12 complex]
+// product per octave (cqt_bank_kernel).  The frequency-domain form needs every rectangular-window STFT bin
+// accurate relative to ITSELF (librosa's FFT runs in float64): the wavelet spectrum then cancels a strong
+// tone's leakage across ~12 bins, and a float32 FFT, whose error is relative to the frame's PEAK bin, left
+// 2e-4 in the normalised features (rows of the un-decimated top octave, profiles/r2_cqt_floor.jsonl).  In
+// the time domain the partial sums of an out-of-band tone stay small, so float32 accumulation holds
+// 4e-5.  9.3 M real MACs per clip as packed FFMA2: CUDA cores, not tcgen05 (operands
+// would need 3-way TF32 splits and an im2col of 32x-overlapping frames in the UMMA layout).
 #include "cqt.h"
 #include "fft_core.cuh"
 #include "gen/decim_taps.inc"   // build-time generated decimator taps (gen_mel.cpp decim)
@@ -207,206 +214,158 @@ __global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
-// One octave: rectangular-window STFT (centre zero-pad) -> banded complex basis -> |.|/sqrt(len)
+// All octaves of a chunk in one launch: time-domain wavelet bank.
+//   grid = (frame blocks of 256, octaves * row blocks of 12, clips), 128 threads.
+//   Per 64-sample slice of the N-sample kernels the CTA stages an im2col tile [64 n][256 frames] of the
+//   octave's signal (16-byte chunks XOR-swizzled by row: the transposing stores spread over the banks,
+//   the float4 reads stay conflict-free) and the slice's coefficients [64 n][12 rows] (re, im); a thread
+//   owns 4 consecutive frames x 6 rows: per n one 128-bit sample load, three 128-bit broadcast coefficient
+//   loads and 24 packed FFMA2 (acc(re, im) += x * (b_re, b_im)).
 // ------------------------------------------------------------------------------------------
-struct OctParams {
-    const void* in; size_t in_stride; int in_len;
-    int hop, n_frames, n_rows, row0, nnz;
-    const float2* tw; const float2* tw2;
-    const float2* basis; const int* k0; const int* cnt; const int* off;
+constexpr int kBankThreads = 128;
+constexpr int kBankFrames = 256;             // frames per CTA: 2 warps x 32 lanes x 4
+constexpr int kBankRows = 12;                // output rows (bins) per CTA: 2 thread groups x 6
+constexpr int kBankSlice = 64;               // kernel samples per staged slice
+constexpr size_t kBankSmem = (size_t)kBankSlice * kBankFrames * 4 + (size_t)kBankSlice * kBankRows * 8 + 64 * 4;
+
+struct BankOct {
+    const void* in; long long in_stride; int in_len; int in_i16;     // this octave's signal, per clip
+    int hop, n_fft, n_rows, row0;
+    const float2* coef;                       // [ceil(n_rows / 12)][n_fft][12] (re, im), zero-padded rows
+};
+struct BankParams {
+    BankOct oct[12];
+    int n_oct, n_frames;
     const float* inv_sqrt_len;
-    float* out; size_t out_stride;            // out[clip*out_stride + row*n_frames + t]
+    float* out; long long out_stride;         // out[clip * out_stride + row * n_frames + t]
     unsigned int* clip_max; unsigned int* clip_min;
 };
 
-template <int LOG2NC> struct OctCfg {
-    using G = FftGeom<LOG2NC>;
-    static constexpr int F = (LOG2NC <= 8) ? 32 : 16;
-    static constexpr int FR = kThreads / G::T;
-    static constexpr int ROUNDS = F / FR;
-    static constexpr int SSTRIDE = G::NC + 1;        // float2 per frame in the spectrum tile
-};
+__global__ void __launch_bounds__(kBankThreads, 3) cqt_bank_kernel(const __grid_constant__ BankParams p) {
+    extern __shared__ __align__(16) unsigned char bank_smem[];
+    float* const s_tile = reinterpret_cast<float*>(bank_smem);                                   // [64][256] swizzled
+    float2* const s_coef = reinterpret_cast<float2*>(bank_smem + (size_t)kBankSlice * kBankFrames * 4);   // [64][12]
+    float* const s_red = reinterpret_cast<float*>(s_coef + kBankSlice * kBankRows);
 
-static size_t oct_smem_bytes(int log2nc, int hop, int n_rows, int nnz) {
-    const int NC = 1 << log2nc, n_fft = 2 * NC, T = NC / 16;
-    const int F = (log2nc <= 8) ? 32 : 16, FR = kThreads / T;
-    const size_t fstride = hop >= n_fft ? (size_t)n_fft : (size_t)hop;
-    size_t cl = fstride * (F - 1) + n_fft;
-    cl = (cl + 7) & ~(size_t)7;
-    size_t b = cl * 4 + (size_t)FR * (NC + NC / 16) * 8 + (size_t)F * (NC + 1) * 8;
-    b = (b + 15) & ~(size_t)15;
-    const int R1 = log2nc >= 8 ? 16 : (1 << (log2nc - 4));
-    b += (size_t)NC * 8 + (size_t)(NC / 2 + 1) * 8 + (size_t)(16 / R1) * (R1 - 1) * T * 8 + (size_t)nnz * 8 + (size_t)n_rows * 12 + 128 * 4;
-    return b + 64;
-}
-
-template <int LOG2NC, bool I16>
-__global__ void __launch_bounds__(kThreads) cqt_octave_kernel(OctParams p) {
-    using G = FftGeom<LOG2NC>;
-    using C = OctCfg<LOG2NC>;
-    constexpr int NC = G::NC, NFFT = G::NFFT, T = G::T, F = C::F, FR = C::FR;
-
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const bool per_frame = p.hop >= NFFT;               // frames do not overlap: stage frame by frame
-    const int fstride = per_frame ? NFFT : p.hop;
-    const int cl = (fstride * (F - 1) + NFFT + 7) & ~7;
-    float* s_audio = reinterpret_cast<float*>(smem_raw);
-    float2* s_xch = reinterpret_cast<float2*>(s_audio + cl);
-    float2* s_spec = s_xch + FR * G::XSTRIDE;
-    const int off_tw = ((cl * 4 + FR * G::XSTRIDE * 8 + F * C::SSTRIDE * 8) + 15) & ~15;   // no integer round trip
-    float2* s_tw = reinterpret_cast<float2*>(smem_raw + off_tw);
-    float2* s_tw2 = s_tw + NC;
-    float2* s_twp = s_tw2 + NC / 2 + 1;
-    float2* s_basis = s_twp + FftTwp<LOG2NC>::SIZE;
-    int* s_k0 = reinterpret_cast<int*>(s_basis + p.nnz);
-    int* s_cnt = s_k0 + p.n_rows;
-    int* s_off = s_cnt + p.n_rows;
-    float* s_red = reinterpret_cast<float*>(s_off + p.n_rows);
-
+    // which (octave, row block) this CTA serves
+    int oi = 0, rb = (int)blockIdx.y;
+    for (;;) {
+        const int nb = (p.oct[oi].n_rows + kBankRows - 1) / kBankRows;
+        if (rb < nb) break;
+        rb -= nb; ++oi;
+    }
+    const BankOct& o = p.oct[oi];
+    const int N = o.n_fft, hop = o.hop, L = o.in_len;
+    const size_t clip = blockIdx.z;
+    const int t0 = blockIdx.x * kBankFrames;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < NC; i += kThreads) s_tw[i] = p.tw[i];
-    for (int i = tid; i < NC / 2 + 1; i += kThreads) s_tw2[i] = p.tw2[i];
-    FftTwp<LOG2NC>::fill(s_twp, p.tw, tid, kThreads);
-    for (int i = tid; i < p.nnz; i += kThreads) s_basis[i] = p.basis[i];
-    for (int i = tid; i < p.n_rows; i += kThreads) { s_k0[i] = p.k0[i]; s_cnt[i] = p.cnt[i]; s_off[i] = p.off[i]; }
+    const int fgrp = warp >> 1;                  // which 128 frames of the block
+    const int rgrp = warp & 1;                   // which 6 of the 12 rows
+    const unsigned char* const base = (const unsigned char*)o.in + clip * (size_t)o.in_stride * (o.in_i16 ? 2 : 4);
+    const float2* const coef = o.coef + (size_t)rb * N * kBankRows;
 
-    const size_t clip = blockIdx.y;
-    const int t0 = blockIdx.x * F;
-    const int n = p.in_len;
-    // ---- stage samples (zero outside [0, n)) ---------------------------------------------------
-    // Vector groups (4 floats / 2 int16) with all the loads of a batch issued before the first
-    // conversion: one DRAM round trip per batch of eight instead of one per sample (this loop, not
-    // the FFT, set the octave kernels' time).  Segment starts are multiples of 8 samples, so a group
-    // is either inside [0, n) and aligned, or it takes the scalar edge path.
-    {
-        using VecT = typename std::conditional<I16, uint32_t, float4>::type;
-        constexpr int V = I16 ? 2 : 4;
-        constexpr int kBatch = 8;
-        const int seg_len = per_frame ? NFFT : cl;                 // samples per contiguous segment
-        const int gps = seg_len / V;                               // groups per segment
-        const int total = (per_frame ? F : 1) * gps;
-        const unsigned char* base = (const unsigned char*)p.in + (clip * p.in_stride) * (I16 ? 2 : 4);
-        const bool vec_ok = (reinterpret_cast<uintptr_t>(base) & (sizeof(VecT) - 1)) == 0;
-        const int c0 = t0 * p.hop - NFFT / 2;
-#pragma unroll 1
-        for (int g0 = tid; g0 < total; g0 += kBatch * kThreads) {
-            VecT raw[kBatch];
-            int src[kBatch], state[kBatch];                        // 0: past the end, 1: vector load, 2: edge / unaligned
+    float2 acc[4][6];
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int g = g0 + u * kThreads;
-                const int f = per_frame ? g / (NFFT / V) : 0;
-                const int o = (per_frame ? g % (NFFT / V) : g) * V;
-                src[u] = c0 + f * p.hop + o;
-                const bool al = vec_ok && ((src[u] * (I16 ? 2 : 4)) & (int)(sizeof(VecT) - 1)) == 0;   // odd hops
-                state[u] = g < total ? ((al && src[u] >= 0 && src[u] + V <= n) ? 1 : 2) : 0;
-                if (state[u] == 1) raw[u] = __ldg(reinterpret_cast<const VecT*>(base + (size_t)src[u] * (I16 ? 2 : 4)));
-            }
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                if (state[u] == 0) continue;
-                const int g = g0 + u * kThreads;
-                float* dst = s_audio + g * V;                      // per_frame: f * NFFT + o == g * V as well
-                float v[V];
-                if (state[u] == 1) {
-                    if constexpr (I16) {
-                        const uint32_t w = raw[u];
-                        v[0] = __int2float_rn((int)(short)(w & 0xffffu)) * (1.0f / 32768.0f);
-                        v[1] = __int2float_rn((int)w >> 16) * (1.0f / 32768.0f);
+        for (int b = 0; b < 6; ++b) acc[i][b] = make_float2(0.f, 0.f);
+
+    const int nvalid = min(kBankFrames, p.n_frames - t0);       // frames of this block inside the clip
+    for (int n0 = 0; n0 < N; n0 += kBankSlice) {
+        __syncthreads();                                       // the previous slice has been consumed
+        // ---- stage coefficients of this slice: contiguous copy ------------------------------------------
+        for (int i = tid; i < kBankSlice * kBankRows; i += kBankThreads) s_coef[i] = coef[(size_t)n0 * kBankRows + i];
+        // ---- stage the im2col tile: item = (frame f, 4 consecutive n) -----------------------------------
+        // 16 items per frame; lanes walk n fastest so that global reads are contiguous runs of 64 samples
+        for (int it = tid; it < kBankFrames * (kBankSlice / 4); it += kBankThreads) {
+            const int f = it >> 4, q = it & 15;
+            const int n = 4 * q;
+            if (f >= nvalid) continue;               // frames past the clip: their accumulators are never stored
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            {
+                const int s0 = (t0 + f) * hop + n0 + n - N / 2;        // sample index of (f, n0 + n)
+                if (s0 >= 0 && s0 + 4 <= L) {
+                    if (o.in_i16) {
+                        const int16_t* ps = reinterpret_cast<const int16_t*>(base) + s0;
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = __int2float_rn((int)__ldg(ps + e)) * (1.0f / 32768.0f);
                     } else {
-                        v[0] = raw[u].x; v[1] = raw[u].y; v[2] = raw[u].z; v[3] = raw[u].w;
+                        const float* ps = reinterpret_cast<const float*>(base) + s0;
+                        if ((reinterpret_cast<uintptr_t>(ps) & 15) == 0) {
+                            const float4 x = __ldg(reinterpret_cast<const float4*>(ps));
+                            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) v[e] = __ldg(ps + e);
+                        }
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < V; ++e) {
-                        const int s1 = src[u] + e;
-                        v[e] = 0.f;
-                        if (s1 >= 0 && s1 < n) {
-                            if (I16) v[e] = __int2float_rn((int)((const int16_t*)base)[s1]) * (1.0f / 32768.0f);
-                            else v[e] = ((const float*)base)[s1];
-                        }
+                    for (int e = 0; e < 4; ++e) {
+                        const int s1 = s0 + e;
+                        if (s1 >= 0 && s1 < L)
+                            v[e] = o.in_i16 ? __int2float_rn((int)reinterpret_cast<const int16_t*>(base)[s1]) * (1.0f / 32768.0f)
+                                            : reinterpret_cast<const float*>(base)[s1];
                     }
                 }
-                if constexpr (I16) *reinterpret_cast<float2*>(dst) = make_float2(v[0], v[1]);
-                else *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
             }
+            // element (n, f) lives at row n, 16-byte chunk ((f >> 2) ^ swz(n)), word f & 3
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int r = n + e;
+                const int chunk = (f >> 2) ^ ((r >> 2) & 7);
+                s_tile[r * kBankFrames + chunk * 4 + (f & 3)] = v[e];
+            }
+        }
+        __syncthreads();
+        // ---- 64 steps: 1 sample load (4 frames), 3 coefficient loads (6 rows), 24 FFMA2 --------------------
+        const float4* const tile4 = reinterpret_cast<const float4*>(s_tile);
+        const float4* const c4 = reinterpret_cast<const float4*>(s_coef) + rgrp * 3;
+        const int my_chunk = fgrp * 32 + lane;
+#pragma unroll 4
+        for (int r = 0; r < kBankSlice; ++r) {
+            const int chunk = my_chunk ^ ((r >> 2) & 7);
+            const float4 x = tile4[r * (kBankFrames / 4) + chunk];
+            const float4 ca = c4[r * (kBankRows / 2)], cb = c4[r * (kBankRows / 2) + 1], cc = c4[r * (kBankRows / 2) + 2];
+            const float2 cf[6] = {make_float2(ca.x, ca.y), make_float2(ca.z, ca.w), make_float2(cb.x, cb.y),
+                                  make_float2(cb.z, cb.w), make_float2(cc.x, cc.y), make_float2(cc.z, cc.w)};
+            const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int b = 0; b < 6; ++b) acc[i][b] = __ffma2_rn(make_float2(xs[i], xs[i]), cf[b], acc[i][b]);
         }
     }
-    __syncthreads();
 
-    // ---- packed real FFT per frame -> spectrum tile -------------------------------------------
-    const int j = tid % T, slot = tid / T;
-    const bool even = (fstride & 1) == 0;
-#pragma unroll 1
-    for (int r = 0; r < C::ROUNDS; ++r) {
-        const int f = r * FR + slot;
-        float2* xb = s_xch + slot * G::XSTRIDE;
-        {
-            float2 v[16];
-            const float* a = s_audio + f * fstride + 2 * j;
-            if (even) {
-#pragma unroll
-                for (int t = 0; t < 16; ++t) v[t] = *reinterpret_cast<const float2*>(a + 2 * T * t);
-            } else {
-#pragma unroll
-                for (int t = 0; t < 16; ++t) v[t] = make_float2(a[2 * T * t], a[2 * T * t + 1]);
-            }
-            Dft<16>::run(v);
-#pragma unroll
-            for (int t = 0; t < 16; ++t) xb[xpad(16 * j + t)] = v[t];
-        }
-        frame_sync<T>();
-        fft_tail_passes<LOG2NC, false>(xb, s_tw, nullptr, s_twp, j);
-        {
-            float2* sp = s_spec + f * C::SSTRIDE;
-#pragma unroll
-            for (int r2 = 0; r2 < 8; ++r2) {
-                const int k = j + T * r2;
-                float2 xk, xnk;
-                rfft_split(xb[xpad(k)], xb[xpad((NC - k) & (NC - 1))], s_tw2[k], xk, xnk);
-                sp[k] = make_float2(0.5f * xk.x, 0.5f * xk.y);
-                sp[NC - k] = make_float2(0.5f * xnk.x, 0.5f * xnk.y);
-            }
-            if (j == 0) {
-                const float2 A = xb[xpad(NC / 2)];
-                sp[NC / 2] = make_float2(A.x, -A.y);
-            }
-        }
-        frame_sync<T>();
-    }
-    __syncthreads();
-
-    // ---- banded complex basis product: item = (row, frame), frame fastest ---------------------
+    // ---- |.| / sqrt(length), per-clip extrema --------------------------------------------------------
     float vmax = 0.f, vmin = 3.0e38f;
-    for (int i = tid; i < p.n_rows * F; i += kThreads) {
-        const int b = i / F, f = i % F;
-        const float2* x = s_spec + f * C::SSTRIDE + s_k0[b];
-        const float2* g = s_basis + s_off[b];
-        const int cnt = s_cnt[b];
-        float ar = 0.f, ai = 0.f;
-        for (int qk = 0; qk < cnt; ++qk) {
-            const float2 gg = g[qk], xx = x[qk];
-            ar = fmaf(gg.x, xx.x, ar); ar = fmaf(-gg.y, xx.y, ar);
-            ai = fmaf(gg.x, xx.y, ai); ai = fmaf(gg.y, xx.x, ai);
-        }
-        const int t = t0 + f;
-        if (t < p.n_frames) {
-            const int row = p.row0 + b;
-            const float mag = sqrtf(ar * ar + ai * ai) * p.inv_sqrt_len[row];
-            p.out[clip * p.out_stride + (size_t)row * p.n_frames + t] = mag;
-            vmax = fmaxf(vmax, mag);
-            vmin = fminf(vmin, mag);
+#pragma unroll
+    for (int b = 0; b < 6; ++b) {
+        const int lr = rb * kBankRows + rgrp * 6 + b;             // row inside the octave
+        if (lr >= o.n_rows) continue;
+        const int row = o.row0 + lr;
+        const float sc = p.inv_sqrt_len[row];
+        float* const orow = p.out + clip * (size_t)p.out_stride + (size_t)row * p.n_frames;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + fgrp * 128 + 4 * lane + i;
+            if (t < p.n_frames) {
+                const float mag = sqrtf(acc[i][b].x * acc[i][b].x + acc[i][b].y * acc[i][b].y) * sc;
+                orow[t] = mag;
+                vmax = fmaxf(vmax, mag);
+                vmin = fminf(vmin, mag);
+            }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, sft));
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, sft));
     }
     if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
     __syncthreads();
     if (tid == 0) {
-        for (int w = 1; w < kThreads / 32; ++w) { vmax = fmaxf(vmax, s_red[w]); vmin = fminf(vmin, s_red[32 + w]); }
+        for (int w = 1; w < kBankThreads / 32; ++w) { vmax = fmaxf(vmax, s_red[w]); vmin = fminf(vmin, s_red[32 + w]); }
         atomicMax(p.clip_max + clip, __float_as_uint(vmax));     // magnitudes are >= 0
         atomicMin(p.clip_min + clip, __float_as_uint(vmin));
     }
@@ -435,22 +394,6 @@ __global__ void cqt_init_minmax(unsigned int* mx, unsigned int* mn, int n) {
     if (i < n) { mx[i] = 0u; mn[i] = 0x7f7fffffu; }
 }
 
-template <int LOG2NC>
-cudaError_t launch_oct(const OctParams& p, bool i16, dim3 grid, size_t smem, cudaStream_t st) {
-    if (i16) {
-        auto k = cqt_octave_kernel<LOG2NC, true>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k<<<grid, kThreads, smem, st>>>(p);
-    } else {
-        auto k = cqt_octave_kernel<LOG2NC, false>;
-        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k<<<grid, kThreads, smem, st>>>(p);
-    }
-    return cudaGetLastError();
-}
-
 template <typename T>
 cudaError_t up(const std::vector<T>& v, T** d) {
     *d = nullptr;
@@ -460,7 +403,6 @@ cudaError_t up(const std::vector<T>& v, T** d) {
     return cudaMemcpy(*d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
 }
 
-int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 
 }  // namespace
 
@@ -476,8 +418,7 @@ int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 void cqt_device_free(CqtDevice* d) {
     cudaFree(d->scratch); cudaFree(d->taps); cudaFree(d->inv_sqrt_len);
     cudaFree(d->clip_max); cudaFree(d->clip_min);
-    for (int i = 0; i < 16; ++i) { cudaFree(d->tw[i]); cudaFree(d->tw2[i]); }
-    for (auto& o : d->oct) { cudaFree(o.basis); cudaFree(o.k0); cudaFree(o.cnt); cudaFree(o.off); }
+    for (auto& o : d->oct) cudaFree(o.coef);
     *d = CqtDevice();
 }
 
@@ -504,48 +445,44 @@ int cqt_device_init(const CqtPlan& plan, const b2a_config& cfg, int sm_count, si
         dev->early_lens.push_back(len);
         off += ((size_t)len + 3) & ~(size_t)3;
     }
+    if (plan.n_octaves > 12) { *err = "cqt: more than 12 octaves"; return B2A_EINVAL; }
+    if (kBankSmem > smem_optin) { *err = "cqt: wavelet-bank tile exceeds shared memory"; return B2A_EINVAL; }
+    CQ_TRY(cudaFuncSetAttribute(cqt_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBankSmem));
     dev->oct.resize(plan.n_octaves);
     size_t cur_off = plan.n_early ? dev->early_offs.back() : (size_t)-1;   // (size_t)-1: the input itself
     for (int i = 0; i < plan.n_octaves; ++i) {
         const CqtOctave& o = plan.oct[i];
         CqtOctaveDev& od = dev->oct[i];
         od.sig_off = cur_off;
-        od.log2nc = ilog2(o.n_fft / 2);
-        if (od.log2nc < 7 || od.log2nc > 9) {
-            *err = "cqt: per-octave n_fft " + std::to_string(o.n_fft) + " unsupported (256..1024)";
+        if (o.n_fft % kBankSlice != 0 || o.n_fft < kBankSlice) {
+            *err = "cqt: per-octave n_fft " + std::to_string(o.n_fft) + " unsupported (multiple of 64)";
             return B2A_EINVAL;
         }
-        // band each row of the sparsified basis
-        const int n_bins = o.n_fft / 2 + 1;
-        std::vector<float2> bw;
-        std::vector<int> k0(o.n_rows), cnt(o.n_rows), offv(o.n_rows);
-        for (int r = 0; r < o.n_rows; ++r) {
-            int lo = n_bins, hi = -1;
-            for (int k = 0; k < n_bins; ++k) {
-                const float re = o.basis[((size_t)r * n_bins + k) * 2], im = o.basis[((size_t)r * n_bins + k) * 2 + 1];
-                if (re != 0.f || im != 0.f) { lo = std::min(lo, k); hi = std::max(hi, k); }
+        // time-domain kernels b[r][n] = sum_k basis[r][k] exp(-2 pi i k n / N), k = 0..N/2 (the bins the
+        // reference multiplies with), in double from the float32 basis entries; laid out
+        // [row block of 12][n][12] (re, im) so that a slice of 64 n is one contiguous copy
+        {
+            const int N = o.n_fft, n_bins = N / 2 + 1;
+            const int n_blocks = (o.n_rows + kBankRows - 1) / kBankRows;
+            std::vector<float2> coef((size_t)n_blocks * N * kBankRows, make_float2(0.f, 0.f));
+            std::vector<double> cs(N), sn(N);
+            for (int m = 0; m < N; ++m) { cs[m] = std::cos(2.0 * M_PI * m / N); sn[m] = std::sin(2.0 * M_PI * m / N); }
+            for (int r = 0; r < o.n_rows; ++r) {
+                const float* br = &o.basis[(size_t)(o.filt0 + r) * n_bins * 2];
+                for (int n = 0; n < N; ++n) {
+                    double re = 0.0, im = 0.0;
+                    for (int k = 0; k < n_bins; ++k) {
+                        const double gr = br[2 * k], gi = br[2 * k + 1];
+                        if (gr == 0.0 && gi == 0.0) continue;
+                        const int m = (int)(((long long)k * n) % N);       // exp(-2 pi i k n / N) = cs[m] - i sn[m]
+                        re += gr * cs[m] + gi * sn[m];
+                        im += gi * cs[m] - gr * sn[m];
+                    }
+                    coef[((size_t)(r / kBankRows) * N + n) * kBankRows + (r % kBankRows)] = make_float2((float)re, (float)im);
+                }
             }
-            offv[r] = (int)bw.size();
-            if (hi < 0) { k0[r] = 0; cnt[r] = 0; continue; }
-            k0[r] = lo; cnt[r] = hi - lo + 1;
-            for (int k = lo; k <= hi; ++k)
-                bw.push_back(make_float2(o.basis[((size_t)r * n_bins + k) * 2], o.basis[((size_t)r * n_bins + k) * 2 + 1]));
-        }
-        od.nnz = (int)bw.size();
-        if (bw.empty()) bw.push_back(make_float2(0.f, 0.f));
-        CQ_TRY(up(bw, &od.basis));
-        CQ_TRY(up(k0, &od.k0));
-        CQ_TRY(up(cnt, &od.cnt));
-        CQ_TRY(up(offv, &od.off));
-        if (oct_smem_bytes(od.log2nc, o.hop, o.n_rows, od.nnz) > smem_optin) {
-            *err = "cqt: octave working set exceeds shared memory";
-            return B2A_EINVAL;
-        }
-        if (!dev->tw[od.log2nc]) {
-            const int NC = o.n_fft / 2;
-            std::vector<float> a = twiddles(NC, NC), b = twiddles(2 * NC, NC / 2 + 1);
-            CQ_TRY(up(a, (float**)&dev->tw[od.log2nc]));
-            CQ_TRY(up(b, (float**)&dev->tw2[od.log2nc]));
+            od.n_blocks = n_blocks;
+            CQ_TRY(up(coef, &od.coef));
         }
         if (o.decimate_after && i + 1 < plan.n_octaves) {
             cur_off = off;
@@ -585,31 +522,29 @@ int cqt_run(const CqtPlan& plan, const b2a_config& cfg, CqtDevice* dev, const vo
             return cudaGetLastError();
         };
         for (int e = 0; e < plan.n_early; ++e) CQ_TRY(decimate(dev->early_offs[e], dev->early_lens[e]));
+        // the decimation cascade first (every octave's signal then sits in the chunk's scratch), ...
+        BankParams bp{};
+        int n_rb = 0;
         for (int i = 0; i < plan.n_octaves; ++i) {
             const CqtOctave& o = plan.oct[i];
             const CqtOctaveDev& od = dev->oct[i];
-            OctParams p{};
-            p.in = sig; p.in_stride = sig_stride; p.in_len = sig_len;
-            p.hop = o.hop; p.n_frames = nfr; p.n_rows = o.n_rows; p.row0 = o.row0; p.nnz = od.nnz;
-            p.tw = dev->tw[od.log2nc]; p.tw2 = dev->tw2[od.log2nc];
-            p.basis = od.basis; p.k0 = od.k0; p.cnt = od.cnt; p.off = od.off;
-            p.inv_sqrt_len = dev->inv_sqrt_len;
-            p.out = out; p.out_stride = out_stride;
-            p.clip_max = dev->clip_max; p.clip_min = dev->clip_min;
-            const int F = od.log2nc <= 8 ? 32 : 16;
-            dim3 grid((nfr + F - 1) / F, nb);
-            const size_t smem = oct_smem_bytes(od.log2nc, o.hop, o.n_rows, od.nnz);
-            cudaError_t e = cudaSuccess;
-            switch (od.log2nc) {
-                case 7: e = launch_oct<7>(p, sig_i16, grid, smem, st); break;
-                case 8: e = launch_oct<8>(p, sig_i16, grid, smem, st); break;
-                case 9: e = launch_oct<9>(p, sig_i16, grid, smem, st); break;
-                default: e = cudaErrorInvalidValue;
-            }
-            CQ_TRY(e);
-            ++*launches;
+            BankOct& bo = bp.oct[i];
+            bo.in = sig; bo.in_stride = (long long)sig_stride; bo.in_len = sig_len; bo.in_i16 = sig_i16 ? 1 : 0;
+            bo.hop = o.hop; bo.n_fft = o.n_fft; bo.n_rows = o.n_rows; bo.row0 = o.row0; bo.coef = od.coef;
+            n_rb += od.n_blocks;
             if (o.decimate_after && i + 1 < plan.n_octaves)
                 CQ_TRY(decimate(dev->oct[i + 1].sig_off, (sig_len + 1) / 2));
+        }
+        // ... then every octave's wavelet bank in one launch
+        bp.n_oct = plan.n_octaves; bp.n_frames = nfr;
+        bp.inv_sqrt_len = dev->inv_sqrt_len;
+        bp.out = out; bp.out_stride = (long long)out_stride;
+        bp.clip_max = dev->clip_max; bp.clip_min = dev->clip_min;
+        {
+            const dim3 grid((nfr + kBankFrames - 1) / kBankFrames, n_rb, nb);
+            cqt_bank_kernel<<<grid, kBankThreads, kBankSmem, st>>>(bp);
+            CQ_TRY(cudaGetLastError());
+            ++*launches;
         }
         cqt_finalize_kernel<<<nb, kThreads, 0, st>>>(out, out_stride, rows * nfr, dev->clip_max, dev->clip_min, cfg.top_db);
         CQ_TRY(cudaGetLastError());

@@ -12,12 +12,8 @@
 namespace b2a {
 
 struct CqtOctaveDev {
-    float2* basis = nullptr;   // banded complex rows, concatenated
-    int* k0 = nullptr;         // per row: first kept FFT bin
-    int* cnt = nullptr;        // per row: band length
-    int* off = nullptr;        // per row: offset into basis
-    int nnz = 0;
-    int log2nc = 0;
+    float2* coef = nullptr;    // time-domain wavelets [row block of 12][n_fft][12] (re, im)
+    int n_blocks = 0;          // row blocks of 12
     size_t sig_off = 0;        // float offset of this octave's signal inside a clip's scratch
 };
 
@@ -29,8 +25,6 @@ struct CqtDevice {
     float* inv_sqrt_len = nullptr;     // [n_bins]
     unsigned int* clip_max = nullptr;  // [chunk_clips] float bits of max |V|
     unsigned int* clip_min = nullptr;  // [chunk_clips] float bits of min |V|
-    float2* tw[16] = {};               // per log2nc
-    float2* tw2[16] = {};
     std::vector<CqtOctaveDev> oct;
     size_t early_off = 0;              // scratch offsets of the early-downsample chain outputs
     std::vector<size_t> early_offs;

@@ -38,12 +38,33 @@ constexpr int kThreads = 256;
 
 thread_local std::string g_rs_err;
 
+// Batched launches (blockIdx.z = clip): clip c reads in + c * in_stride elements, in_len[c] of them (or
+// n_in when in_len is NULL), and owns the row out + c * out_stride of which outputs [0, out_cap) are
+// written: the resampled signal while it lasts (ceil(n_in * up / down) samples), zeros after it — the
+// pad/trim to a fixed duration that follows librosa.load in the reference (deep.py:52-61).
+struct RsBatch {
+    long long in_stride, out_stride;
+    const int* in_len;
+};
+
 template <bool I16>
-__global__ void __launch_bounds__(kThreads) resample_kernel(const void* __restrict__ in, long long n_in,
-                                                            float* __restrict__ out, long long n_out,
+__global__ void __launch_bounds__(kThreads) resample_kernel(const void* __restrict__ in_, long long n_in,
+                                                            float* __restrict__ out_, long long n_out,
                                                             const float* __restrict__ poly, int up, int down,
-                                                            int K, int half_len, int win) {
+                                                            int K, int half_len, int win, RsBatch bt) {
     extern __shared__ __align__(16) float s_x[];
+    const void* in = (const unsigned char*)in_ + (size_t)blockIdx.z * bt.in_stride * (I16 ? 2 : 4);
+    float* out = out_ + (size_t)blockIdx.z * bt.out_stride;
+    long long n_real = n_out;                       // outputs the signal really has; [n_real, n_out) are zeros
+    if (bt.in_len) {
+        n_in = bt.in_len[blockIdx.z];
+        n_real = (n_in * up + down - 1) / down;
+        if ((long long)blockIdx.x * kThreads >= n_real) {       // whole block past the signal: just the padding
+            const long long m = (long long)blockIdx.x * kThreads + threadIdx.x;
+            if (m < n_out) out[m] = 0.f;
+            return;
+        }
+    }
     const long long m0 = (long long)blockIdx.x * kThreads;
     // newest sample any output of this CTA touches, oldest = that of the first output minus K-1
     const long long k_first = (m0 * down + half_len) / up;
@@ -58,6 +79,7 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(const void* __restri
     __syncthreads();
     const long long m = m0 + threadIdx.x;
     if (m >= n_out) return;
+    if (m >= n_real) { out[m] = 0.f; return; }
     const long long u = m * down + half_len;
     const int p = (int)(u % up);
     const float* xs = s_x + (int)(u / up - k_lo);            // x[(u / up) - i] = xs[-i]
@@ -77,12 +99,25 @@ __global__ void __launch_bounds__(kThreads) resample_kernel(const void* __restri
 constexpr int kPhWarps = kThreads / 32;
 
 template <bool I16>
-__global__ void __launch_bounds__(kThreads) resample_phase_kernel(const void* __restrict__ in, long long n_in,
-                                                                  float* __restrict__ out, long long n_out,
+__global__ void __launch_bounds__(kThreads) resample_phase_kernel(const void* __restrict__ in_, long long n_in,
+                                                                  float* __restrict__ out_, long long n_out,
                                                                   const float* __restrict__ poly, int up, int down,
-                                                                  int K, int half_len, int win) {
+                                                                  int K, int half_len, int win, RsBatch bt) {
     extern __shared__ __align__(16) float s_x[];
+    const void* in = (const unsigned char*)in_ + (size_t)blockIdx.z * bt.in_stride * (I16 ? 2 : 4);
+    float* out = out_ + (size_t)blockIdx.z * bt.out_stride;
     const long long mb = (long long)blockIdx.x * 32 * up;          // first output of this block of 32 * up
+    long long n_real = n_out;
+    if (bt.in_len) {
+        n_in = bt.in_len[blockIdx.z];
+        n_real = (n_in * up + down - 1) / down;
+        if (mb >= n_real) {                                         // whole block past the signal: padding only
+            const int j = blockIdx.y * kPhWarps + (threadIdx.x >> 5);
+            const long long m = mb + j + (long long)up * (threadIdx.x & 31);
+            if (j < up && m < n_out) out[m] = 0.f;
+            return;
+        }
+    }
     const long long k_lo = (mb * down + half_len) / up - (K - 1);   // oldest sample the block touches
     constexpr int kBatch = 8;
 #pragma unroll 1
@@ -104,6 +139,7 @@ __global__ void __launch_bounds__(kThreads) resample_phase_kernel(const void* __
     if (j >= up) return;
     const long long m = mb + j + (long long)up * (threadIdx.x & 31);
     if (m >= n_out) return;
+    if (m >= n_real) { out[m] = 0.f; return; }
     const long long u = m * down + half_len;                        // u % up is the same for all 32 lanes
     const float* xs = s_x + (int)(u / up - k_lo);                   // lanes are `down` samples apart
     const float4* h4 = reinterpret_cast<const float4*>(poly + (size_t)(u % up) * K);
@@ -148,24 +184,28 @@ int rs_fail(int code, const std::string& msg) {
                            std::string(#expr) + ": " + cudaGetErrorString(e__));          \
     } while (0)
 
-int rs_launch(b2a_resampler* r, const void* d_in, int in_dtype, long long n_in, float* d_out, cudaStream_t st) {
-    const long long n_out = b2a_resampler_out_len(r, n_in);
-    if (n_out <= 0) return B2A_OK;
+// One launch for `n_clips` signals.  Single-signal calls pass n_clips = 1, bt = {0, 0, NULL}, n_out = the
+// signal's own length; batched calls pass the row capacity as n_out and per-clip lengths in bt.in_len.
+int rs_launch(b2a_resampler* r, const void* d_in, int in_dtype, long long n_in, float* d_out, long long n_out,
+              int n_clips, RsBatch bt, cudaStream_t st) {
+    if (n_out <= 0 || n_clips <= 0) return B2A_OK;
+    if (n_clips > 65535) return rs_fail(B2A_EINVAL, "at most 65535 clips per batched resampler launch");
     const int K = r->d.taps_per_phase;
     const int up = r->d.up, down = r->d.down;
     // phase-aligned kernel: 32 lanes x `down` samples + the filter must fit shared memory
     const long long win_ph = 32LL * down + K + 2;
     if (up >= 8 && (down & 1) && win_ph * (long long)sizeof(float) <= 200 * 1024) {
         const size_t smem = (size_t)win_ph * sizeof(float);
-        const dim3 grid((unsigned)((n_out + 32LL * up - 1) / (32LL * up)), (unsigned)((up + kPhWarps - 1) / kPhWarps));
+        const dim3 grid((unsigned)((n_out + 32LL * up - 1) / (32LL * up)), (unsigned)((up + kPhWarps - 1) / kPhWarps),
+                        (unsigned)n_clips);
         if (in_dtype == B2A_IN_I16) {
             auto k = resample_phase_kernel<true>;
             RS_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, up, down, K, r->d.half_len, (int)win_ph);
+            k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, up, down, K, r->d.half_len, (int)win_ph, bt);
         } else {
             auto k = resample_phase_kernel<false>;
             RS_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, up, down, K, r->d.half_len, (int)win_ph);
+            k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, up, down, K, r->d.half_len, (int)win_ph, bt);
         }
         RS_TRY(cudaGetLastError());
         return B2A_OK;
@@ -173,15 +213,15 @@ int rs_launch(b2a_resampler* r, const void* d_in, int in_dtype, long long n_in, 
     // input samples spanned by 256 consecutive outputs, plus the filter length
     const int win = K + (int)(((long long)(kThreads - 1) * r->d.down + r->d.up - 1) / r->d.up) + 2;
     const size_t smem = (size_t)win * sizeof(float);
-    const unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
+    const dim3 grid((unsigned)((n_out + kThreads - 1) / kThreads), 1, (unsigned)n_clips);
     if (in_dtype == B2A_IN_I16) {
         auto k = resample_kernel<true>;
         RS_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, r->d.up, r->d.down, K, r->d.half_len, win);
+        k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, r->d.up, r->d.down, K, r->d.half_len, win, bt);
     } else {
         auto k = resample_kernel<false>;
         RS_TRY(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, r->d.up, r->d.down, K, r->d.half_len, win);
+        k<<<grid, kThreads, smem, st>>>(d_in, n_in, d_out, n_out, r->d_poly, r->d.up, r->d.down, K, r->d.half_len, win, bt);
     }
     RS_TRY(cudaGetLastError());
     return B2A_OK;
@@ -272,7 +312,34 @@ int b2a_resampler_run_device(b2a_resampler* r, const void* d_in, int32_t in_dtyp
     if (n_in == 0) return B2A_OK;
     if (!d_in || !d_out) return rs_fail(B2A_EINVAL, "NULL buffer");
     RS_TRY(cudaSetDevice(r->device));
-    return rs_launch(r, d_in, in_dtype, n_in, d_out, (cudaStream_t)stream);
+    return rs_launch(r, d_in, in_dtype, n_in, d_out, b2a_resampler_out_len(r, n_in), 1, RsBatch{0, 0, nullptr}, (cudaStream_t)stream);
+}
+
+int b2a_resampler_run_device_batch(b2a_resampler* r, const void* d_in, int32_t in_dtype, int64_t n_clips,
+                                   int64_t in_stride, const int32_t* d_in_len, float* d_out, int64_t out_stride,
+                                   int64_t out_cap, void* stream) {
+    if (!r) return rs_fail(B2A_EINVAL, "resampler is NULL");
+    if (n_clips < 0 || in_stride <= 0 || out_cap <= 0 || out_stride < out_cap) return rs_fail(B2A_EINVAL, "bad batch geometry");
+    if (in_dtype != B2A_IN_I16 && in_dtype != B2A_IN_F32) return rs_fail(B2A_EINVAL, "unknown input dtype");
+    if (n_clips == 0) return B2A_OK;
+    if (!d_in || !d_out || !d_in_len) return rs_fail(B2A_EINVAL, "NULL buffer");
+    RS_TRY(cudaSetDevice(r->device));
+    for (int64_t c0 = 0; c0 < n_clips; c0 += 32768) {         // gridDim.z limit
+        const int nb = (int)std::min<int64_t>(32768, n_clips - c0);
+        const int rc = rs_launch(r, (const unsigned char*)d_in + (size_t)c0 * in_stride * (in_dtype == B2A_IN_I16 ? 2 : 4),
+                                 in_dtype, in_stride, d_out + (size_t)c0 * out_stride, out_cap, nb,
+                                 RsBatch{in_stride, out_stride, d_in_len + c0}, (cudaStream_t)stream);
+        if (rc != B2A_OK) return rc;
+    }
+    return B2A_OK;
+}
+
+int b2a_resampler_rates(const b2a_resampler* r, int32_t* orig_sr, int32_t* target_sr, int32_t* device) {
+    if (!r) return rs_fail(B2A_EINVAL, "resampler is NULL");
+    if (orig_sr) *orig_sr = r->orig;
+    if (target_sr) *target_sr = r->target;
+    if (device) *device = r->device;
+    return B2A_OK;
 }
 
 int b2a_resampler_run_host(b2a_resampler* r, const void* in, int32_t in_dtype, int64_t n_in, float* out) {
@@ -298,7 +365,7 @@ int b2a_resampler_run_host(b2a_resampler* r, const void* in, int32_t in_dtype, i
         r->cap_out = out_bytes;
     }
     RS_TRY(cudaMemcpyAsync(r->d_in, in, in_bytes, cudaMemcpyHostToDevice, r->stream));
-    const int rc = rs_launch(r, r->d_in, in_dtype, n_in, r->d_out, r->stream);
+    const int rc = rs_launch(r, r->d_in, in_dtype, n_in, r->d_out, b2a_resampler_out_len(r, n_in), 1, RsBatch{0, 0, nullptr}, r->stream);
     if (rc != B2A_OK) return rc;
     RS_TRY(cudaMemcpyAsync(out, r->d_out, out_bytes, cudaMemcpyDeviceToHost, r->stream));
     RS_TRY(cudaStreamSynchronize(r->stream));

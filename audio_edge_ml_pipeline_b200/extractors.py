@@ -182,74 +182,145 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
         audio = self._prepare(sample_path, start_time, end_time)
         return self.extract_batch(audio[None, :])[0]
 
+    # ---- dataset extraction ------------------------------------------------------------------
+    def _run_sharded(self, n: int, fn) -> None:
+        """fn(device_slot, device, a, b): clips [a, b) of a batch of n on one device; contiguous blocks,
+        one host thread per device (no collective, the gather is each device's D2H)."""
+        devs = self.devices[:max(1, min(len(self.devices), n))]
+        if len(devs) == 1:
+            fn(0, devs[0], 0, n)
+            return
+        bounds = [n * g // len(devs) for g in range(len(devs) + 1)]
+        errs: list = []
+
+        def work(g):
+            try:
+                if bounds[g + 1] > bounds[g]:
+                    fn(g, devs[g], bounds[g], bounds[g + 1])
+            except Exception as exc:  # noqa: BLE001
+                errs.append(exc)
+
+        threads = [threading.Thread(target=work, args=(g,)) for g in range(len(devs))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errs:
+            raise errs[0]
+
+    def _stage(self, key, shape_tail, dtype):
+        """Pinned staging rows, reused across windows and calls: key -> array (HOST_BATCH_CLIPS or fewer rows)."""
+        ent = self._staging.get(key)
+        if ent is None:
+            arr, hnd = _alloc_staging((key[1],) + tuple(shape_tail), dtype)
+            ent = self._staging[key] = (arr, None, hnd, None)
+        return ent[0]
+
+    def _resample_group(self, paths, offs, durs, rate: int, n: int, mono16: bool, dst: np.ndarray) -> None:
+        """Files at `rate` != sample_rate (deep.py:44-50: librosa.load resamples them): native decode at the
+        file rate -> pinned staging -> device resampler + pad / trim to n samples + kernels -> dst rows."""
+        up, down, half, _poly = B.resampler_design(rate, self.sample_rate)
+        need_in = ((n - 1) * down + half) // up + 1          # input frames the first n outputs touch
+        dt = np.int16 if mono16 else np.float32
+        per = max(1, min(HOST_BATCH_CLIPS, (256 << 20) // (need_in * np.dtype(dt).itemsize)))
+        raw = self._stage(("raw", per, need_in, np.dtype(dt).str), (need_in,), dt)
+        for a in range(0, len(paths), per):
+            b = min(len(paths), a + per)
+            _r, n_out, status = B.decode_wav_batch(paths[a:b], need_in, raw, offs[a:b], durs[a:b], DECODE_WORKERS)
+            if status.any():
+                raise RuntimeError(f"decode failed for {paths[a + int(np.flatnonzero(status)[0])]} (status {status.max()})")
+
+            def one(slot, dev, lo, hi):
+                eng = self._engine(n, np.float32, dev)
+                eng.run_host_resampled(B.get_resampler(rate, self.sample_rate, dev), raw[lo:hi], n_out[lo:hi],
+                                       dst[a + lo:a + hi])
+            self._run_sharded(b - a, one)
+
+    def _float_group(self, paths, offs, durs, n: int, dst: np.ndarray) -> None:
+        """Files at the right rate that are not mono PCM16 (stereo, 8/24/32-bit, float): native decode to
+        float32 with the channel mean, then the float32-input engine."""
+        per = max(1, min(HOST_BATCH_CLIPS, (256 << 20) // (n * 4)))
+        raw = self._stage(("f32", per, n, "f4"), (n,), np.float32)
+        for a in range(0, len(paths), per):
+            b = min(len(paths), a + per)
+            _r, _n, status = B.decode_wav_batch(paths[a:b], n, raw, offs[a:b], durs[a:b], DECODE_WORKERS)
+            if status.any():
+                raise RuntimeError(f"decode failed for {paths[a + int(np.flatnonzero(status)[0])]} (status {status.max()})")
+            self._run_sharded(b - a, lambda slot, dev, lo, hi: self._engine(n, np.float32, dev)
+                              .run_host(raw[lo:hi], dst[a + lo:a + hi]))
+
+    def _window_native(self, items, dst: np.ndarray) -> list:
+        """One window of loader items, fixed duration, through the native front end.  Features of item i go
+        to dst[i]; returns a per-item list: None = done, an Exception = skip this sample, "py" = not a
+        file the native decoder covers (the Python path decides: other containers raise there)."""
+        n = int(self.duration * self.sample_rate)
+        paths = [str(p_) for p_, _l, _m in items]
+        metas = [m for _p, _l, m in items]
+        offs = np.array([float(m.get("start_time") or 0.0) for m in metas])
+        durs = np.array([max(float(m["end_time"]) - o, 0.1) if m.get("end_time") is not None else -1.0
+                         for m, o in zip(metas, offs)])
+        info = B.probe_wav_batch(paths, DECODE_WORKERS)
+        res: list = [None] * len(items)
+        groups: dict = {}
+        for i in range(len(items)):
+            if info["status"][i] != B.DEC_OK:
+                res[i] = "py"
+                continue
+            mono16 = bool(info["format_tag"][i] == 1 and info["bits"][i] == 16 and info["channels"][i] == 1)
+            groups.setdefault((int(info["rate"][i]), mono16), []).append(i)
+
+        def run(key, idxs):
+            """A group, or on failure its halves, down to single clips (skip granularity = one sample)."""
+            rate, mono16 = key
+            sub = lambda arr: [arr[i] for i in idxs] if isinstance(arr, list) else arr[idxs]  # noqa: E731
+            contiguous = idxs[-1] - idxs[0] + 1 == len(idxs)
+            out = dst[idxs[0]:idxs[-1] + 1] if contiguous else np.empty((len(idxs),) + dst.shape[1:], np.float32)
+            try:
+                if rate == self.sample_rate and mono16:
+                    a_in = self._stage(("i16", HOST_BATCH_CLIPS, n, "i2"), (n,), np.int16)
+                    status = B.decode_wav_pcm16_batch(sub(paths), self.sample_rate, n, a_in, sub(offs), sub(durs),
+                                                      DECODE_WORKERS)
+                    if status.any():
+                        raise RuntimeError(f"decode failed (status {int(status.max())})")
+                    self.extract_batch(a_in[:len(idxs)], out)
+                elif rate == self.sample_rate:
+                    self._float_group(sub(paths), sub(offs), sub(durs), n, out)
+                else:
+                    self._resample_group(sub(paths), sub(offs), sub(durs), rate, n, mono16, out)
+                if not contiguous:
+                    dst[idxs] = out
+            except Exception as exc:  # noqa: BLE001
+                if len(idxs) == 1:
+                    res[idxs[0]] = exc
+                else:
+                    h = len(idxs) // 2
+                    run(key, idxs[:h])
+                    run(key, idxs[h:])
+
+        for key, idxs in groups.items():
+            run(key, idxs)
+        return res
+
     def extract_dataset(self, loader, max_samples: Optional[int] = None) -> FeatureSet:
-        feats: list = []
+        feats: list = []             # arrays (k, rows, T) (or per-clip (1, rows, T_i) when ragged), loader order
         labels: list = []
         metas: list = []
         label_to_idx: dict = {}
-        pending: list = []           # (audio, label, meta, path)
-
-        staging = self._staging      # (n_samples, dtype) -> (in array, out array, keep-alive handles)
-        final = {"arr": None, "pos": 0, "ok": True}   # features written in place when every window is 'fast'
-
-        def run_group(idxs):
-            """One (length, dtype) group of the pending window -> (n, rows, T) features."""
-            first = pending[idxs[0]][0]
-            key = (len(first), first.dtype.str)
-            if key not in staging and len(staging) < 4:
-                eng = self._engine(len(first), first.dtype, self.devices[0])
-                a_in, h1 = _alloc_staging((HOST_BATCH_CLIPS, len(first)), first.dtype)
-                a_out, h2 = _alloc_staging((HOST_BATCH_CLIPS, eng.rows, eng.frames), np.float32)
-                staging[key] = (a_in, a_out, h1, h2)
-            if key in staging and len(idxs) <= HOST_BATCH_CLIPS:
-                a_in, a_out = staging[key][0], staging[key][1]
-                for k, i in enumerate(idxs):
-                    a_in[k] = pending[i][0]
-                return self.extract_batch(a_in[:len(idxs)], a_out[:len(idxs)]).copy()
-            return self.extract_batch(np.stack([pending[i][0] for i in idxs]))
-
         ragged = self.duration is None and self._kind != B.KIND_CQT
+        n_fixed = int(self.duration * self.sample_rate) if self.duration is not None else 0
+        native = NATIVE_DECODE and self.duration is not None and n_fixed >= self._min_samples()
+        # fixed duration + a sized loader: windows land in one preallocated array (no concatenation) for as
+        # long as every window goes through the native front end; whatever comes after is appended (`tail`)
+        final = {"arr": None, "pos": 0, "open": True}
+        tail: list = []
 
-        def run_ragged(idxs):
-            """duration=None: clips keep their own lengths; one ragged launch per dtype."""
-            clips = [pending[i][0] for i in idxs]
-            cap = 1 << int(np.ceil(np.log2(max(len(c) for c in clips))))     # few engines: power-of-two maxima
-            return self._engine(cap, clips[0].dtype, self.devices[0]).run_host_ragged(clips)
-
-        def flush():
-            if not pending:
-                return
-            # group by (length, dtype) — by dtype only when ragged — keeping loader order
-            results: list = [None] * len(pending)
-            groups: dict = {}
-            for idx, (audio, _l, _m, _p) in enumerate(pending):
-                groups.setdefault((0 if ragged else len(audio), audio.dtype.str), []).append(idx)
-            for (_n, _dt), idxs in groups.items():
-                try:
-                    got = run_ragged(idxs) if ragged else run_group(idxs)
-                    for k, i in enumerate(idxs):
-                        results[i] = got[k]
-                except Exception as exc:  # noqa: BLE001 — same policy as a failing extract()
-                    for i in idxs:
-                        logger.warning("Skipping %s: %s", pending[i][3], exc)
-            for i, (_a, label, meta, _p) in enumerate(pending):
-                if results[i] is None:
-                    continue
-                feats.append(results[i][None])
-                final["ok"] = False
-                metas.append(meta)
-                if label is not None:
-                    if label not in label_to_idx:
-                        label_to_idx[label] = len(label_to_idx)
-                    labels.append(label_to_idx[label])
-            pending.clear()
-
-        def decode(item):
-            sample_path, _label, meta = item
-            try:
-                return self._prepare(sample_path, meta.get("start_time"), meta.get("end_time"))
-            except Exception as exc:  # noqa: BLE001 — reference semantics: warn and skip (base.py:204-206)
-                return exc
+        def book(item) -> None:
+            _p, label, meta = item
+            metas.append(meta)
+            if label is not None:
+                if label not in label_to_idx:
+                    label_to_idx[label] = len(label_to_idx)
+                labels.append(label_to_idx[label])
 
         def window():
             buf = []
@@ -263,81 +334,96 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
             if buf:
                 yield buf
 
-        def native_window(items):
-            """Fixed-duration windows: threaded native decode of mono PCM16 WAVs straight into the
-            pinned batch (b2a_decode_wav_pcm16_batch).  Returns (int16 batch view, status) or None."""
-            if self.duration is None or not NATIVE_DECODE:
-                return None
-            n = int(self.duration * self.sample_rate)
-            if n < self._min_samples():
-                return None
-            key = (n, np.dtype(np.int16).str)
-            if key not in staging:
-                eng = self._engine(n, np.int16, self.devices[0])
-                a_in, h1 = _alloc_staging((HOST_BATCH_CLIPS, n), np.int16)
-                a_out, h2 = _alloc_staging((HOST_BATCH_CLIPS, eng.rows, eng.frames), np.float32)
-                staging[key] = (a_in, a_out, h1, h2)
-            offs = np.array([float(m.get("start_time") or 0.0) for _p, _l, m in items])
-            durs = np.array([max(float(m["end_time"]) - o, 0.1) if m.get("end_time") is not None else -1.0
-                             for (_p, _l, m), o in zip(items, offs)])
-            status = B.decode_wav_pcm16_batch([p_ for p_, _l, _m in items], self.sample_rate, n, staging[key][0],
-                                              offs, durs, DECODE_WORKERS)
-            return staging[key][0][:len(items)], staging[key][1][:len(items)], status
+        def decode(item):
+            sample_path, _label, meta = item
+            try:
+                return self._prepare(sample_path, meta.get("start_time"), meta.get("end_time"))
+            except Exception as exc:  # noqa: BLE001 — reference semantics: warn and skip (base.py:204-206)
+                return exc
+
+        def python_path(items, pool) -> list:
+            """Python decoder + one engine call per (length, dtype) group (one ragged call per dtype when
+            duration is None).  Returns per item a (rows, T) array or an Exception."""
+            decoded = list(pool.map(decode, items)) if DECODE_WORKERS > 1 else [decode(it) for it in items]
+            out: list = list(decoded)
+            groups: dict = {}
+            for i, a in enumerate(decoded):
+                if not isinstance(a, Exception):
+                    groups.setdefault((0 if ragged else len(a), a.dtype.str), []).append(i)
+
+            def run(idxs):
+                try:
+                    clips = [decoded[i] for i in idxs]
+                    if ragged:
+                        cap = 1 << int(np.ceil(np.log2(max(len(c) for c in clips))))   # few engines: power-of-two maxima
+                        got = self._engine(cap, clips[0].dtype, self.devices[0]).run_host_ragged(clips)
+                    else:
+                        got = self.extract_batch(np.stack(clips))
+                    for k, i in enumerate(idxs):
+                        out[i] = got[k]
+                except Exception as exc:  # noqa: BLE001 — a failing batch is retried in halves: the skip
+                    if len(idxs) == 1:    # granularity stays one sample, as in the reference loop
+                        out[idxs[0]] = exc
+                    else:
+                        run(idxs[:len(idxs) // 2])
+                        run(idxs[len(idxs) // 2:])
+
+            for idxs in groups.values():
+                run(idxs)
+            return out
 
         from concurrent.futures import ThreadPoolExecutor
         with ThreadPoolExecutor(max_workers=DECODE_WORKERS) as pool:
             for items in window():
-                nat = None
-                try:
-                    nat = native_window(items)
-                except Exception as exc:  # noqa: BLE001 — e.g. engine creation failed: per-sample policy below
-                    logger.debug("native decode unavailable: %s", exc)
-                if nat is not None and not nat[2].any():
-                    # every file decoded natively: the pinned batch goes to the GPU(s) as is
+                res: list = ["py"] * len(items)
+                dst, in_place = None, False
+                if native:
                     try:
-                        k = len(items)
-                        if final["arr"] is None and final["ok"] and hasattr(loader, "__len__"):
+                        eng = self._engine(n_fixed, np.int16, self.devices[0])
+                        shape = (eng.rows, eng.frames)
+                        if final["arr"] is None and final["open"] and hasattr(loader, "__len__"):
                             cap = len(loader) if max_samples is None else min(len(loader), max_samples)
-                            final["arr"] = np.empty((cap,) + nat[1].shape[1:], dtype=np.float32)
-                        if final["arr"] is not None and final["ok"] and final["pos"] + k <= len(final["arr"]):
-                            got = self.extract_batch(nat[0], final["arr"][final["pos"]:final["pos"] + k])
-                            final["pos"] += k
+                            final["arr"] = np.empty((cap,) + shape, dtype=np.float32)
+                        pos = final["pos"]
+                        in_place = final["open"] and final["arr"] is not None and pos + len(items) <= len(final["arr"])
+                        if in_place:
+                            dst = final["arr"][pos:pos + len(items)]
                         else:
-                            final["ok"] = False
-                            got = self.extract_batch(nat[0], nat[1]).copy()
-                    except Exception as exc:  # noqa: BLE001
-                        for sample_path, _l, _m in items:
-                            logger.warning("Skipping %s: %s", sample_path, exc)
-                        continue
-                    feats.append(got)
-                    for sample_path, label, meta in items:
-                        metas.append(meta)
-                        if label is not None:
-                            if label not in label_to_idx:
-                                label_to_idx[label] = len(label_to_idx)
-                            labels.append(label_to_idx[label])
-                    continue
-                # general path: Python decoder (more formats, segment slicing, exact error messages)
-                if nat is not None:
-                    todo = [it for it, st in zip(items, nat[2]) if st != 0]
-                    redo = dict(zip((id(it) for it in todo),
-                                    pool.map(decode, todo) if DECODE_WORKERS > 1 else map(decode, todo)))
-                    decoded = [nat[0][k].copy() if nat[2][k] == 0 else redo[id(it)] for k, it in enumerate(items)]
+                            final["open"] = False
+                            dst = np.empty((len(items),) + shape, dtype=np.float32)
+                        res = self._window_native(items, dst)
+                    except Exception as exc:  # noqa: BLE001 — e.g. engine creation failed: per-sample policy below
+                        logger.debug("native front end unavailable: %s", exc)
+                        res, dst, in_place = ["py"] * len(items), None, False
+                todo = [i for i, r in enumerate(res) if isinstance(r, str)]
+                if todo:
+                    got = python_path([items[i] for i in todo], pool)
+                    for i, g in zip(todo, got):
+                        res[i] = g
+                # commit in loader order
+                ok = [i for i, r in enumerate(res) if not isinstance(r, Exception)]
+                for i, r in enumerate(res):
+                    if isinstance(r, Exception):
+                        logger.warning("Skipping %s: %s", items[i][0], r)
+                if dst is not None:
+                    for i in ok:
+                        if res[i] is not None:
+                            dst[i] = res[i]                      # rows the Python path produced join the window's array
+                    if len(ok) != len(items):
+                        dst[:len(ok)] = dst[ok]                  # close the gaps the skipped samples left
+                    if in_place:
+                        final["pos"] += len(ok)                  # the next window starts right behind these rows
+                    elif ok:
+                        tail.append(dst[:len(ok)])
                 else:
-                    decoded = list(pool.map(decode, items)) if DECODE_WORKERS > 1 else [decode(it) for it in items]
-                for (sample_path, label, meta), audio in zip(items, decoded):
-                    if isinstance(audio, Exception):
-                        logger.warning("Skipping %s: %s", sample_path, audio)
-                        continue
-                    pending.append((audio, label, meta, sample_path))
-                flush()
-        flush()
-        if not feats:
+                    final["open"] = False                        # rows from here on are appended, not placed
+                    tail.extend(np.asarray(res[i])[None] for i in ok)
+                for i in ok:
+                    book(items[i])
+        if not metas:
             raise RuntimeError("No features were successfully extracted.")
-        if final["ok"] and final["arr"] is not None:
-            features = final["arr"][:final["pos"]]              # every window decoded natively: no copy
-        else:
-            features = feats[0] if len(feats) == 1 else np.concatenate(feats)   # ragged shapes -> ValueError
+        parts = ([final["arr"][:final["pos"]]] if final["pos"] else []) + tail
+        features = parts[0] if len(parts) == 1 else np.concatenate(parts)       # ragged shapes -> ValueError
         return assemble_feature_set(self, features, labels, metas, label_to_idx)
 
 

@@ -137,6 +137,22 @@ int b2a_decode_wav_pcm16_batch(const char* const* paths, int64_t n_files, int32_
                                const double* offset_s, const double* duration_s, int32_t n_samples,
                                int16_t* dst, int32_t* status, int32_t n_threads);
 
+/* The general case of the same front end (what librosa.load -> soundfile covers for RIFF/WAVE,
+ * deep.py:44-50; header probe of dataset_loaders/audio_folder_loader.py:76-103): PCM 8/16/24/32-bit and
+ * IEEE float 32/64, any channel count (float32 channel mean = librosa.to_mono), any rate.
+ * b2a_probe_wav_batch reads headers only; every output array is optional except status.
+ * b2a_decode_wav_batch decodes frames [offset, offset + duration) of each file AT THE FILE'S RATE, at most
+ * max_frames of them, into row i of dst (dst_stride elements apart; the rest of the row is zero-filled):
+ * out_dtype B2A_IN_I16 copies mono PCM16 as is (anything else: B2A_DEC_EUNSUPPORTED), B2A_IN_F32 converts
+ * every supported format the way libsndfile scales it (PCM16 / 32768, ...).  rate[i] / n_out[i] receive the
+ * file's rate and the frames written; files at another rate than the extractor's go on to the resampler
+ * (b2a_run_host_resampled).  Non-WAV containers report B2A_DEC_EFORMAT and are the caller's to skip. */
+int b2a_probe_wav_batch(const char* const* paths, int64_t n_files, int32_t* rate, int32_t* channels,
+                        int32_t* bits, int32_t* format_tag, int64_t* n_frames, int32_t* status, int32_t n_threads);
+int b2a_decode_wav_batch(const char* const* paths, int64_t n_files, const double* offset_s,
+                         const double* duration_s, int64_t max_frames, int32_t out_dtype, void* dst,
+                         int64_t dst_stride, int32_t* rate, int32_t* n_out, int32_t* status, int32_t n_threads);
+
 /* Rational resampler for files whose rate differs from `sample_rate` — what librosa.load does
  * with soxr_hq inside `_load_segment` (deep.py:44-50) before any extractor sees the samples.
  * Zero-phase Kaiser-sinc low-pass (pass band to 0.913 x, stop band from 1.0 x the lower Nyquist,
@@ -161,6 +177,20 @@ int b2a_resampler_design(int32_t orig_sr, int32_t target_sr, int32_t* up, int32_
 int b2a_resampler_run_host(b2a_resampler* r, const void* in, int32_t in_dtype, int64_t n_in, float* out);
 int b2a_resampler_run_device(b2a_resampler* r, const void* d_in, int32_t in_dtype, int64_t n_in,
                              float* d_out, void* stream);
+/* Many signals per launch: clip i = in[i * in_stride, + in_len[i]) (d_in_len is a DEVICE array); row i of
+ * d_out (out_stride floats apart) receives outputs [0, out_cap): the resampled signal while it lasts
+ * (ceil(in_len * target / orig) samples), zeros after it — librosa.load followed by the pad / trim to a
+ * fixed duration (deep.py:52-61).  Asynchronous on `stream`. */
+int b2a_resampler_run_device_batch(b2a_resampler* r, const void* d_in, int32_t in_dtype, int64_t n_clips,
+                                   int64_t in_stride, const int32_t* d_in_len, float* d_out, int64_t out_stride,
+                                   int64_t out_cap, void* stream);
+int b2a_resampler_rates(const b2a_resampler* r, int32_t* orig_sr, int32_t* target_sr, int32_t* device);
+/* Host batch of clips at the FILES' rate -> features: H2D, batched resampling to the handle's sample rate
+ * with pad / trim to its n_samples, the extractor's kernels, D2H; chunked and overlapped like b2a_run_host.
+ * `h` must be a float32-input handle on the resampler's device whose sample_rate is the resampler's target.
+ * clips: [n_clips][in_stride] of in_dtype (host), in_len[i] <= in_stride valid samples each (host array). */
+int b2a_run_host_resampled(b2a_handle* h, b2a_resampler* r, const void* clips, int32_t in_dtype, int64_t in_stride,
+                           const int32_t* in_len, int64_t n_clips, float* out);
 const char* b2a_resampler_last_error(void);   /* same text b2a_last_error() returns after a resampler call */
 
 /* Number of CUDA kernel launches the last b2a_run_* call on this handle enqueued. */

@@ -61,6 +61,33 @@ def main():
     x = (rng.standard_normal((40, 101)) * 20 - 40).astype(np.float32)
     np.savez_compressed(OUT / "helpers_ref.npz", a=a, trim=pad_or_trim(a, 600), pad=pad_or_trim(a, 1500),
                         x=x, norm=normalize(x), norm_const=normalize(np.full((4, 5), -100.0, np.float32)))
+    # Stage-1b augmentors, executed from the reference's own source (augment.py:88-212; the module itself
+    # imports librosa/soundfile at import time, so its functions are lifted one by one like the helpers above)
+    glb = {"np": np}
+    aug = REF / "src/preprocessing/augment.py"
+    names = {"volume_scale": "_volume_scale", "gaussian_noise": "_gaussian_noise", "time_shift": "_time_shift",
+             "polarity_inversion": "_polarity_inversion", "pdm_hiss": "_pdm_hiss"}
+    glb["_AUGMENTORS"] = {k: _func_from_source(aug, v, glb) for k, v in names.items()}
+    apply_aug = _func_from_source(aug, "_apply_augmentations", glb)
+    preserve = _func_from_source(aug, "_preserve_length", glb)
+    specs = [
+        {"type": "volume_scale", "min_gain": 0.7, "max_gain": 1.3},
+        {"type": "pdm_hiss", "min_amplitude": 0.01, "max_amplitude": 0.04},
+        {"type": "gaussian_noise", "min_amplitude": 0.001, "max_amplitude": 0.004},
+        {"type": "time_shift", "max_fraction": 0.2},
+        {"type": "polarity_inversion"},
+    ]                                   # config/augmentation.yaml:38-60 minus the two librosa-backed steps
+    arng = np.random.default_rng(42)    # augment.py:325 with the YAML's seed (augmentation.yaml:22)
+    srng = np.random.default_rng(99)
+    sr, n = 16000, 4000
+    clips = [(0.3 * srng.standard_normal(n)).astype(np.float32), synth.make_clip(srng, 2, sr, n).astype(np.float32),
+             np.clip(3.0 * srng.standard_normal(n), -1, 1).astype(np.float32)]
+    outs = []
+    for y in clips:                     # the per-file loop of run(): 4 copies each, one rng for the whole run
+        for _ in range(4):
+            outs.append(preserve(apply_aug(y, sr, specs, arng), len(y)))
+    np.savez_compressed(OUT / "augment_ref.npz", clips=np.stack(clips), out=np.stack(outs), sr=sr, seed=42,
+                        specs=np.array([repr(specs)]), pad=preserve(clips[0][:100], 150), trim=preserve(clips[0], 90))
     for f in sorted(OUT.glob("*.npz")):
         print(f.name, f.stat().st_size)
 

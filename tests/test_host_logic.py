@@ -254,6 +254,68 @@ def test_native_batch_decoder_matches_python_decoder(tmp_path, lib_built):
     assert np.array_equal(out[1], wavio.pad_or_trim(wavio.load_segment(tmp_path / "2.wav", 16000, 1.4, None), 16000))
 
 
+def _write_wav_raw(path, fmt_tag, channels, rate, bits, payload: bytes, extensible=False):
+    import struct
+    align = channels * bits // 8
+    if extensible:
+        guid = struct.pack("<H", fmt_tag) + bytes.fromhex("000000001000800000aa00389b71")
+        fmt = struct.pack("<HHIIHHHHI", 0xFFFE, channels, rate, rate * align, align, bits, 22, bits, 0) + guid
+    else:
+        fmt = struct.pack("<HHIIHH", fmt_tag, channels, rate, rate * align, align, bits)
+    body = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + b"LIST" + struct.pack("<I", 4) + b"abcd" \
+        + b"data" + struct.pack("<I", len(payload)) + payload
+    Path(path).write_bytes(b"RIFF" + struct.pack("<I", len(body)) + body)
+
+
+def test_native_general_decoder_matches_python_decoder(tmp_path, lib_built):
+    """b2a_probe_wav_batch / b2a_decode_wav_batch (stereo, 8/24/32-bit PCM, float32/64, extensible headers,
+    any rate) against wavio.decode_wav, which restates what librosa.load -> soundfile returns (deep.py:44-50)."""
+    from audio_edge_ml_pipeline_b200 import _lib as B
+    import scipy.io.wavfile as wf
+    rng = np.random.default_rng(13)
+    n = 5000
+    x16 = synth.to_pcm16(rng.standard_normal(n) * 0.2)
+    files = {}
+    wavio.write_wav_pcm16(tmp_path / "m16_16k.wav", x16, 16000); files["m16_16k.wav"] = (16000, 1, 16, 1)
+    wavio.write_wav_pcm16(tmp_path / "m16_44k.wav", x16, 44100); files["m16_44k.wav"] = (44100, 1, 16, 1)
+    wf.write(tmp_path / "s16.wav", 22050, np.stack([x16, x16[::-1]], axis=1)); files["s16.wav"] = (22050, 2, 16, 1)
+    wf.write(tmp_path / "f32.wav", 48000, (rng.standard_normal(n) * 0.1).astype(np.float32)); files["f32.wav"] = (48000, 1, 32, 3)
+    wf.write(tmp_path / "f64s.wav", 8000, rng.standard_normal((n, 2)) * 0.1); files["f64s.wav"] = (8000, 2, 64, 3)
+    wf.write(tmp_path / "i32.wav", 16000, rng.integers(-2**31, 2**31 - 1, n).astype(np.int32)); files["i32.wav"] = (16000, 1, 32, 1)
+    wf.write(tmp_path / "u8.wav", 16000, rng.integers(0, 256, n).astype(np.uint8)); files["u8.wav"] = (16000, 1, 8, 1)
+    p24 = rng.integers(-2**23, 2**23 - 1, (n, 3))
+    _write_wav_raw(tmp_path / "i24x3.wav", 1, 3, 32000, 24,
+                   b"".join(int(v).to_bytes(3, "little", signed=True) for v in p24.reshape(-1)), extensible=True)
+    files["i24x3.wav"] = (32000, 3, 24, 1)
+    (tmp_path / "junk.wav").write_bytes(b"RIFFxxxxjunk")
+    _write_wav_raw(tmp_path / "adpcm.wav", 2, 1, 16000, 8, b"\0" * 64)
+    names = list(files) + ["junk.wav", "adpcm.wav", "missing.wav"]
+    info = B.probe_wav_batch([tmp_path / k for k in names], n_threads=3)
+    for i, k in enumerate(files):
+        assert (info["rate"][i], info["channels"][i], info["bits"][i], info["format_tag"][i]) == files[k], k
+        assert info["status"][i] == B.DEC_OK and info["n_frames"][i] == n
+    assert info["status"][len(files):].tolist() == [B.DEC_EFORMAT, B.DEC_EUNSUPPORTED, B.DEC_EIO]
+    # float32 output: every format, channel mean, zero-filled tail
+    out = np.full((len(names), n + 100), 7.0, np.float32)
+    rate, n_out, status = B.decode_wav_batch([tmp_path / k for k in names], n + 100, out, n_threads=2)
+    assert status.tolist() == [0] * len(files) + [B.DEC_EFORMAT, B.DEC_EUNSUPPORTED, B.DEC_EIO]
+    for i, k in enumerate(files):
+        ref, sr = wavio.decode_wav(tmp_path / k)
+        ref = L.pcm16_to_float(ref) if ref.dtype == np.int16 else ref
+        assert rate[i] == sr == files[k][0] and n_out[i] == n
+        assert np.array_equal(out[i, :n], ref), k
+        assert not out[i, n:].any()
+    assert not out[len(files):].any()
+    # int16 output: mono PCM16 only; segments in native frames; truncation to max_frames
+    o16 = np.zeros((3, 2000), np.int16)
+    rate, n_out, status = B.decode_wav_batch([tmp_path / "m16_44k.wav", tmp_path / "s16.wav", tmp_path / "m16_16k.wav"],
+                                             2000, o16, offsets=[0.01, 0.0, 0.2], durations=[0.02, -1.0, -1.0])
+    assert status.tolist() == [0, B.DEC_EUNSUPPORTED, 0] and rate.tolist() == [44100, 22050, 16000]
+    assert n_out.tolist() == [882, 0, 1800]
+    assert np.array_equal(o16[0, :882], x16[441:441 + 882]) and not o16[0, 882:].any()
+    assert np.array_equal(o16[2, :1800], x16[3200:5000])
+
+
 def test_native_and_python_decode_paths_give_the_same_dataset(tmp_path, fake, monkeypatch):
     _make_dataset(tmp_path / "ds", n=8000, broken={("axe", 1)})
     from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from audio_edge_ml_pipeline_b200 import _lib as B
-from audio_edge_ml_pipeline_b200 import wavio
+from audio_edge_ml_pipeline_b200 import synth, wavio
 from oracle import librosa_restated as L
 
 RATIOS = [(44100, 16000), (48000, 16000), (22050, 16000), (8000, 16000), (44100, 22050), (32000, 22050), (11025, 22050)]
@@ -173,3 +173,72 @@ def test_shared_resampler_is_safe_from_many_threads():
         for g, s in zip(got, serial):
             assert g.shape == s.shape and np.array_equal(g, s)
     assert len([k for k in B._resamplers if k[:2] == (44100, 16000)]) == 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("orig,dtype", [(44100, np.int16), (22050, np.float32), (48000, np.int16), (8000, np.int16)])
+def test_batched_resample_then_extract_equals_per_clip_path(orig, dtype):
+    """b2a_run_host_resampled: ragged clips at the file rate -> device resampler (many clips per launch,
+    pad / trim to n_samples) -> log-mel, against the single-clip resampler + extract_batch, bit for bit,
+    and against the oracle within the mel tolerance."""
+    import audio_edge_ml_pipeline_b200 as P
+    rng = np.random.default_rng(orig)
+    n_t = 16000                                             # 1 s at 16 kHz
+    lens = [int(f * orig) for f in (0.31, 1.0, 1.7, 0.05, 1.02)] + [1]
+    stride = max(lens)
+    raw = np.zeros((len(lens), stride), dtype)
+    for i, n in enumerate(lens):
+        y = 0.3 * rng.standard_normal(n) + 0.3 * np.sin(2 * np.pi * 700 * np.arange(n) / orig)
+        raw[i, :n] = np.clip(np.round(y * 32768), -32768, 32767).astype(np.int16) if dtype == np.int16 else y
+    mel = P.AudioMelSpectrogram(duration=1.0)
+    eng = mel._engine(n_t, np.float32, 0)
+    got = eng.run_host_resampled(B.get_resampler(orig, 16000, 0), raw, np.array(lens, np.int32))
+    assert got.shape == (len(lens), 40, 101)
+    for i, n in enumerate(lens):
+        y = B.resample(raw[i, :n], orig, 16000)              # one clip per launch
+        clip = np.zeros(n_t, np.float32)
+        clip[:min(n_t, len(y))] = y[:n_t]
+        one = mel.extract_batch(clip[None])[0]
+        assert np.array_equal(got[i], one), (i, float(np.abs(got[i] - one).max()))
+        yr = L.resample_restated(L.pcm16_to_float(raw[i, :n]) if dtype == np.int16 else raw[i, :n], orig, 16000)
+        ref = L.audio_mel_spec(yr, 16000, 40, 512, 160, 1.0)
+        assert np.abs(got[i] - ref).max() <= 1e-4
+    mel.close()
+
+
+@pytest.mark.gpu
+def test_mixed_format_dataset_through_the_native_front_end(tmp_path, caplog):
+    """One folder with mono PCM16 at the target rate, 44.1 kHz PCM16, stereo 22.05 kHz, float32 at the target
+    rate, 24-bit at 48 kHz and a broken file: every decodable file yields the features the per-file
+    extract() path yields (librosa.load semantics: channel mean, resample, pad / trim), in loader order,
+    and the broken one is skipped with a warning — one sample, not its whole batch."""
+    import logging
+    import scipy.io.wavfile as wf
+    import audio_edge_ml_pipeline_b200 as P
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    rng = np.random.default_rng(17)
+    d = tmp_path / "ds" / "c0"
+    d.mkdir(parents=True)
+
+    def sig(n, sr):
+        return 0.2 * rng.standard_normal(n) + 0.3 * np.sin(2 * np.pi * 600 * np.arange(n) / sr)
+    for k in range(5):
+        wavio.write_wav_pcm16(d / f"a{k}_m16.wav", synth.to_pcm16(sig(14000 + 900 * k, 16000)), 16000)
+        wavio.write_wav_pcm16(d / f"b{k}_44k.wav", synth.to_pcm16(sig(40000 + 2500 * k, 44100)), 44100)
+        wf.write(d / f"c{k}_stereo22k.wav", 22050, np.stack([synth.to_pcm16(sig(25000, 22050)),
+                                                            synth.to_pcm16(sig(25000, 22050))], axis=1))
+        wf.write(d / f"d{k}_f32.wav", 16000, sig(17000, 16000).astype(np.float32))
+        wf.write(d / f"e{k}_i32_48k.wav", 48000, (sig(50000, 48000) * 2**30).astype(np.int32))
+    (d / "b9_broken.wav").write_bytes(b"RIFF\x00\x00\x00\x00WAVEfmt ")
+    ex = P.AudioMelSpectrogram(duration=1.0)
+    loader = AudioFolderLoader(tmp_path / "ds")
+    with caplog.at_level(logging.WARNING):
+        fs = ex.extract_dataset(loader)
+    assert fs.n_samples == 25 and fs.features.shape == (25, 40, 101)
+    assert sum("Skipping" in r.message for r in caplog.records) == 1
+    names = [m["filename"] for m in fs.metadata]
+    assert names == sorted(names) and "b9_broken.wav" not in names
+    for row, meta in zip(fs.features, fs.metadata):
+        one = ex.extract(d / meta["filename"])                # Python decode + single-clip resampler
+        assert np.abs(row - one).max() <= 2e-6, (meta["filename"], float(np.abs(row - one).max()))
+    ex.close()
