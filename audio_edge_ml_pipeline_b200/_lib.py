@@ -31,6 +31,7 @@ EXPORTED_SYMBOLS = [
     "b2a_resampler_create", "b2a_resampler_destroy", "b2a_resampler_out_len", "b2a_resampler_geometry",
     "b2a_resampler_design", "b2a_resampler_run_host", "b2a_resampler_run_device", "b2a_resampler_last_error",
     "b2a_resampler_run_device_batch", "b2a_resampler_rates", "b2a_run_host_resampled",
+    "b2a_augment_host", "b2a_augment_device",
 ]
 
 

@@ -23,6 +23,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <mutex>
 #include <type_traits>
 
 namespace b2a {
@@ -156,6 +158,10 @@ __global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
     // Tap pairs come from constant memory, indexed by the loop-uniform step: the shared-memory
     // pipe only carries the samples.
     const int lb = tid * kDecR + (kDecHalf - 1);     // local index of the pair (B[m_0], A[m_0]) of output r = 0
+#ifndef B2A_AB_DECLVL
+#define B2A_AB_DECLVL 0
+#endif
+#if B2A_AB_DECLVL == 0
     float2 acc2[kDecR];
 #pragma unroll
     for (int r = 0; r < kDecR; ++r) acc2[r] = make_float2(0.f, 0.f);
@@ -180,6 +186,56 @@ __global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
     double accd[kDecR];
 #pragma unroll
     for (int r = 0; r < kDecR; ++r) { acc[r] = acc2[r].x + acc2[r].y; accd[r] = 0.0; }
+#else
+    // Two-level accumulation: every window step (kDecU tap pairs) sums into FRESH packed accumulators whose
+    // partial sums stay small, and only the step totals meet the running sum — 22 roundings at the running
+    // sum's magnitude instead of 176 (level 1: float32; level 2: float32 (DECLVL 1) or float64 (DECLVL 2)).
+#if B2A_AB_DECLVL == 1
+    float2 tot2[kDecR];
+#pragma unroll
+    for (int r = 0; r < kDecR; ++r) tot2[r] = make_float2(0.f, 0.f);
+#else
+    double accd[kDecR];
+#pragma unroll
+    for (int r = 0; r < kDecR; ++r) accd[r] = 0.0;
+#endif
+    auto step_f32 = [&](int i0) {                    // tap pairs [i0, i0 + kDecU)
+        float2 x[kDecR + kDecU - 1];
+        float2 a2[kDecR];
+        const float2* w = s2 + (lb - i0 - (kDecU - 1));
+#pragma unroll
+        for (int d = 0; d < kDecR + kDecU - 1; ++d) x[d] = w[d];
+#pragma unroll
+        for (int u = 0; u < kDecU; ++u) {
+            const float2 h = kDecTapP[i0 + u];
+#pragma unroll
+            for (int r = 0; r < kDecR; ++r)
+                a2[r] = u == 0 ? __fmul2_rn(x[r - u + kDecU - 1], h) : __ffma2_rn(x[r - u + kDecU - 1], h, a2[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < kDecR; ++r) {
+#if B2A_AB_DECLVL == 1
+            tot2[r] = __fadd2_rn(tot2[r], a2[r]);
+#else
+            accd[r] += (double)(a2[r].x + a2[r].y);
+#endif
+        }
+    };
+#pragma unroll 1
+    for (int c = 0; c < kDecOuter / kDecU; ++c) {
+        step_f32(c * kDecU);
+        step_f32(kDecHalf - (c + 1) * kDecU);
+    }
+    float acc[kDecR];
+#if B2A_AB_DECLVL == 1
+    double accd[kDecR];
+#pragma unroll
+    for (int r = 0; r < kDecR; ++r) { acc[r] = tot2[r].x + tot2[r].y; accd[r] = 0.0; }
+#else
+#pragma unroll
+    for (int r = 0; r < kDecR; ++r) acc[r] = 0.f;
+#endif
+#endif
     // centre pairs [88, 104) in fp64, one polyphase component at a time (a window of doubles for both
     // would not fit the register budget); the 32-bit loads of a phase are 2-way bank conflicted,
     // which this short pass can afford.
@@ -371,6 +427,137 @@ __global__ void __launch_bounds__(kBankThreads, 3) cqt_bank_kernel(const __grid_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same bank with the coefficients in the kernel's PARAMETER block (constant bank 0): they reach
+// the FFMA2s through uniform registers (LDCU.64), not through the shared-memory pipe, which then only
+// carries samples.  (With shared-memory coefficients every broadcast 128-bit load still returns 512 B
+// to the register file — 4 cycles of the 128 B/cycle pipe — and the kernel above is LSU-bound at
+// 27 % of the FFMA2 rate.)  A parameter block holds one table of <= 3072 coefficients (N = 256, 12
+// rows); octaves whose tables are equal up to a power of two — every other octave of a cqt, since the
+// wavelets depend on f / sr only and the per-octave scale is sqrt(2)^o — share a launch.
+//   grid = (frame blocks of 256, octaves of the group, clips), 64 threads; thread = 4 frames
+//   (lane + 32 i + 128 warp) x 12 rows; per n: 4 conflict-free sample loads, 12 LDCU.64, 48 FFMA2.
+//   Tile [256 frames][64 n] is a plain copy of each frame's slice (row pitch 65 words).
+// ------------------------------------------------------------------------------------------
+constexpr int kFastThreads = 64;
+constexpr int kFastFrames = 256;
+constexpr int kFastPitch = kBankSlice + 1;
+constexpr int kFastMaxCoef = 3072;
+constexpr size_t kFastSmem = (size_t)kFastFrames * kFastPitch * 4 + 64 * 4;
+
+struct FastOct {
+    const void* in; long long in_stride; int in_len; int in_i16;
+    int hop, n_rows, row0; float scale;      // scale: the power of two this octave's table is of the group's
+};
+struct FastParams {
+    float2 coef[kFastMaxCoef];               // [n][12] (re, im)
+    FastOct oct[8];
+    int n_fft, n_frames;
+    const float* inv_sqrt_len;
+    float* out; long long out_stride;
+    unsigned int* clip_max; unsigned int* clip_min;
+};
+
+__global__ void __launch_bounds__(kFastThreads, 3) cqt_bank_fast_kernel(const __grid_constant__ FastParams p) {
+    extern __shared__ __align__(16) unsigned char bank_smem[];
+    float* const s_tile = reinterpret_cast<float*>(bank_smem);                       // [256][65]
+    float* const s_red = s_tile + kFastFrames * kFastPitch;
+    const FastOct& o = p.oct[blockIdx.y];
+    const int N = p.n_fft, hop = o.hop, L = o.in_len;
+    const size_t clip = blockIdx.z;
+    const int t0 = blockIdx.x * kFastFrames;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned char* const base = (const unsigned char*)o.in + clip * (size_t)o.in_stride * (o.in_i16 ? 2 : 4);
+
+    float2 acc[4][12];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < 12; ++b) acc[i][b] = make_float2(0.f, 0.f);
+
+    const int nvalid = min(kFastFrames, p.n_frames - t0);
+    const float* const xrow = s_tile + (warp * 128 + lane) * kFastPitch;            // frame lane + 128 warp (+ 32 i)
+    for (int n0 = 0; n0 < N; n0 += kBankSlice) {
+        __syncthreads();
+        for (int it = tid; it < kFastFrames * (kBankSlice / 4); it += kFastThreads) {
+            const int f = it >> 4, n = 4 * (it & 15);
+            if (f >= nvalid) break;                                  // (items are frame-major: nothing valid follows)
+            float v[4] = {0.f, 0.f, 0.f, 0.f};
+            const int s0 = (t0 + f) * hop + n0 + n - N / 2;
+            if (s0 >= 0 && s0 + 4 <= L) {
+                if (o.in_i16) {
+                    const int16_t* ps = reinterpret_cast<const int16_t*>(base) + s0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = __int2float_rn((int)__ldg(ps + e)) * (1.0f / 32768.0f);
+                } else {
+                    const float* ps = reinterpret_cast<const float*>(base) + s0;
+                    if ((reinterpret_cast<uintptr_t>(ps) & 15) == 0) {
+                        const float4 x = __ldg(reinterpret_cast<const float4*>(ps));
+                        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) v[e] = __ldg(ps + e);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int s1 = s0 + e;
+                    if (s1 >= 0 && s1 < L)
+                        v[e] = o.in_i16 ? __int2float_rn((int)reinterpret_cast<const int16_t*>(base)[s1]) * (1.0f / 32768.0f)
+                                        : reinterpret_cast<const float*>(base)[s1];
+                }
+            }
+            float* d = s_tile + f * kFastPitch + n;
+            d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int r = 0; r < kBankSlice; ++r) {
+            const float x0 = xrow[r], x1 = xrow[32 * kFastPitch + r], x2 = xrow[64 * kFastPitch + r], x3 = xrow[96 * kFastPitch + r];
+            const float2* c = p.coef + (n0 + r) * 12;                // uniform: constant bank -> uniform registers
+#pragma unroll
+            for (int b = 0; b < 12; ++b) {
+                const float2 cf = c[b];
+                acc[0][b] = __ffma2_rn(make_float2(x0, x0), cf, acc[0][b]);
+                acc[1][b] = __ffma2_rn(make_float2(x1, x1), cf, acc[1][b]);
+                acc[2][b] = __ffma2_rn(make_float2(x2, x2), cf, acc[2][b]);
+                acc[3][b] = __ffma2_rn(make_float2(x3, x3), cf, acc[3][b]);
+            }
+        }
+    }
+    float vmax = 0.f, vmin = 3.0e38f;
+#pragma unroll
+    for (int b = 0; b < 12; ++b) {
+        if (b >= o.n_rows) continue;
+        const int row = o.row0 + b;
+        const float sc = p.inv_sqrt_len[row] * o.scale;              // (power of two: exact)
+        float* const orow = p.out + clip * (size_t)p.out_stride + (size_t)row * p.n_frames;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int t = t0 + warp * 128 + 32 * i + lane;
+            if (t < p.n_frames) {
+                const float mag = sqrtf(acc[i][b].x * acc[i][b].x + acc[i][b].y * acc[i][b].y) * sc;
+                orow[t] = mag;
+                vmax = fmaxf(vmax, mag);
+                vmin = fminf(vmin, mag);
+            }
+        }
+    }
+#pragma unroll
+    for (int sft = 16; sft > 0; sft >>= 1) {
+        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, sft));
+        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, sft));
+    }
+    if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
+    __syncthreads();
+    if (tid == 0) {
+        vmax = fmaxf(vmax, s_red[1]); vmin = fminf(vmin, s_red[33]);
+        atomicMax(p.clip_max + clip, __float_as_uint(vmax));
+        atomicMin(p.clip_min + clip, __float_as_uint(vmin));
+    }
+}
+
 // amplitude_to_db(ref=np.max, amin=1e-5, top_db) then _normalize (deep.py:259-260)
 __global__ void __launch_bounds__(kThreads) cqt_finalize_kernel(float* out, size_t out_stride, int total,
                                                                const unsigned int* clip_max,
@@ -448,6 +635,8 @@ int cqt_device_init(const CqtPlan& plan, const b2a_config& cfg, int sm_count, si
     if (plan.n_octaves > 12) { *err = "cqt: more than 12 octaves"; return B2A_EINVAL; }
     if (kBankSmem > smem_optin) { *err = "cqt: wavelet-bank tile exceeds shared memory"; return B2A_EINVAL; }
     CQ_TRY(cudaFuncSetAttribute(cqt_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBankSmem));
+    CQ_TRY(cudaFuncSetAttribute(cqt_bank_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
+    dev->fast.clear(); dev->fast_ok = kFastSmem <= smem_optin;
     dev->oct.resize(plan.n_octaves);
     size_t cur_off = plan.n_early ? dev->early_offs.back() : (size_t)-1;   // (size_t)-1: the input itself
     for (int i = 0; i < plan.n_octaves; ++i) {
@@ -483,6 +672,32 @@ int cqt_device_init(const CqtPlan& plan, const b2a_config& cfg, int sm_count, si
             }
             od.n_blocks = n_blocks;
             CQ_TRY(up(coef, &od.coef));
+            // fast path: does this table equal an earlier one up to a power of two?
+            if (n_blocks == 1 && (size_t)N * kBankRows <= (size_t)kFastMaxCoef && dev->fast_ok) {
+                bool placed = false;
+                for (auto& g : dev->fast) {
+                    if (g.table.size() != coef.size()) continue;
+                    float ratio = 0.f;
+                    for (size_t q = 0; q < coef.size() && ratio == 0.f; ++q)
+                        if (g.table[q].x != 0.f && coef[q].x != 0.f) ratio = coef[q].x / g.table[q].x;
+                    int ex = 0;
+                    if (!(ratio > 0.f) || std::frexp(ratio, &ex) != 0.5f) continue;
+                    bool same = true;
+                    for (size_t q = 0; q < coef.size() && same; ++q)
+                        same = coef[q].x == g.table[q].x * ratio && coef[q].y == g.table[q].y * ratio;
+                    if (!same) continue;
+                    g.octaves.push_back(i); g.scales.push_back(ratio);
+                    placed = true;
+                    break;
+                }
+                if (!placed) {
+                    CqtFastGroup g;
+                    g.table = coef; g.octaves.push_back(i); g.scales.push_back(1.0f);
+                    dev->fast.push_back(std::move(g));
+                }
+            } else {
+                dev->fast_ok = false;
+            }
         }
         if (o.decimate_after && i + 1 < plan.n_octaves) {
             cur_off = off;
@@ -540,7 +755,30 @@ int cqt_run(const CqtPlan& plan, const b2a_config& cfg, CqtDevice* dev, const vo
         bp.inv_sqrt_len = dev->inv_sqrt_len;
         bp.out = out; bp.out_stride = (long long)out_stride;
         bp.clip_max = dev->clip_max; bp.clip_min = dev->clip_min;
-        {
+        bool fast = dev->fast_ok && !dev->fast.empty();
+        for (const auto& g : dev->fast) fast = fast && g.octaves.size() <= 8;
+        if (fast) {
+            static FastParams fp;                                   // 25 KB: not on the stack
+            static std::mutex fp_mu;
+            std::lock_guard<std::mutex> guard(fp_mu);
+            for (const auto& g : dev->fast) {
+                std::memcpy(fp.coef, g.table.data(), g.table.size() * sizeof(float2));
+                for (size_t q = 0; q < g.octaves.size(); ++q) {
+                    const BankOct& bo = bp.oct[g.octaves[q]];
+                    FastOct& fo = fp.oct[q];
+                    fo.in = bo.in; fo.in_stride = bo.in_stride; fo.in_len = bo.in_len; fo.in_i16 = bo.in_i16;
+                    fo.hop = bo.hop; fo.n_rows = bo.n_rows; fo.row0 = bo.row0; fo.scale = g.scales[q];
+                }
+                fp.n_fft = bp.oct[g.octaves[0]].n_fft; fp.n_frames = nfr;
+                fp.inv_sqrt_len = dev->inv_sqrt_len;
+                fp.out = out; fp.out_stride = (long long)out_stride;
+                fp.clip_max = dev->clip_max; fp.clip_min = dev->clip_min;
+                const dim3 grid((nfr + kFastFrames - 1) / kFastFrames, (unsigned)g.octaves.size(), nb);
+                cqt_bank_fast_kernel<<<grid, kFastThreads, kFastSmem, st>>>(fp);     // parameters are copied at launch
+                CQ_TRY(cudaGetLastError());
+                ++*launches;
+            }
+        } else {
             const dim3 grid((nfr + kBankFrames - 1) / kBankFrames, n_rb, nb);
             cqt_bank_kernel<<<grid, kBankThreads, kBankSmem, st>>>(bp);
             CQ_TRY(cudaGetLastError());

@@ -49,10 +49,14 @@ def _parse_header(buf: memoryview):
 def wav_info(path) -> dict:
     """duration / sample_rate / n_channels without decoding (audio_folder_loader.py:76-103)."""
     try:
-        with open(path, "rb") as f:
-            head = f.read(1 << 16)
-        (tag, ch, sr, align, bits), (off, size) = _parse_header(memoryview(head))
         import os
+        with open(path, "rb") as f:
+            head = f.read(4096)                      # canonical headers are 44 bytes; LIST chunks rarely pass 4 KB
+            try:
+                (tag, ch, sr, align, bits), (off, size) = _parse_header(memoryview(head))
+            except AudioDecodeError:
+                head += f.read((1 << 16) - len(head))
+                (tag, ch, sr, align, bits), (off, size) = _parse_header(memoryview(head))
         size = min(size, os.path.getsize(path) - off) if size >= len(head) - off else size
         frames = size // max(align, 1)
         return {"duration": frames / sr if sr else 0.0, "sample_rate": int(sr), "n_channels": int(ch)}

@@ -193,6 +193,40 @@ int b2a_run_host_resampled(b2a_handle* h, b2a_resampler* r, const void* clips, i
                            const int32_t* in_len, int64_t n_clips, float* out);
 const char* b2a_resampler_last_error(void);   /* same text b2a_last_error() returns after a resampler call */
 
+/* Stage-1b waveform augmentation on the device (src/preprocessing/augment.py:88-212, 325-375): every output
+ * row is one source clip pushed through a chain of steps whose random parameters the HOST has already drawn
+ * with the reference's generator, in the reference's order (numpy default_rng(seed), augment.py:325), so the
+ * result equals the reference's y_aug bit for bit.  Ragged: row r reads lengths[r] samples at element offset
+ * src_off[r] of `src` and writes lengths[r] samples at element offset out_off[r] of `out`
+ * (_preserve_length, augment.py:206-212, is the identity for these length-preserving steps).
+ *   B2A_AUG_GAIN      y * a                               volume_scale :88-93 and the level match :344-345
+ *   B2A_AUG_NOISE     clip(y + noise[noise_off + i] * a)  gaussian_noise :96-102 (noise = float32 of the host's draws)
+ *   B2A_AUG_ROLL      np.roll(y, shift)                   time_shift :121-126
+ *   B2A_AUG_POLARITY  -y                                  polarity_inversion :129-132
+ * A row's chain is steps[r * max_steps ...] up to the first op < 0.  out_dtype B2A_IN_F32 gives y_aug;
+ * B2A_IN_I16 quantises it the way soundfile writes PCM_16 (lrintf(x * 32768), saturated) — the samples
+ * Stage 2 reads back after the reference's WAV round trip.  time_stretch / pitch_shift / pdm_hiss are not built. */
+#define B2A_AUG_END      -1
+#define B2A_AUG_GAIN      0
+#define B2A_AUG_NOISE     1
+#define B2A_AUG_ROLL      2
+#define B2A_AUG_POLARITY  3
+typedef struct b2a_aug_step {
+    int32_t op;          /* B2A_AUG_*                                   */
+    float   a;           /* gain / noise amplitude (float32 of the draw) */
+    int32_t shift;       /* roll: int(uniform * len)                     */
+    int32_t reserved;
+    int64_t noise_off;   /* element offset of this step's noise row      */
+} b2a_aug_step;
+int b2a_augment_host(int32_t device, const void* src, int32_t src_dtype, int64_t src_elems, const int64_t* src_off,
+                     const int32_t* lengths, const int64_t* out_off, int64_t n_out, const b2a_aug_step* steps,
+                     int32_t max_steps, const float* noise, int64_t noise_elems, void* out, int32_t out_dtype,
+                     int64_t out_elems);
+/* Device variant: every pointer is a device pointer on the current device; asynchronous on `stream`. */
+int b2a_augment_device(const void* d_src, int32_t src_dtype, const int64_t* d_src_off, const int32_t* d_lengths,
+                       const int64_t* d_out_off, int64_t n_out, int32_t max_len, const b2a_aug_step* d_steps,
+                       int32_t max_steps, const float* d_noise, void* d_out, int32_t out_dtype, void* stream);
+
 /* Number of CUDA kernel launches the last b2a_run_* call on this handle enqueued. */
 int64_t b2a_last_launch_count(const b2a_handle* h);
 
