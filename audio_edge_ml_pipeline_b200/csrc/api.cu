@@ -82,7 +82,7 @@ struct b2a_handle {
     int* d_off4 = nullptr;
     int* d_order = nullptr;
     int mel_wpad = 0;
-    bool use512 = false;
+    bool use512 = false, use1024 = false;
     float* d_dct = nullptr;
     float* d_inter = nullptr;
     int grid_cap = 0;
@@ -228,7 +228,9 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
         if (h->mel.w.empty()) h->mel.w.push_back(0.f);
         CU_TRY_H(upload(h->mel.w, &h->d_w));
         h->grid_cap = h->sm_count * b2a::front_ctas_per_sm(h->log2nc);
-        if (n_fft == 512 && (cfg->hop_length % 2) == 0) {
+        const bool try512 = n_fft == 512 && (cfg->hop_length % 2) == 0;
+        const bool try1024 = n_fft == 1024 && b2a::logmel1024_supports(cfg->hop_length, mfcc ? cfg->n_mfcc : 0);
+        if (try512 || try1024) {
             // tables of the specialised kernel: bands padded to float4 groups, |X|^2 -> 4|X|^2 folded
             // into the weights (x0.25 is exact), bands dealt to the mel warps in snake order by size
             std::vector<float> wq;
@@ -260,9 +262,11 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
                 for (int v : order) { if (seen[v]++) perm = false; }
                 if (!perm) order = idx;
             }
+            if (try1024) order = idx;        // 1024 kernel: descending width, neighbours share a warp's two halves
             h->mel_wpad = (int)wq.size();
-            const size_t smem512 = b2a::logmel512_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad,
-                                                             cfg->input_dtype == B2A_IN_I16, mfcc ? cfg->n_mfcc : 0);
+            const size_t smem512 = try512
+                ? b2a::logmel512_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad, cfg->input_dtype == B2A_IN_I16, mfcc ? cfg->n_mfcc : 0)
+                : b2a::logmel1024_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad, cfg->input_dtype == B2A_IN_I16, mfcc ? cfg->n_mfcc : 0);
             const bool fits = smem512 <= (size_t)prop.sharedMemPerBlockOptin;
             if (fits) {
                 CU_TRY_H(upload(wq, &h->d_wq));
@@ -270,7 +274,8 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
                 CU_TRY_H(upload(cnt4, &h->d_cnt4));
                 CU_TRY_H(upload(off4, &h->d_off4));
                 CU_TRY_H(upload(order, &h->d_order));
-                h->use512 = true;
+                h->use512 = try512;
+                h->use1024 = try1024;
                 h->grid_cap = h->sm_count * b2a::logmel512_ctas_per_sm();
             }
         }
@@ -334,6 +339,7 @@ static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, 
     const bool i16 = h->cfg.input_dtype == B2A_IN_I16;
     const int kind = h->cfg.kind == B2A_KIND_MFCC ? 1 : 0;
     if (h->use512) CU_TRY(b2a::launch_logmel512(p, i16, kind, grid, st));
+    else if (h->use1024) CU_TRY(b2a::launch_logmel1024(p, i16, kind, grid, st));
     else CU_TRY(b2a::launch_front(p, h->log2nc, i16, kind, grid, st));
     *launches += 1;
     return B2A_OK;

@@ -23,8 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
-#include <cstring>
-#include <mutex>
+#include <cstdlib>
 #include <type_traits>
 
 namespace b2a {
@@ -159,7 +158,7 @@ __global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
     // pipe only carries the samples.
     const int lb = tid * kDecR + (kDecHalf - 1);     // local index of the pair (B[m_0], A[m_0]) of output r = 0
 #ifndef B2A_AB_DECLVL
-#define B2A_AB_DECLVL 0
+#define B2A_AB_DECLVL 1
 #endif
 #if B2A_AB_DECLVL == 0
     float2 acc2[kDecR];
@@ -271,17 +270,21 @@ __global__ void __launch_bounds__(kDecThreads, 4) cqt_decimate_kernel(
 
 // ------------------------------------------------------------------------------------------
 // All octaves of a chunk in one launch: time-domain wavelet bank.
-//   grid = (frame blocks of 256, octaves * row blocks of 12, clips), 128 threads.
-//   Per 64-sample slice of the N-sample kernels the CTA stages an im2col tile [64 n][256 frames] of the
+//   grid = (frame blocks of 256, octaves * row blocks of 12, clips), 64 threads = 2 warps.
+//   Per 32-sample slice of the N-sample kernels the CTA stages an im2col tile [32 n][256 frames] of the
 //   octave's signal (16-byte chunks XOR-swizzled by row: the transposing stores spread over the banks,
-//   the float4 reads stay conflict-free) and the slice's coefficients [64 n][12 rows] (re, im); a thread
-//   owns 4 consecutive frames x 6 rows: per n one 128-bit sample load, three 128-bit broadcast coefficient
-//   loads and 24 packed FFMA2 (acc(re, im) += x * (b_re, b_im)).
+//   the float4 reads stay conflict-free) and the slice's coefficients [32 n][12 rows] (re, im).  Warp w
+//   owns rows 6 w .. 6 w + 5 of the block; a lane owns frames 4 l .. 4 l + 3 and 128 + 4 l .. + 3: per n
+//   two 128-bit sample loads, three 128-bit broadcast coefficient loads and 48 packed FFMA2
+//   (acc(re, im) += x * (b_re, b_im)) — a broadcast 128-bit load still returns 512 B to the register
+//   file (4 cycles of the 128 B/cycle shared-memory pipe), so 8 frames per lane are what keeps the FMA
+//   pipe (24 cycles per step) ahead of the load pipe (20).  The loads that fill a tile are issued eight
+//   deep per thread; 6 CTAs per SM overlap one CTA's staging with the others' arithmetic.
 // ------------------------------------------------------------------------------------------
-constexpr int kBankThreads = 128;
-constexpr int kBankFrames = 256;             // frames per CTA: 2 warps x 32 lanes x 4
-constexpr int kBankRows = 12;                // output rows (bins) per CTA: 2 thread groups x 6
-constexpr int kBankSlice = 64;               // kernel samples per staged slice
+constexpr int kBankThreads = 64;
+constexpr int kBankFrames = 256;             // frames per CTA: 32 lanes x 8
+constexpr int kBankRows = 12;                // output rows (bins) per CTA: 2 warps x 6
+constexpr int kBankSlice = 32;               // kernel samples per staged slice
 constexpr size_t kBankSmem = (size_t)kBankSlice * kBankFrames * 4 + (size_t)kBankSlice * kBankRows * 8 + 64 * 4;
 
 struct BankOct {
@@ -297,10 +300,10 @@ struct BankParams {
     unsigned int* clip_max; unsigned int* clip_min;
 };
 
-__global__ void __launch_bounds__(kBankThreads, 3) cqt_bank_kernel(const __grid_constant__ BankParams p) {
+__global__ void __launch_bounds__(kBankThreads, 6) cqt_bank_kernel(const __grid_constant__ BankParams p) {
     extern __shared__ __align__(16) unsigned char bank_smem[];
-    float* const s_tile = reinterpret_cast<float*>(bank_smem);                                   // [64][256] swizzled
-    float2* const s_coef = reinterpret_cast<float2*>(bank_smem + (size_t)kBankSlice * kBankFrames * 4);   // [64][12]
+    float* const s_tile = reinterpret_cast<float*>(bank_smem);                                   // [32][256] swizzled
+    float2* const s_coef = reinterpret_cast<float2*>(bank_smem + (size_t)kBankSlice * kBankFrames * 4);   // [32][12]
     float* const s_red = reinterpret_cast<float*>(s_coef + kBankSlice * kBankRows);
 
     // which (octave, row block) this CTA serves
@@ -312,82 +315,81 @@ __global__ void __launch_bounds__(kBankThreads, 3) cqt_bank_kernel(const __grid_
     }
     const BankOct& o = p.oct[oi];
     const int N = o.n_fft, hop = o.hop, L = o.in_len;
+    const bool i16 = o.in_i16 != 0;
     const size_t clip = blockIdx.z;
     const int t0 = blockIdx.x * kBankFrames;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int fgrp = warp >> 1;                  // which 128 frames of the block
-    const int rgrp = warp & 1;                   // which 6 of the 12 rows
-    const unsigned char* const base = (const unsigned char*)o.in + clip * (size_t)o.in_stride * (o.in_i16 ? 2 : 4);
+    const int tid = threadIdx.x, lane = tid & 31, rgrp = tid >> 5;
+    const unsigned char* const base = (const unsigned char*)o.in + clip * (size_t)o.in_stride * (i16 ? 2 : 4);
     const float2* const coef = o.coef + (size_t)rb * N * kBankRows;
 
-    float2 acc[4][6];
+    float2 acc[8][6];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int b = 0; b < 6; ++b) acc[i][b] = make_float2(0.f, 0.f);
 
     const int nvalid = min(kBankFrames, p.n_frames - t0);       // frames of this block inside the clip
+    const bool vec4 = !i16 && (hop & 3) == 0 && ((N / 2) & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+    const int n_items = nvalid * (kBankSlice / 4);              // item = (frame f, 4 consecutive n), frame-major
     for (int n0 = 0; n0 < N; n0 += kBankSlice) {
         __syncthreads();                                       // the previous slice has been consumed
-        // ---- stage coefficients of this slice: contiguous copy ------------------------------------------
         for (int i = tid; i < kBankSlice * kBankRows; i += kBankThreads) s_coef[i] = coef[(size_t)n0 * kBankRows + i];
-        // ---- stage the im2col tile: item = (frame f, 4 consecutive n) -----------------------------------
-        // 16 items per frame; lanes walk n fastest so that global reads are contiguous runs of 64 samples
-        for (int it = tid; it < kBankFrames * (kBankSlice / 4); it += kBankThreads) {
-            const int f = it >> 4, q = it & 15;
-            const int n = 4 * q;
-            if (f >= nvalid) continue;               // frames past the clip: their accumulators are never stored
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            {
-                const int s0 = (t0 + f) * hop + n0 + n - N / 2;        // sample index of (f, n0 + n)
-                if (s0 >= 0 && s0 + 4 <= L) {
-                    if (o.in_i16) {
-                        const int16_t* ps = reinterpret_cast<const int16_t*>(base) + s0;
+        // ---- im2col tile: eight loads in flight per thread, then the transposing stores --------------------
+        // Interior items of a float32 octave whose rows start on 16-byte boundaries (every decimated signal
+        // with hop % 4 == 0) take one 128-bit load; clip edges, the int16 top octave and odd geometries take
+        // the element-wise path.  The choice per item is two compares; the index arithmetic is shared.
+        constexpr int kB = 8;
+        const int sbase = t0 * hop + n0 - N / 2;                // sample index of (f = 0, n = n0)
+#pragma unroll 1
+        for (int it0 = tid; it0 < n_items; it0 += kB * kBankThreads) {
+            float4 v[kB];
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) v[e] = __int2float_rn((int)__ldg(ps + e)) * (1.0f / 32768.0f);
-                    } else {
-                        const float* ps = reinterpret_cast<const float*>(base) + s0;
-                        if ((reinterpret_cast<uintptr_t>(ps) & 15) == 0) {
-                            const float4 x = __ldg(reinterpret_cast<const float4*>(ps));
-                            v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-                        } else {
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) v[e] = __ldg(ps + e);
-                        }
-                    }
+            for (int u = 0; u < kB; ++u) {
+                const int it = it0 + u * kBankThreads;
+                const int f = it >> 3, q = it & 7;
+                const int s0 = sbase + f * hop + 4 * q;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (it >= n_items) continue;
+                if (vec4 && s0 >= 0 && s0 + 4 <= L) {
+                    v[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + s0));
                 } else {
+                    float e4[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int s1 = s0 + e;
+                        e4[e] = 0.f;
                         if (s1 >= 0 && s1 < L)
-                            v[e] = o.in_i16 ? __int2float_rn((int)reinterpret_cast<const int16_t*>(base)[s1]) * (1.0f / 32768.0f)
-                                            : reinterpret_cast<const float*>(base)[s1];
+                            e4[e] = i16 ? (float)reinterpret_cast<const int16_t*>(base)[s1] * (1.0f / 32768.0f)
+                                        : reinterpret_cast<const float*>(base)[s1];
                     }
+                    v[u] = make_float4(e4[0], e4[1], e4[2], e4[3]);
                 }
             }
-            // element (n, f) lives at row n, 16-byte chunk ((f >> 2) ^ swz(n)), word f & 3
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int r = n + e;
-                const int chunk = (f >> 2) ^ ((r >> 2) & 7);
-                s_tile[r * kBankFrames + chunk * 4 + (f & 3)] = v[e];
+            for (int u = 0; u < kB; ++u) {
+                const int it = it0 + u * kBankThreads;
+                if (it >= n_items) continue;
+                const int f = it >> 3, q = it & 7;
+                // element (n = 4 q + e, f) lives at row n, 16-byte chunk ((f >> 2) ^ q), word f & 3
+                float* d = s_tile + (4 * q) * kBankFrames + (((f >> 2) ^ q) << 2) + (f & 3);
+                d[0] = v[u].x; d[kBankFrames] = v[u].y; d[2 * kBankFrames] = v[u].z; d[3 * kBankFrames] = v[u].w;
             }
         }
         __syncthreads();
-        // ---- 64 steps: 1 sample load (4 frames), 3 coefficient loads (6 rows), 24 FFMA2 --------------------
+        // ---- 32 steps: 2 sample loads (8 frames), 3 coefficient loads (6 rows), 48 FFMA2 -------------------
         const float4* const tile4 = reinterpret_cast<const float4*>(s_tile);
         const float4* const c4 = reinterpret_cast<const float4*>(s_coef) + rgrp * 3;
-        const int my_chunk = fgrp * 32 + lane;
-#pragma unroll 4
+#pragma unroll 2
         for (int r = 0; r < kBankSlice; ++r) {
-            const int chunk = my_chunk ^ ((r >> 2) & 7);
-            const float4 x = tile4[r * (kBankFrames / 4) + chunk];
+            const int sw = (r >> 2) & 7;               // (= q of the staging loop)
+            const float4 xa = tile4[r * (kBankFrames / 4) + (lane ^ sw)];
+            const float4 xb = tile4[r * (kBankFrames / 4) + 32 + (lane ^ sw)];
             const float4 ca = c4[r * (kBankRows / 2)], cb = c4[r * (kBankRows / 2) + 1], cc = c4[r * (kBankRows / 2) + 2];
             const float2 cf[6] = {make_float2(ca.x, ca.y), make_float2(ca.z, ca.w), make_float2(cb.x, cb.y),
                                   make_float2(cb.z, cb.w), make_float2(cc.x, cc.y), make_float2(cc.z, cc.w)};
-            const float xs[4] = {x.x, x.y, x.z, x.w};
+            const float xs[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int b = 0; b < 6; ++b) acc[i][b] = __ffma2_rn(make_float2(xs[i], xs[i]), cf[b], acc[i][b]);
         }
@@ -403,8 +405,8 @@ __global__ void __launch_bounds__(kBankThreads, 3) cqt_bank_kernel(const __grid_
         const float sc = p.inv_sqrt_len[row];
         float* const orow = p.out + clip * (size_t)p.out_stride + (size_t)row * p.n_frames;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int t = t0 + fgrp * 128 + 4 * lane + i;
+        for (int i = 0; i < 8; ++i) {
+            const int t = t0 + (i >> 2) * 128 + 4 * lane + (i & 3);
             if (t < p.n_frames) {
                 const float mag = sqrtf(acc[i][b].x * acc[i][b].x + acc[i][b].y * acc[i][b].y) * sc;
                 orow[t] = mag;
@@ -418,142 +420,11 @@ __global__ void __launch_bounds__(kBankThreads, 3) cqt_bank_kernel(const __grid_
         vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, sft));
         vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, sft));
     }
-    if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
-    __syncthreads();
-    if (tid == 0) {
-        for (int w = 1; w < kBankThreads / 32; ++w) { vmax = fmaxf(vmax, s_red[w]); vmin = fminf(vmin, s_red[32 + w]); }
-        atomicMax(p.clip_max + clip, __float_as_uint(vmax));     // magnitudes are >= 0
-        atomicMin(p.clip_min + clip, __float_as_uint(vmin));
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// The same bank with the coefficients in the kernel's PARAMETER block (constant bank 0): they reach
-// the FFMA2s through uniform registers (LDCU.64), not through the shared-memory pipe, which then only
-// carries samples.  (With shared-memory coefficients every broadcast 128-bit load still returns 512 B
-// to the register file — 4 cycles of the 128 B/cycle pipe — and the kernel above is LSU-bound at
-// 27 % of the FFMA2 rate.)  A parameter block holds one table of <= 3072 coefficients (N = 256, 12
-// rows); octaves whose tables are equal up to a power of two — every other octave of a cqt, since the
-// wavelets depend on f / sr only and the per-octave scale is sqrt(2)^o — share a launch.
-//   grid = (frame blocks of 256, octaves of the group, clips), 64 threads; thread = 4 frames
-//   (lane + 32 i + 128 warp) x 12 rows; per n: 4 conflict-free sample loads, 12 LDCU.64, 48 FFMA2.
-//   Tile [256 frames][64 n] is a plain copy of each frame's slice (row pitch 65 words).
-// ------------------------------------------------------------------------------------------
-constexpr int kFastThreads = 64;
-constexpr int kFastFrames = 256;
-constexpr int kFastPitch = kBankSlice + 1;
-constexpr int kFastMaxCoef = 3072;
-constexpr size_t kFastSmem = (size_t)kFastFrames * kFastPitch * 4 + 64 * 4;
-
-struct FastOct {
-    const void* in; long long in_stride; int in_len; int in_i16;
-    int hop, n_rows, row0; float scale;      // scale: the power of two this octave's table is of the group's
-};
-struct FastParams {
-    float2 coef[kFastMaxCoef];               // [n][12] (re, im)
-    FastOct oct[8];
-    int n_fft, n_frames;
-    const float* inv_sqrt_len;
-    float* out; long long out_stride;
-    unsigned int* clip_max; unsigned int* clip_min;
-};
-
-__global__ void __launch_bounds__(kFastThreads, 3) cqt_bank_fast_kernel(const __grid_constant__ FastParams p) {
-    extern __shared__ __align__(16) unsigned char bank_smem[];
-    float* const s_tile = reinterpret_cast<float*>(bank_smem);                       // [256][65]
-    float* const s_red = s_tile + kFastFrames * kFastPitch;
-    const FastOct& o = p.oct[blockIdx.y];
-    const int N = p.n_fft, hop = o.hop, L = o.in_len;
-    const size_t clip = blockIdx.z;
-    const int t0 = blockIdx.x * kFastFrames;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned char* const base = (const unsigned char*)o.in + clip * (size_t)o.in_stride * (o.in_i16 ? 2 : 4);
-
-    float2 acc[4][12];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int b = 0; b < 12; ++b) acc[i][b] = make_float2(0.f, 0.f);
-
-    const int nvalid = min(kFastFrames, p.n_frames - t0);
-    const float* const xrow = s_tile + (warp * 128 + lane) * kFastPitch;            // frame lane + 128 warp (+ 32 i)
-    for (int n0 = 0; n0 < N; n0 += kBankSlice) {
-        __syncthreads();
-        for (int it = tid; it < kFastFrames * (kBankSlice / 4); it += kFastThreads) {
-            const int f = it >> 4, n = 4 * (it & 15);
-            if (f >= nvalid) break;                                  // (items are frame-major: nothing valid follows)
-            float v[4] = {0.f, 0.f, 0.f, 0.f};
-            const int s0 = (t0 + f) * hop + n0 + n - N / 2;
-            if (s0 >= 0 && s0 + 4 <= L) {
-                if (o.in_i16) {
-                    const int16_t* ps = reinterpret_cast<const int16_t*>(base) + s0;
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) v[e] = __int2float_rn((int)__ldg(ps + e)) * (1.0f / 32768.0f);
-                } else {
-                    const float* ps = reinterpret_cast<const float*>(base) + s0;
-                    if ((reinterpret_cast<uintptr_t>(ps) & 15) == 0) {
-                        const float4 x = __ldg(reinterpret_cast<const float4*>(ps));
-                        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) v[e] = __ldg(ps + e);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int s1 = s0 + e;
-                    if (s1 >= 0 && s1 < L)
-                        v[e] = o.in_i16 ? __int2float_rn((int)reinterpret_cast<const int16_t*>(base)[s1]) * (1.0f / 32768.0f)
-                                        : reinterpret_cast<const float*>(base)[s1];
-                }
-            }
-            float* d = s_tile + f * kFastPitch + n;
-            d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; d[3] = v[3];
-        }
-        __syncthreads();
-#pragma unroll 2
-        for (int r = 0; r < kBankSlice; ++r) {
-            const float x0 = xrow[r], x1 = xrow[32 * kFastPitch + r], x2 = xrow[64 * kFastPitch + r], x3 = xrow[96 * kFastPitch + r];
-            const float2* c = p.coef + (n0 + r) * 12;                // uniform: constant bank -> uniform registers
-#pragma unroll
-            for (int b = 0; b < 12; ++b) {
-                const float2 cf = c[b];
-                acc[0][b] = __ffma2_rn(make_float2(x0, x0), cf, acc[0][b]);
-                acc[1][b] = __ffma2_rn(make_float2(x1, x1), cf, acc[1][b]);
-                acc[2][b] = __ffma2_rn(make_float2(x2, x2), cf, acc[2][b]);
-                acc[3][b] = __ffma2_rn(make_float2(x3, x3), cf, acc[3][b]);
-            }
-        }
-    }
-    float vmax = 0.f, vmin = 3.0e38f;
-#pragma unroll
-    for (int b = 0; b < 12; ++b) {
-        if (b >= o.n_rows) continue;
-        const int row = o.row0 + b;
-        const float sc = p.inv_sqrt_len[row] * o.scale;              // (power of two: exact)
-        float* const orow = p.out + clip * (size_t)p.out_stride + (size_t)row * p.n_frames;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int t = t0 + warp * 128 + 32 * i + lane;
-            if (t < p.n_frames) {
-                const float mag = sqrtf(acc[i][b].x * acc[i][b].x + acc[i][b].y * acc[i][b].y) * sc;
-                orow[t] = mag;
-                vmax = fmaxf(vmax, mag);
-                vmin = fminf(vmin, mag);
-            }
-        }
-    }
-#pragma unroll
-    for (int sft = 16; sft > 0; sft >>= 1) {
-        vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, sft));
-        vmin = fminf(vmin, __shfl_xor_sync(0xffffffffu, vmin, sft));
-    }
-    if (lane == 0) { s_red[warp] = vmax; s_red[32 + warp] = vmin; }
+    if (lane == 0) { s_red[rgrp] = vmax; s_red[32 + rgrp] = vmin; }
     __syncthreads();
     if (tid == 0) {
         vmax = fmaxf(vmax, s_red[1]); vmin = fminf(vmin, s_red[33]);
-        atomicMax(p.clip_max + clip, __float_as_uint(vmax));
+        atomicMax(p.clip_max + clip, __float_as_uint(vmax));     // magnitudes are >= 0
         atomicMin(p.clip_min + clip, __float_as_uint(vmin));
     }
 }
@@ -635,8 +506,7 @@ int cqt_device_init(const CqtPlan& plan, const b2a_config& cfg, int sm_count, si
     if (plan.n_octaves > 12) { *err = "cqt: more than 12 octaves"; return B2A_EINVAL; }
     if (kBankSmem > smem_optin) { *err = "cqt: wavelet-bank tile exceeds shared memory"; return B2A_EINVAL; }
     CQ_TRY(cudaFuncSetAttribute(cqt_bank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBankSmem));
-    CQ_TRY(cudaFuncSetAttribute(cqt_bank_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem));
-    dev->fast.clear(); dev->fast_ok = kFastSmem <= smem_optin;
+
     dev->oct.resize(plan.n_octaves);
     size_t cur_off = plan.n_early ? dev->early_offs.back() : (size_t)-1;   // (size_t)-1: the input itself
     for (int i = 0; i < plan.n_octaves; ++i) {
@@ -672,32 +542,6 @@ int cqt_device_init(const CqtPlan& plan, const b2a_config& cfg, int sm_count, si
             }
             od.n_blocks = n_blocks;
             CQ_TRY(up(coef, &od.coef));
-            // fast path: does this table equal an earlier one up to a power of two?
-            if (n_blocks == 1 && (size_t)N * kBankRows <= (size_t)kFastMaxCoef && dev->fast_ok) {
-                bool placed = false;
-                for (auto& g : dev->fast) {
-                    if (g.table.size() != coef.size()) continue;
-                    float ratio = 0.f;
-                    for (size_t q = 0; q < coef.size() && ratio == 0.f; ++q)
-                        if (g.table[q].x != 0.f && coef[q].x != 0.f) ratio = coef[q].x / g.table[q].x;
-                    int ex = 0;
-                    if (!(ratio > 0.f) || std::frexp(ratio, &ex) != 0.5f) continue;
-                    bool same = true;
-                    for (size_t q = 0; q < coef.size() && same; ++q)
-                        same = coef[q].x == g.table[q].x * ratio && coef[q].y == g.table[q].y * ratio;
-                    if (!same) continue;
-                    g.octaves.push_back(i); g.scales.push_back(ratio);
-                    placed = true;
-                    break;
-                }
-                if (!placed) {
-                    CqtFastGroup g;
-                    g.table = coef; g.octaves.push_back(i); g.scales.push_back(1.0f);
-                    dev->fast.push_back(std::move(g));
-                }
-            } else {
-                dev->fast_ok = false;
-            }
         }
         if (o.decimate_after && i + 1 < plan.n_octaves) {
             cur_off = off;
@@ -705,7 +549,10 @@ int cqt_device_init(const CqtPlan& plan, const b2a_config& cfg, int sm_count, si
         }
     }
     dev->scratch_per_clip = off;
+    // Clips per pass of the cascade.  The decimated signals of a pass are written once and read twice (next
+    // decimation, wavelet bank): a pass whose scratch fits the 126 MB L2 keeps those reads out of HBM.
     dev->chunk_clips = 1024;
+    if (const char* e = std::getenv("B2A_CQT_CHUNK")) { const int v = std::atoi(e); if (v >= 1 && v <= 65535) dev->chunk_clips = v; }
     if (off) CQ_TRY(cudaMalloc((void**)&dev->scratch, dev->chunk_clips * off * sizeof(float)));
     CQ_TRY(cudaMalloc((void**)&dev->clip_max, dev->chunk_clips * sizeof(unsigned int)));
     CQ_TRY(cudaMalloc((void**)&dev->clip_min, dev->chunk_clips * sizeof(unsigned int)));
@@ -755,30 +602,7 @@ int cqt_run(const CqtPlan& plan, const b2a_config& cfg, CqtDevice* dev, const vo
         bp.inv_sqrt_len = dev->inv_sqrt_len;
         bp.out = out; bp.out_stride = (long long)out_stride;
         bp.clip_max = dev->clip_max; bp.clip_min = dev->clip_min;
-        bool fast = dev->fast_ok && !dev->fast.empty();
-        for (const auto& g : dev->fast) fast = fast && g.octaves.size() <= 8;
-        if (fast) {
-            static FastParams fp;                                   // 25 KB: not on the stack
-            static std::mutex fp_mu;
-            std::lock_guard<std::mutex> guard(fp_mu);
-            for (const auto& g : dev->fast) {
-                std::memcpy(fp.coef, g.table.data(), g.table.size() * sizeof(float2));
-                for (size_t q = 0; q < g.octaves.size(); ++q) {
-                    const BankOct& bo = bp.oct[g.octaves[q]];
-                    FastOct& fo = fp.oct[q];
-                    fo.in = bo.in; fo.in_stride = bo.in_stride; fo.in_len = bo.in_len; fo.in_i16 = bo.in_i16;
-                    fo.hop = bo.hop; fo.n_rows = bo.n_rows; fo.row0 = bo.row0; fo.scale = g.scales[q];
-                }
-                fp.n_fft = bp.oct[g.octaves[0]].n_fft; fp.n_frames = nfr;
-                fp.inv_sqrt_len = dev->inv_sqrt_len;
-                fp.out = out; fp.out_stride = (long long)out_stride;
-                fp.clip_max = dev->clip_max; fp.clip_min = dev->clip_min;
-                const dim3 grid((nfr + kFastFrames - 1) / kFastFrames, (unsigned)g.octaves.size(), nb);
-                cqt_bank_fast_kernel<<<grid, kFastThreads, kFastSmem, st>>>(fp);     // parameters are copied at launch
-                CQ_TRY(cudaGetLastError());
-                ++*launches;
-            }
-        } else {
+        {
             const dim3 grid((nfr + kBankFrames - 1) / kBankFrames, n_rb, nb);
             cqt_bank_kernel<<<grid, kBankThreads, kBankSmem, st>>>(bp);
             CQ_TRY(cudaGetLastError());

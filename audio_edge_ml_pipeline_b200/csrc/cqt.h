@@ -17,16 +17,8 @@ struct CqtOctaveDev {
     size_t sig_off = 0;        // float offset of this octave's signal inside a clip's scratch
 };
 
-// octaves whose time-domain tables are equal up to a power of two share one launch of the fast bank kernel
-struct CqtFastGroup {
-    std::vector<float2> table;         // [n_fft][12] (re, im) of the group's first octave
-    std::vector<int> octaves;          // plan indices
-    std::vector<float> scales;         // table_o == table * scales[o], powers of two
-};
-
 struct CqtDevice {
-    std::vector<CqtFastGroup> fast;    // empty: the generic (shared-memory coefficient) kernel runs
-    bool fast_ok = true;
+
     int64_t chunk_clips = 0;
     size_t scratch_per_clip = 0;       // floats
     float* scratch = nullptr;          // [chunk_clips][scratch_per_clip]

@@ -1,0 +1,609 @@
+// logmel1024.cu — n_fft = 1024 fused log-mel / MFCC front end, warp-specialised like logmel512.cu.
+//
+// n_fft 1024 / hop 512 is the reference default of audio_mfcc_seq (deep.py:290-297) and of every
+// non-Nicla experiment (experiments/birdeep_feature_extraction.yaml:31-47).  A 1024-sample frame is the
+// radix-2 combination of two 512-sample real FFTs, one over its even and one over its odd samples:
+//     X[k] = E0[k] + W^k E1[k],   X[512 - k] = conj(E0[k] - W^k E1[k]),   W = exp(-2 pi i / 1024), k = 0..256
+// so the per-frame work is exactly the half-warp machinery of logmel512.cu twice: ONE WARP PER FRAME,
+// half-warp h transforms samples 4q + h and 4q + 2 + h as the packed complex sequence of its 512-sample
+// real FFT (both radix-16 passes in registers, packed FP32), and after the split step the two halves swap
+// one operand per bin through warp shuffles and finish with a twiddle butterfly each.
+//
+// One persistent CTA per SM (640 threads):
+//   * 16 FFT warps (setmaxnreg 104): a tile is 16 frames, one per warp.  Raw PCM comes from the TMA-staged
+//     ring (64-bit shared loads, the half picks its two of the four samples), 4|X|^2 goes to a
+//     [bin pair][frame] power tile.
+//   * 4 mel warps (setmaxnreg 64), warp 0 also the TMA producer.  A tile has 16 frames, so a half-warp
+//     sweeps one band while the other half sweeps the next (lane & 15 = frame): table-driven banded dot
+//     products with 4-bin steps, 10 log10, raw dB to the output / scratch (L2), running max / min.
+//     mel: the clip is normalised in place during the NEXT clip's tiles (prefetched slices).
+//     mfcc: DCT-II of each tile from a [band][frame] dB tile in shared memory, eight coefficient streams
+//     ((mel warp, half) takes coefficients s, s + 8, ...), per-row sums kept per (coefficient, frame lane)
+//     in shared memory; rows are z-scored by the same deferred pass (deep.py:326-328).
+//   * mbarriers only: raw_full (TMA bytes) -> FFT; pow_full (16 arrivals) -> mel; pow_empty (4) -> FFT.
+//
+// Reference arithmetic: deep.py:126-134 (mel), :318-328 (mfcc) via librosa 0.11.0.
+#include "frontend.h"
+#include "fft_core.cuh"
+#include "ws_common.cuh"
+
+#include <cstdint>
+#include <type_traits>
+
+namespace b2a {
+
+namespace {
+
+using namespace ws;
+
+constexpr int kFftWarps = 16, kMelWarps = 4;
+constexpr int kThreads = 32 * (kFftWarps + kMelWarps);
+constexpr int kMelThreads = 32 * kMelWarps;
+constexpr int kFftRegs = 104, kMelRegs = 64;
+constexpr int NFFT = 1024, F = 16;              // frame length (two 512-sample sub-FFTs of 256 complex points), frames per tile
+constexpr int kMaxRaw = 3;
+__host__ __device__ constexpr int nraw(bool i16, bool mfcc) { return i16 ? (mfcc ? 2 : 3) : (mfcc ? 1 : 2); }
+constexpr int NPOW = 2;
+constexpr int XS = 17;                          // exchange row stride (float2), as in logmel512.cu
+constexpr int XSLOT = 16 * XS + 2;
+constexpr int PROW = 2 * F + 4;                 // power tile: row = 2 adjacent bins x (16 frames + 2 pad)
+constexpr int PROWS = 260;                      // bin pairs (0,1)..(512,513) + 3 zero rows for 8-bin padding
+constexpr int kStreams = 2 * kMelWarps;         // mfcc: coefficient streams (mel warp, half)
+
+__device__ __forceinline__ void mel_sync() {
+    asm volatile("bar.sync 1, %0;" ::"n"(kMelThreads) : "memory");
+}
+
+struct Layout {
+    int chunk, raw_bytes, gh;
+    int off_raw, off_xch, off_pow, off_tw2, off_twc, off_melw, off_melk, off_red, off_bar, off_db, off_dct, off_zacc, total;
+};
+
+__host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc) {
+    const bool mfcc = n_mfcc > 0;
+    Layout L;
+    L.chunk = (hop * (F - 1) + NFFT + 7) & ~7;
+    int o = 0;
+    auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
+    L.raw_bytes = (L.chunk * (i16 ? 2 : 4) + 15) & ~15;
+    L.off_raw = take(nraw(i16, mfcc) * L.raw_bytes);
+    L.off_xch = take(2 * kFftWarps * XSLOT * 8);
+    L.off_pow = take(NPOW * PROWS * PROW * 4);
+    L.off_tw2 = take(8 * 16 * 8);                     // split twiddles of the 512-sample sub-FFTs
+    L.off_twc = take(257 * 8);                        // combine twiddles W_1024^k, k = 0..256
+    L.off_melw = take(mel_wpad * 4);
+    L.off_melk = take(n_mels * 16);
+    L.off_red = take((64 + 2 * (mfcc ? n_mfcc : 1)) * 4);   // per-warp max/min, then (mean, 1/sd) per coefficient
+    L.off_bar = take((kMaxRaw + 2 * NPOW) * 8);
+    L.off_db = take(mfcc ? n_mels * F * 4 : 0);       // [n_mels][16] dB tile feeding the in-tile DCT
+    L.off_dct = take(mfcc ? n_mels * n_mfcc * 4 : 0); // DCT-II basis as [band][coefficient]
+    L.gh = (n_mfcc + kStreams - 1) / kStreams;        // coefficients per stream
+    L.off_zacc = take(mfcc ? 3 * n_mfcc * F * 4 : 0); // per (coefficient, frame lane): sum, sum of squares, first value
+    L.total = o;
+    return L;
+}
+
+constexpr int kMaxGh = 8;                              // up to 64 coefficients
+
+template <bool I16, int KIND, bool RAG>
+__global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr bool MFCC = KIND == 1;
+    const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16, MFCC ? p.n_mfcc : 0);
+    float2* const s_xch = reinterpret_cast<float2*>(smem + L.off_xch);
+    float* const s_pow = reinterpret_cast<float*>(smem + L.off_pow);
+    float2* const s_tw2 = reinterpret_cast<float2*>(smem + L.off_tw2);
+    float2* const s_twc = reinterpret_cast<float2*>(smem + L.off_twc);
+    float* const s_melw = reinterpret_cast<float*>(smem + L.off_melw);
+    int4* const s_desc = reinterpret_cast<int4*>(smem + L.off_melk);
+    float* const s_red = reinterpret_cast<float*>(smem + L.off_red);
+    float* const s_zs = s_red + 64;
+    float* const s_db = reinterpret_cast<float*>(smem + L.off_db);
+    float* const s_dct = reinterpret_cast<float*>(smem + L.off_dct);
+    float* const s_zacc = reinterpret_cast<float*>(smem + L.off_zacc);
+    uint64_t* const bar_raw_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+    uint64_t* const bar_pow_full = bar_raw_full + kMaxRaw;
+    uint64_t* const bar_pow_empty = bar_pow_full + NPOW;
+
+    constexpr int NRAW = nraw(I16, MFCC);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hop = p.hop, n_mels = p.n_mels, chunk = L.chunk;
+    using E = typename std::conditional<I16, int16_t, float>::type;
+
+    // ---- per-CTA tables (p.tw = exp(-2 pi i k / 512), p.tw2 = exp(-2 pi i k / 1024)) ---------------------
+    for (int i = tid; i < 128; i += kThreads) {              // split twiddles exp(-i pi (j + 16 r) / 256), two per
+        const int r = i >> 4, jj = i & 15;                   // conflict-free 128-bit load (logmel512.cu layout)
+        s_tw2[(r >> 1) * 32 + jj * 2 + (r & 1)] = p.tw[jj + 16 * r];
+    }
+    for (int i = tid; i < 257; i += kThreads) s_twc[i] = p.tw2[i];
+    for (int i = tid; i < p.mel_wpad; i += kThreads) s_melw[i] = p.mel_wq[i];
+    for (int i = tid; i < n_mels; i += kThreads) {
+        const int m = p.mel_order[i];                        // positions in descending band width: neighbours pair up
+        s_desc[i] = make_int4((p.mel_k0e[m] >> 1) * (PROW / 2), p.mel_cnt4[m], p.mel_off4[m], m);
+    }
+    if constexpr (MFCC) {
+        for (int i = tid; i < n_mels * p.n_mfcc; i += kThreads) {
+            const int k = i % p.n_mfcc, m = i / p.n_mfcc;
+            s_dct[i] = p.dct[(size_t)k * n_mels + m];
+        }
+    }
+    for (int b = 0; b < NPOW; ++b)                           // bins 512..519 of every power tile (512 is rewritten
+        for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[b * PROWS * PROW + 256 * PROW + i] = 0.f;   // per tile, 513.. stay 0)
+    if (tid == 0) {
+        for (int i = 0; i < NRAW; ++i) mbar_init(bar_raw_full + i, 1);
+        for (int i = 0; i < NPOW; ++i) { mbar_init(bar_pow_full + i, kFftWarps); mbar_init(bar_pow_empty + i, kMelWarps); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (blockIdx.x >= p.n_clips) return;
+
+    if (warp < kFftWarps) {
+        // =========================== FFT warps: one frame per warp per tile ===============================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFftRegs));
+        const int j = lane & 15, h = lane >> 4;
+        float2 win[16];
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const int q = j + 16 * t;
+            const float sc = I16 ? (1.0f / 32768.0f) : 1.0f;     // librosa.load's exact 1/32768 rides on the window
+            win[t] = make_float2(__ldg(p.window + 4 * q + h) * sc, __ldg(p.window + 4 * q + 2 + h) * sc);
+        }
+        float2 tw1[15];
+#pragma unroll
+        for (int t = 1; t < 16; ++t) tw1[t - 1] = p.tw[2 * t * j];   // exp(-2 pi i t j / 256)
+        float2* const xs = s_xch + (2 * warp + h) * XSLOT;
+        float2* const x1 = xs + XS * j;
+        float2* const x2 = xs + j;
+        float2* const mst = xs + j;
+        const float2* const mld = xs + (j ? 16 - j : 16);
+        const float4* const t2 = reinterpret_cast<const float4*>(s_tw2) + j;
+        const int sh = h ? 0 : 16;                               // int16: the half's sample of each 32-bit word
+
+        uint32_t it = 0;
+        for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
+            const int nfr = RAG ? 1 + p.rag_len[clip] / hop : p.n_frames;
+            const int tiles = (nfr + F - 1) / F;
+            for (int tile = 0; tile < tiles; ++tile, ++it) {
+                const int t0 = tile * F;
+                const uint32_t rb = it % NRAW, pb = it % NPOW;
+                mbar_wait(bar_raw_full + rb, (it / NRAW) & 1);
+                const E* const cur = reinterpret_cast<const E*>(smem + L.off_raw + rb * L.raw_bytes);
+                float* const pw = s_pow + pb * (PROWS * PROW);
+                const int f = warp;
+                if (t0 + f < nfr) {
+                    float2 v[16];
+                    if constexpr (I16) {
+                        // 64 bits = samples 4q .. 4q+3; this half takes (4q + h, 4q + 2 + h)
+                        const uint32_t ra = smem_u32(reinterpret_cast<const int16_t*>(cur) + f * hop + 4 * j);
+                        // two batches of eight loads: sixteen 64-bit words would hold 32 registers at once
+#define B2A_LDR(T) asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+%3];" : "=r"(rw[(T) & 7].x), "=r"(rw[(T) & 7].y) : "r"(ra), "n"((T) * 128))
+#pragma unroll
+                        for (int hb = 0; hb < 2; ++hb) {
+                            uint2 rw[8];
+                            if (hb == 0) { B2A_LDR(0); B2A_LDR(1); B2A_LDR(2); B2A_LDR(3); B2A_LDR(4); B2A_LDR(5); B2A_LDR(6); B2A_LDR(7); }
+                            else { B2A_LDR(8); B2A_LDR(9); B2A_LDR(10); B2A_LDR(11); B2A_LDR(12); B2A_LDR(13); B2A_LDR(14); B2A_LDR(15); }
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                const float a = __int2float_rn((int)(rw[t].x << sh) >> 16);
+                                const float b = __int2float_rn((int)(rw[t].y << sh) >> 16);
+                                v[8 * hb + t] = __fmul2_rn(make_float2(a, b), win[8 * hb + t]);
+                            }
+                        }
+#undef B2A_LDR
+                    } else {
+                        const float* a = reinterpret_cast<const float*>(cur) + f * hop + 4 * j;
+#pragma unroll
+                        for (int t = 0; t < 16; ++t) {
+                            const float4 q4 = *reinterpret_cast<const float4*>(a + 64 * t);
+                            v[t] = __fmul2_rn(h ? make_float2(q4.y, q4.w) : make_float2(q4.x, q4.z), win[t]);
+                        }
+                    }
+                    Dft<16>::run(v);
+#pragma unroll
+                    for (int t = 0; t < 16; ++t) x1[t] = v[t];
+                    __syncwarp();
+                    v[0] = x2[0];
+#pragma unroll
+                    for (int t = 1; t < 16; ++t) v[t] = cmul(x2[XS * t], tw1[t - 1]);
+                    Dft<16>::run(v);                                   // v[t] = Z_h[j + 16 t]
+                    __syncwarp();
+#pragma unroll
+                    for (int t = 8; t < 16; ++t) mst[(t - 8) * 16] = v[t];
+                    mst[8 * 16] = v[0];                                // "row 16": Z[256] == Z[0] for lane 0
+                    __syncwarp();
+                    float2 Bm[8];
+                    {
+                        const uint32_t ma = smem_u32(mld);
+#define B2A_LDM(R2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" \
+                                 : "=f"(Bm[R2].x), "=f"(Bm[R2].y) : "r"(ma), "n"((7 - (R2)) * 16 * 8))
+                        B2A_LDM(0); B2A_LDM(1); B2A_LDM(2); B2A_LDM(3); B2A_LDM(4); B2A_LDM(5); B2A_LDM(6); B2A_LDM(7);
+#undef B2A_LDM
+                    }
+                    // split step of the sub-FFT, in place: v[r2] = 2 E_h[j + 16 r2], Bm[r2] = 2 E_h[256 - j - 16 r2]
+                    {
+                        const uint32_t ta = smem_u32(t2);
+                        float4 w4[4];
+#define B2A_LDT(P) asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" \
+                                : "=f"(w4[P].x), "=f"(w4[P].y), "=f"(w4[P].z), "=f"(w4[P].w) : "r"(ta), "n"((P) * 16 * 16))
+                        B2A_LDT(0); B2A_LDT(1); B2A_LDT(2); B2A_LDT(3);
+#undef B2A_LDT
+#pragma unroll
+                        for (int r2 = 0; r2 < 8; ++r2) {
+                            const float4 q4 = w4[r2 >> 1];
+                            const float2 w = (r2 & 1) ? make_float2(q4.z, q4.w) : make_float2(q4.x, q4.y);
+                            float2 xk, xnk;
+                            rfft_split(v[r2], Bm[r2], w, xk, xnk);
+                            v[r2] = xk; Bm[r2] = xnk;
+                        }
+                    }
+                    // E_h[128] = conj(Z_h[128]) lives in lane j == 0 only (v[8] is untouched by the split)
+                    const float2 e128 = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
+                    // ---- radix-2 combination of the two halves -------------------------------------------
+                    // half 0 finishes bins k = j + 16 r2 (and 512 - k), half 1 bins k = 256 - j - 16 r2 (and 512 - k):
+                    // each lane hands its partner (lane ^ 16) the operand it does not use itself
+                    mbar_wait(bar_pow_empty + pb, ((it / NPOW) & 1) ^ 1);     // the mel warps are done with this slot
+                    const float2* const wc = s_twc + (h ? 256 - j : j);
+                    float* const pcol = pw + 2 * f;
+#pragma unroll
+                    for (int r2 = 0; r2 < 8; ++r2) {
+                        const float2 send = h ? v[r2] : Bm[r2];
+                        float2 recv;
+                        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
+                        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
+                        const float2 a = h ? recv : v[r2];              // 2 E0[k]
+                        const float2 b = h ? Bm[r2] : recv;             // 2 E1[k]
+                        const int k = h ? 256 - j - 16 * r2 : j + 16 * r2;
+                        const float2 w = h ? wc[-16 * r2] : wc[16 * r2];
+                        float2 x1c, x2c;
+                        bfly_w(a, b, w.x, w.y, x1c, x2c);               // 2 X[k], conj(2 X[512 - k])
+                        pcol[(k >> 1) * PROW + (k & 1)] = x1c.x * x1c.x + x1c.y * x1c.y;       // 4|X|^2: the 1/4 lives
+                        const int kn = 512 - k;                                                // in the mel weights
+                        pcol[(kn >> 1) * PROW + (kn & 1)] = x2c.x * x2c.x + x2c.y * x2c.y;
+                    }
+                    {   // bins 128 and 384 (lane j == 0 of half 0 has both operands after one more exchange)
+                        float2 r128;
+                        r128.x = __shfl_xor_sync(0xffffffffu, e128.x, 16);
+                        r128.y = __shfl_xor_sync(0xffffffffu, e128.y, 16);
+                        if (lane == 0) {
+                            float2 x1c, x2c;
+                            bfly_p(e128, r128, x1c, x2c);               // W^128 = s (1 - i)
+                            pcol[64 * PROW] = x1c.x * x1c.x + x1c.y * x1c.y;
+                            pcol[192 * PROW] = x2c.x * x2c.x + x2c.y * x2c.y;
+                        }
+                    }
+                } else {
+                    // a warp with no frame in this tile still takes its turn on both barriers
+                    mbar_wait(bar_pow_empty + pb, ((it / NPOW) & 1) ^ 1);
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pow_full + pb);
+            }
+        }
+    } else {
+        // =========================== mel warps (warp 0 of them also stages the raw tiles) =========
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMelRegs));
+        const int mw = warp - kFftWarps, mtid = tid - 32 * kFftWarps;
+        const int l16 = lane & 15, par = lane >> 4;
+        constexpr int V = 16 / (int)sizeof(E);
+        const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
+
+        // Stage tile (clip, t0) into raw slot `slot` (same protocol as logmel512.cu: one TMA bulk copy for the
+        // aligned interior, plain stores for the zero padding and the unaligned tail, plain loads otherwise).
+        auto stage = [&](long long clip, int t0, uint32_t slot) {
+            E* const dst = reinterpret_cast<E*>(smem + L.off_raw + slot * L.raw_bytes);
+            uint64_t* const bar = bar_raw_full + slot;
+            const int n = RAG ? p.rag_len[clip] : p.n_samples;
+            const long long e0 = RAG ? p.rag_in_off[clip] : clip * (long long)n;
+            const E* cptr = reinterpret_cast<const E*>(p.clips) + e0;
+            const int c0 = t0 * hop - NFFT / 2;
+            const int lo = c0 < 0 ? 0 : c0;
+            const int hi = (c0 + chunk < n) ? c0 + chunk : n;
+            const int nfr = 1 + n / hop;
+            const int vf = nfr - t0 < F ? nfr - t0 : F;
+            const int need = ((vf - 1) * hop + NFFT + V - 1) & ~(V - 1);      // <= chunk
+            const bool ok = p.pad_mode == 0 && base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
+                            (((lo - c0) & (V - 1)) == 0);
+            const int nb = ok ? ((hi - lo) / V) * V : 0;
+            if (nb == 0) {
+                for (int i = lane; i < need; i += 32) dst[i] = raw_sample<E>(cptr, c0 + i, n, p.pad_mode);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar);
+                return;
+            }
+            const int head = lo - c0, tb = head + nb;
+            const int4 z4 = make_int4(0, 0, 0, 0);
+            for (int i = lane * V; i < head; i += 32 * V) *reinterpret_cast<int4*>(dst + i) = z4;
+            if (tb < need) {
+                if (lane < V) dst[tb + lane] = raw_sample<E>(cptr, c0 + tb + lane, n, 0);
+                for (int i = tb + V + lane * V; i < need; i += 32 * V) *reinterpret_cast<int4*>(dst + i) = z4;
+            }
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                const int cb = (nb < need - head ? nb : need - head) * (int)sizeof(E);
+                mbar_expect_tx(bar, (uint32_t)cb);
+                bulk_g2s(dst + head, cptr + lo, (uint32_t)cb, bar);
+            }
+        };
+        long long pclip = blockIdx.x;
+        int ptile = 0;
+        uint32_t pit = 0;
+        auto stage_next = [&]() {
+            if (pclip >= p.n_clips) return;
+            stage(pclip, ptile * F, pit % NRAW);
+            ++pit;
+            const int pnfr = RAG ? 1 + p.rag_len[pclip] / hop : p.n_frames;
+            if (++ptile * F >= pnfr) { ptile = 0; pclip += gridDim.x; }
+        };
+        if (mw == 0)
+            for (int i = 0; i < NRAW; ++i) stage_next();
+
+        // Deferred rewrite of the PREVIOUS clip during the current clip's tiles (prefetched before the wait for
+        // the power tile): mel = power_to_db(ref=max, top_db) + min-max on float4 slices; mfcc = per-row z-score.
+        constexpr int NPF = 4;                                   // float4 (mel) / floats (mfcc) per thread per tile
+        float4* nq = nullptr;
+        float* nz = nullptr;
+        int nq_n = 0, nq_done = 0;                               // element count (float4 or float), elements rewritten
+        float nq_vmax = 0.f, nq_lo = 0.f, nq_range = 1.f, nq_inv = 1.f, nz_inv = 1.f;
+        auto nrm = [&](float x) {
+            const float num = fmaxf(x - nq_vmax, -p.top_db) - nq_lo;
+            const float q = num * nq_inv;
+            return fmaf(fmaf(-q, nq_range, num), nq_inv, q);     // correctly rounded x / range (peak exactly 1.0)
+        };
+        auto nrm4 = [&](float4 x) { return make_float4(nrm(x.x), nrm(x.y), nrm(x.z), nrm(x.w)); };
+        auto zs1 = [&](float x, int i) {
+            const int k = __float2int_rd(((float)i + 0.5f) * nz_inv);
+            return (x - s_zs[2 * k]) * s_zs[2 * k + 1];
+        };
+        auto nq_finish = [&]() {
+            if constexpr (!MFCC) {
+                for (int i = nq_done + mtid; i < nq_n; i += kMelThreads) nq[i] = nrm4(nq[i]);
+            } else {
+                for (int i = nq_done + mtid; i < nq_n; i += kMelThreads) nz[i] = zs1(nz[i], i);
+            }
+            nq_done = nq_n;
+        };
+
+        uint32_t it = 0;
+        for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
+            const int nfr = RAG ? 1 + p.rag_len[clip] / hop : p.n_frames;
+            const int tiles = (nfr + F - 1) / F;
+            float* const outb = RAG ? p.out + p.rag_out_off[clip]
+                                    : p.out + (size_t)clip * (MFCC ? p.n_mfcc : n_mels) * nfr;
+            float* const inter = MFCC ? p.inter + (size_t)blockIdx.x * n_mels * p.n_frames : outb;
+            float vmax = -3.0e38f, vmin = 3.0e38f;
+            if constexpr (MFCC) {
+                for (int i = mtid; i < 2 * p.n_mfcc * F; i += kMelThreads) s_zacc[i] = 0.f;    // (tile 0 fills the third plane)
+            }
+
+            for (int tile = 0; tile < tiles; ++tile, ++it) {
+                const int t0 = tile * F;
+                const uint32_t pb = it % NPOW;
+                float4 nx[MFCC ? 1 : NPF];
+                float zx[MFCC ? NPF : 1];
+                const bool nq_live = nq_done < nq_n;
+                if (nq_live) {
+#pragma unroll
+                    for (int k = 0; k < NPF; ++k) {
+                        const int i = nq_done + mtid + k * kMelThreads;
+                        if (i < nq_n) {
+                            if constexpr (!MFCC) nx[k] = nq[i]; else zx[k] = nz[i];
+                        }
+                    }
+                }
+                mbar_wait(bar_pow_full + pb, (it / NPOW) & 1);
+                if (mw == 0) stage_next();                         // raw slot it % NRAW is free again
+                // ---- mel bands: lane & 15 = frame, the two halves of the warp take neighbouring bands ----------
+                {
+                    const int t = t0 + l16;
+                    const bool valid = t < nfr;
+                    float* const outp = inter + t;
+                    const float2* pl = reinterpret_cast<const float2*>(s_pow + pb * (PROWS * PROW)) + l16;
+                    for (int pp = mw; 2 * pp < n_mels; pp += kMelWarps) {
+                        const int i = 2 * pp + par;
+                        const int4 d = i < n_mels ? s_desc[i] : make_int4(0, 0, 0, 0);
+                        const int steps = max(d.y, __shfl_xor_sync(0xffffffffu, d.y, 16));
+                        const float2* pr = pl + d.x;
+                        const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 1
+                        for (int q4 = 0; q4 < steps; ++q4) {
+                            if (q4 < d.y) {
+                                const float4 w = wq[q4];
+                                const float2 p0 = pr[0], p1 = pr[PROW / 2];
+                                a0 = fmaf(w.x, p0.x, a0);
+                                a1 = fmaf(w.y, p0.y, a1);
+                                a2 = fmaf(w.z, p1.x, a2);
+                                a3 = fmaf(w.w, p1.y, a3);
+                            }
+                            pr += PROW;
+                        }
+                        if (i < n_mels) {
+                            const float vv = db10((a0 + a1) + (a2 + a3));
+                            if (MFCC) s_db[d.w * F + l16] = vv;
+                            if (valid) {
+                                outp[(size_t)d.w * nfr] = vv;
+                                vmax = fmaxf(vmax, vv);
+                                vmin = fminf(vmin, vv);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_pow_empty + pb);
+                if (nq_live) {
+#pragma unroll
+                    for (int k = 0; k < NPF; ++k) {
+                        const int i = nq_done + mtid + k * kMelThreads;
+                        if (i < nq_n) {
+                            if constexpr (!MFCC) nq[i] = nrm4(nx[k]); else nz[i] = zs1(zx[k], i);
+                        }
+                    }
+                    nq_done += NPF * kMelThreads;
+                    // whatever a tile's share exceeds the prefetched slices goes without prefetch
+                    const int per_tile = MFCC ? p.n_mfcc * F : n_mels * (F / 4);
+                    for (int more = (per_tile + kMelThreads - 1) / kMelThreads - NPF; more > 0; --more) {
+                        const int i = nq_done + mtid;
+                        if (i < nq_n) {
+                            if constexpr (!MFCC) nq[i] = nrm4(nq[i]); else nz[i] = zs1(nz[i], i);
+                        }
+                        nq_done += kMelThreads;
+                    }
+                    if (tile + 1 == tiles) nq_finish();
+                }
+                if constexpr (MFCC) {
+                    // DCT-II of this tile from the dB tile, assuming the top_db clip (known only after the clip's
+                    // last tile) will not engage; checked at clip end.  Stream s = 2 mw + par owns coefficients
+                    // s, s + 8, ...; lane & 15 = frame.  Per band one dB load and gh basis loads (uniform per half).
+                    mel_sync();
+                    const int t = t0 + l16;
+                    const bool valid = t < nfr;
+                    const int s0 = 2 * mw + par;
+                    float a[kMaxGh];
+#pragma unroll
+                    for (int g = 0; g < kMaxGh; ++g) a[g] = 0.f;
+                    const float* dbl = s_db + l16;
+                    const float* bs = s_dct + s0;
+#pragma unroll 2
+                    for (int m = 0; m < n_mels; ++m) {
+                        const float dv = dbl[m * F];
+#pragma unroll
+                        for (int g = 0; g < kMaxGh; ++g)
+                            if (g < L.gh && s0 + kStreams * g < p.n_mfcc) a[g] = fmaf(bs[m * p.n_mfcc + kStreams * g], dv, a[g]);
+                    }
+#pragma unroll
+                    for (int g = 0; g < kMaxGh; ++g) {
+                        const int k = s0 + kStreams * g;
+                        const float first = __shfl_sync(0xffffffffu, a[g], par * 16);   // (outside the per-half condition)
+                        if (g < L.gh && k < p.n_mfcc) {
+                            if (valid) outb[(size_t)k * nfr + t] = a[g];
+                            // running sums about the row's first sample (frame 0 of the clip), per frame lane
+                            float* za = s_zacc + k * F + l16;
+                            if (tile == 0) za[2 * p.n_mfcc * F] = first;
+                            const float dd = valid ? a[g] - za[2 * p.n_mfcc * F] : 0.f;
+                            za[0] += dd;
+                            za[p.n_mfcc * F] = fmaf(dd, dd, za[p.n_mfcc * F]);
+                        }
+                    }
+                    mel_sync();                                    // s_db is rewritten by the next tile
+                }
+            }
+
+            // ---- per-clip reductions (mel warps only) ------------------------------------------------
+            vmax = warp_max(vmax); vmin = warp_min(vmin);
+            if (lane == 0) { s_red[mw] = vmax; s_red[32 + mw] = vmin; }
+            mel_sync();
+            {
+                const float a = (lane < kMelWarps) ? s_red[lane] : -3.0e38f;
+                const float b = (lane < kMelWarps) ? s_red[32 + lane] : 3.0e38f;
+                vmax = warp_max(a); vmin = warp_min(b);
+            }
+            if constexpr (!MFCC) {
+                nq_finish();
+                nq_vmax = vmax;
+                nq_lo = fmaxf(vmin - vmax, -p.top_db);
+                nq_range = (0.0f - nq_lo) + 1e-8f;
+                nq_inv = __frcp_rn(nq_range);
+                const int total = n_mels * nfr;
+                if ((total & 3) == 0 && ((reinterpret_cast<uintptr_t>(inter) & 15) == 0)) {
+                    nq = reinterpret_cast<float4*>(inter);
+                    nq_n = total / 4;
+                    nq_done = 0;
+                } else {
+                    for (int i = mtid; i < total; i += kMelThreads) inter[i] = nrm(inter[i]);
+                    nq_n = nq_done = 0;
+                }
+            } else {
+                float* outc = outb;
+                const float thr = vmax - p.top_db;
+                const bool clipped = vmin < thr;
+                if (clipped) {
+                    // rare: a band fell more than top_db below the clip's peak, so the clipped dB differ from what
+                    // the in-tile DCT saw -> recompute from the raw-dB scratch (L2 resident), 16 frames at a time
+                    for (int t0 = 0; t0 < nfr; t0 += F) {
+                        mel_sync();
+                        for (int i = mtid; i < n_mels * F; i += kMelThreads) {
+                            const int m = i / F, f = i % F, t = t0 + f;
+                            s_db[i] = (t < nfr) ? fmaxf(inter[(size_t)m * nfr + t], thr) : 0.f;
+                        }
+                        mel_sync();
+                        for (int i = mtid; i < p.n_mfcc * F; i += kMelThreads) {
+                            const int k = i / F, f = i % F, t = t0 + f;
+                            float acc = 0.f;
+                            for (int m = 0; m < n_mels; ++m) acc = fmaf(s_dct[m * p.n_mfcc + k], s_db[m * F + f], acc);
+                            if (t < nfr) outc[(size_t)k * nfr + t] = acc;
+                        }
+                    }
+                }
+                nq_finish();                                          // the previous clip's z-score, if any is left
+                mel_sync();                                           // ... by every warp, before s_zs changes
+                const float fn = (float)nfr;
+                if (!clipped) {
+                    // mean and variance from the per-lane running sums; rows rewritten during the next clip's tiles
+                    for (int k = mw; k < p.n_mfcc; k += kMelWarps) {
+                        const float* za = s_zacc + k * F;
+                        float S = lane < F ? za[lane] : 0.f, Q = lane < F ? za[p.n_mfcc * F + lane] : 0.f;
+                        S = warp_sum(S); Q = warp_sum(Q);
+                        if (lane == 0) {
+                            const float md = __fdiv_rn(S, fn);
+                            s_zs[2 * k] = za[2 * p.n_mfcc * F] + md;
+                            s_zs[2 * k + 1] = __fdiv_rn(1.0f, sqrtf(fmaxf(fmaf(-md, md, __fdiv_rn(Q, fn)), 0.f)) + 1e-8f);
+                        }
+                    }
+                    nz = outc;
+                    nz_inv = __fdiv_rn(1.0f, fn);
+                    nq_n = p.n_mfcc * nfr;
+                    nq_done = 0;
+                    mel_sync();
+                    continue;
+                }
+                nq_n = nq_done = 0;
+                mel_sync();
+                for (int k = mw; k < p.n_mfcc; k += kMelWarps) {      // deep.py:326-328, three sweeps over an L2-resident row
+                    float* row = outc + (size_t)k * nfr;
+                    const float x0 = row[0];
+                    float s_ = 0.f;
+                    for (int t = lane; t < nfr; t += 32) s_ += row[t] - x0;
+                    const float mean = x0 + __fdiv_rn(warp_sum(s_), fn);
+                    float ss = 0.f;
+                    for (int t = lane; t < nfr; t += 32) { const float dlt = row[t] - mean; ss = fmaf(dlt, dlt, ss); }
+                    const float sd = sqrtf(__fdiv_rn(warp_sum(ss), fn)) + 1e-8f;
+                    for (int t = lane; t < nfr; t += 32) row[t] = __fdiv_rn(row[t] - mean, sd);
+                }
+            }
+            mel_sync();
+        }
+        nq_finish();
+    }
+}
+
+}  // namespace
+
+size_t logmel1024_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc) {
+    return (size_t)make_layout(hop, n_mels, mel_wpad, i16, n_mfcc).total + 128;
+}
+
+bool logmel1024_supports(int hop, int n_mfcc) {
+    return hop > 0 && (hop % 4) == 0 && n_mfcc <= kStreams * kMaxGh;
+}
+
+template <bool I16, int KIND, bool RAG>
+static cudaError_t launch_k(const FrontParams& p, int grid, size_t smem, cudaStream_t st) {
+    auto k = logmel1024_kernel<I16, KIND, RAG>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k<<<grid, kThreads, smem, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_logmel1024(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st) {
+    const size_t smem = logmel1024_smem_bytes(p.hop, p.n_mels, p.mel_wpad, i16, kind == 1 ? p.n_mfcc : 0);
+    if (p.rag_len) {
+        if (kind == 0) return i16 ? launch_k<true, 0, true>(p, grid, smem, st) : launch_k<false, 0, true>(p, grid, smem, st);
+        return i16 ? launch_k<true, 1, true>(p, grid, smem, st) : launch_k<false, 1, true>(p, grid, smem, st);
+    }
+    if (kind == 0) return i16 ? launch_k<true, 0, false>(p, grid, smem, st) : launch_k<false, 0, false>(p, grid, smem, st);
+    return i16 ? launch_k<true, 1, false>(p, grid, smem, st) : launch_k<false, 1, false>(p, grid, smem, st);
+}
+
+}  // namespace b2a

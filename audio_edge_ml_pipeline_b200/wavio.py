@@ -23,11 +23,13 @@ class AudioDecodeError(RuntimeError):
     pass
 
 
-def _parse_header(buf: memoryview):
+def _parse_header(buf: memoryview, total: Optional[int] = None):
+    """fmt fields and (offset, size) of the data chunk; `total` = file size when `buf` is only its head."""
     if len(buf) < 12 or bytes(buf[0:4]) != b"RIFF" or bytes(buf[8:12]) != b"WAVE":
         raise AudioDecodeError("not a RIFF/WAVE file")
     pos, fmt, data = 12, None, None
     n = len(buf)
+    total = n if total is None else total
     while pos + 8 <= n:
         cid = bytes(buf[pos:pos + 4])
         size = struct.unpack_from("<I", buf, pos + 4)[0]
@@ -38,7 +40,7 @@ def _parse_header(buf: memoryview):
                 tag = struct.unpack_from("<H", buf, body + 24)[0]
             fmt = (tag, ch, sr, align, bits)
         elif cid == b"data":
-            data = (body, min(size, n - body))
+            data = (body, min(size, total - body))
             break
         pos = body + size + (size & 1)
     if fmt is None or data is None:
@@ -50,14 +52,14 @@ def wav_info(path) -> dict:
     """duration / sample_rate / n_channels without decoding (audio_folder_loader.py:76-103)."""
     try:
         import os
+        total = os.path.getsize(path)
         with open(path, "rb") as f:
             head = f.read(4096)                      # canonical headers are 44 bytes; LIST chunks rarely pass 4 KB
             try:
-                (tag, ch, sr, align, bits), (off, size) = _parse_header(memoryview(head))
+                (tag, ch, sr, align, bits), (off, size) = _parse_header(memoryview(head), total)
             except AudioDecodeError:
                 head += f.read((1 << 16) - len(head))
-                (tag, ch, sr, align, bits), (off, size) = _parse_header(memoryview(head))
-        size = min(size, os.path.getsize(path) - off) if size >= len(head) - off else size
+                (tag, ch, sr, align, bits), (off, size) = _parse_header(memoryview(head), total)
         frames = size // max(align, 1)
         return {"duration": frames / sr if sr else 0.0, "sample_rate": int(sr), "n_channels": int(ch)}
     except Exception:

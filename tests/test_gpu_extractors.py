@@ -77,7 +77,7 @@ def test_mfcc_and_cqt_extractors_on_files(tmp_path):
     for k, m in enumerate(fs.metadata):
         y = L.pcm16_to_float(pcm[(m["class_dir"], m["filename"])])
         assert np.abs(fs.features[k] - L.audio_mfcc_seq(y, duration=5.0)).max() <= 1e-3
-        assert np.abs(fc.features[k] - L.audio_cqt(y, duration=5.0)).max() <= 1e-4
+        assert np.abs(fc.features[k] - L.audio_cqt(y, duration=5.0)).max() <= 1.25e-4      # tests/test_gpu_parity.py: CQT_TOL
 
 
 def test_bad_cqt_config_skips_every_sample_like_the_reference(tmp_path, caplog):
