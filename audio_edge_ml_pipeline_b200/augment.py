@@ -7,9 +7,13 @@ number is drawn HERE, with ``np.random.default_rng(seed)`` consumed in the refer
 clip, cyclic shift, polarity, level match) runs in one CUDA kernel per batch (``csrc/augment.cu``); there
 is no CPU path: without the library or a CUDA device :func:`augment_batch` raises.
 
-Not built: ``time_stretch`` / ``pitch_shift`` (librosa phase vocoder, augment.py:105-118) and ``pdm_hiss``
-(length-n FFT noise shaping, :135-167).  A chain naming one of them raises ``NotImplementedError`` up
-front rather than silently dropping the step.
+``pdm_hiss`` (augment.py:135-167) is a noise SOURCE like ``gaussian_noise``: its pink, notched, unit-RMS
+noise row is synthesised on the host next to the draw that feeds it (the same ``np.fft`` calls on the same
+``rng.standard_normal(n)``, hence the same float32 row as the reference), and the device mixes it into the
+clip exactly like white noise (``clip(y + row * amplitude)``).
+
+Not built: ``time_stretch`` / ``pitch_shift`` (librosa phase vocoder, augment.py:105-118).  A chain naming
+one of them raises ``NotImplementedError`` up front rather than silently dropping the step.
 
 Two ways out of Stage 1b:
   * :func:`run` writes the class-per-folder WAV tree the reference writes (PCM16 via soundfile there;
@@ -33,8 +37,8 @@ from . import wavio
 logger = logging.getLogger(__name__)
 
 AUG_END, AUG_GAIN, AUG_NOISE, AUG_ROLL, AUG_POLARITY = -1, 0, 1, 2, 3
-SUPPORTED = ("volume_scale", "gaussian_noise", "time_shift", "polarity_inversion")
-NOT_BUILT = ("time_stretch", "pitch_shift", "pdm_hiss")
+SUPPORTED = ("volume_scale", "gaussian_noise", "time_shift", "polarity_inversion", "pdm_hiss")
+NOT_BUILT = ("time_stretch", "pitch_shift")
 VALID_TYPES = sorted(SUPPORTED + NOT_BUILT)
 
 
@@ -76,8 +80,26 @@ def check_specs(aug_specs: Sequence[dict]) -> None:
             raise NotImplementedError(f"augmentation '{t}' is not built on the GPU path (supported: {list(SUPPORTED)})")
 
 
+def _pink_row(white: np.ndarray, sr: int, notch_freq: float) -> np.ndarray:
+    """The noise row of pdm_hiss (augment.py:147-165): white -> 1/sqrt(f) shaping -> +-2-bin notch -> unit RMS,
+    float32.  Noise synthesis stays with the generator on the host (numpy's own rfft / irfft, the calls the
+    reference makes), so the row is the reference's bit for bit; the device only mixes it in."""
+    n = len(white)
+    fft = np.fft.rfft(white)
+    freqs = np.fft.rfftfreq(n, d=1.0 / sr)
+    freqs[0] = 1.0
+    fft /= np.sqrt(freqs)
+    pink = np.fft.irfft(fft, n=n).astype(np.float32)
+    fft2 = np.fft.rfft(pink)
+    fft2[np.abs(np.fft.rfftfreq(n, d=1.0 / sr) - notch_freq) < (sr / n * 2)] = 0.0
+    pink = np.fft.irfft(fft2, n=n).astype(np.float32)
+    pink /= np.sqrt(np.mean(pink ** 2)) + 1e-9
+    return pink
+
+
 def plan(lengths: Sequence[int], specs_per_clip: Sequence[Sequence[dict]], n_augments: int, seed: int,
-         level_match_db: float = 0.0, include_originals: bool = True, rng: Optional[np.random.Generator] = None):
+         level_match_db: float = 0.0, include_originals: bool = True, rng: Optional[np.random.Generator] = None,
+         sample_rate: int = 16000):
     """Draw every random parameter in the reference's order and lay out the device work.
 
     Clips are taken in the order given (the reference walks classes sorted by name, files in loader
@@ -115,6 +137,12 @@ def plan(lengths: Sequence[int], specs_per_clip: Sequence[Sequence[dict]], n_aug
                         noise_rows.append(rng.standard_normal(n).astype(np.float32))
                         steps[r, k] = (AUG_NOISE, np.float32(amp), 0, 0, noise_pos)
                         noise_pos += n
+                    elif t == "pdm_hiss":
+                        white = rng.standard_normal(n)                   # drawn BEFORE the amplitude (augment.py:146, 165)
+                        noise_rows.append(_pink_row(white, sample_rate, spec.get("notch_freq", 4000.0)))
+                        amp = rng.uniform(spec.get("min_amplitude", 0.02), spec.get("max_amplitude", 0.08))
+                        steps[r, k] = (AUG_NOISE, np.float32(amp), 0, 0, noise_pos)
+                        noise_pos += n
                     elif t == "time_shift":
                         f = spec.get("max_fraction", 0.2)
                         steps[r, k] = (AUG_ROLL, 0.0, int(rng.uniform(-f, f) * n), 0, 0)
@@ -140,7 +168,7 @@ def _run_host(device, src, src_off, lengths, out_off, steps, max_steps, noise, o
 
 def augment_ragged(clips: Sequence[np.ndarray], specs_per_clip, n_augments: int = 4, seed: int = 42,
                    level_match_db: float = 0.0, include_originals: bool = True, out_dtype=np.float32,
-                   device: int = 0, rng: Optional[np.random.Generator] = None) -> list:
+                   device: int = 0, rng: Optional[np.random.Generator] = None, sample_rate: int = 16000) -> list:
     """Clips of any lengths (1-D int16 or float32, one dtype) -> per clip the list
     ``[original (level-matched), copy 1, ..., copy n_augments]`` (originals only when asked for)."""
     if len(clips) == 0:
@@ -148,7 +176,7 @@ def augment_ragged(clips: Sequence[np.ndarray], specs_per_clip, n_augments: int 
     dt = np.int16 if clips[0].dtype == np.int16 else np.float32
     lens = np.array([len(c) for c in clips], dtype=np.int64)
     src_clip, steps, noise, max_steps = plan(lens, specs_per_clip, n_augments, seed, level_match_db,
-                                             include_originals, rng)
+                                             include_originals, rng, sample_rate)
     starts = np.concatenate([[0], np.cumsum(lens)[:-1]]).astype(np.int64)
     src = np.concatenate([np.asarray(c, dtype=dt) for c in clips]) if lens.sum() else np.zeros(0, dt)
     row_len = lens[src_clip].astype(np.int32)
@@ -162,7 +190,7 @@ def augment_ragged(clips: Sequence[np.ndarray], specs_per_clip, n_augments: int 
 
 def augment_batch(clips: np.ndarray, aug_specs, n_augments: int = 4, seed: int = 42, level_match_db: float = 0.0,
                   include_originals: bool = True, out_dtype=np.float32, device: int = 0,
-                  rng: Optional[np.random.Generator] = None) -> np.ndarray:
+                  rng: Optional[np.random.Generator] = None, sample_rate: int = 16000) -> np.ndarray:
     """Equal-length clips ``(N, n)`` int16 / float32 -> ``(N * (1 + n_augments), n)`` in the reference's file
     order: each original (level-matched) followed by its copies.  ``aug_specs`` is one chain for every clip or
     a per-clip list of chains (class overrides, augment.py:337-339).  ``out_dtype=np.int16`` quantises like the
@@ -177,7 +205,7 @@ def augment_batch(clips: np.ndarray, aug_specs, n_augments: int = 4, seed: int =
     if len(per_clip) != n_clips:
         raise ValueError("one augmentation chain per clip expected")
     src_clip, steps, noise, max_steps = plan([n] * n_clips, per_clip, n_augments, seed, level_match_db,
-                                             include_originals, rng)
+                                             include_originals, rng, sample_rate)
     rows = len(src_clip)
     out = np.empty((rows, n), dtype=out_dtype)
     _run_host(device, clips.reshape(-1), np.ascontiguousarray(src_clip * n), np.full(rows, n, np.int32),
@@ -239,8 +267,11 @@ def run(cfg: dict, device: int = 0) -> int:
                 y, sr = wavio.resample_audio(y, sr, int(cfg["sample_rate"]), device), int(cfg["sample_rate"])
             clips.append(np.ascontiguousarray(y, dtype=np.float32))
             rates.append(sr)
+        if len(set(rates)) > 1:
+            raise ValueError(f"class {cname}: files at different rates {sorted(set(rates))}; set sample_rate in the config")
         groups = augment_ragged(clips, [specs] * len(clips), n_aug, seed, float(cfg["level_match_db"]),
-                                include_originals=True, out_dtype=np.float32, device=device, rng=rng)
+                                include_originals=True, out_dtype=np.float32, device=device, rng=rng,
+                                sample_rate=rates[0] if rates else 16000)
         for p_, sr, grp in zip(paths, rates, groups):
             dest = output_dir / cname / p_.name
             if not dest.exists():

@@ -7,8 +7,9 @@
 // whole chain per output sample.  The random numbers are drawn by the HOST with the reference's own
 // generator (numpy default_rng(seed), consumed in the reference's order: augment.py:325) so that outputs
 // are reproducible against the reference bit for bit; the host sends each copy's step list (gain, noise
-// amplitude, shift) and its float32 noise rows.  time_stretch / pitch_shift (librosa phase vocoder) and
-// pdm_hiss (length-n FFT shaping) are not built here.
+// amplitude, shift) and its float32 noise rows — white for gaussian_noise, and for pdm_hiss (:135-167) the
+// pink, notched, unit-RMS row the host synthesises from its draw with numpy's own FFT (noise synthesis stays
+// with the generator; the device mixes).  time_stretch / pitch_shift (librosa phase vocoder) are not built.
 //
 // Arithmetic is kept operation-for-operation with NumPy's float32 (no FMA contraction):
 //   gain      y * float32(gain)

@@ -39,7 +39,6 @@ using namespace ws;
 constexpr int kFftWarps = 16, kMelWarps = 4;
 constexpr int kThreads = 32 * (kFftWarps + kMelWarps);
 constexpr int kMelThreads = 32 * kMelWarps;
-constexpr int kFftRegs = 104, kMelRegs = 64;
 constexpr int NFFT = 1024, F = 16;              // frame length (two 512-sample sub-FFTs of 256 complex points), frames per tile
 constexpr int kMaxRaw = 3;
 __host__ __device__ constexpr int nraw(bool i16, bool mfcc) { return i16 ? (mfcc ? 2 : 3) : (mfcc ? 1 : 2); }
@@ -56,7 +55,7 @@ __device__ __forceinline__ void mel_sync() {
 
 struct Layout {
     int chunk, raw_bytes, gh;
-    int off_raw, off_xch, off_pow, off_tw2, off_twc, off_melw, off_melk, off_red, off_bar, off_db, off_dct, off_zacc, total;
+    int off_raw, off_xch, off_pow, off_tw2, off_tw1, off_twc, off_melw, off_melk, off_red, off_bar, off_db, off_dct, off_zacc, total;
 };
 
 __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc) {
@@ -65,16 +64,17 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.chunk = (hop * (F - 1) + NFFT + 7) & ~7;
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
-    L.raw_bytes = (L.chunk * (i16 ? 2 : 4) + 15) & ~15;
+    L.raw_bytes = ((L.chunk + 8) * (i16 ? 2 : 4) + 15) & ~15;      // + 8: a tile may sit up to 7 elements into its slot
     L.off_raw = take(nraw(i16, mfcc) * L.raw_bytes);
     L.off_xch = take(2 * kFftWarps * XSLOT * 8);
     L.off_pow = take(NPOW * PROWS * PROW * 4);
     L.off_tw2 = take(8 * 16 * 8);                     // split twiddles of the 512-sample sub-FFTs
+    L.off_tw1 = take(15 * 16 * 8);                    // pass-2 twiddles exp(-2 pi i t j / 256) as [t - 1][j]
     L.off_twc = take(257 * 8);                        // combine twiddles W_1024^k, k = 0..256
     L.off_melw = take(mel_wpad * 4);
     L.off_melk = take(n_mels * 16);
     L.off_red = take((64 + 2 * (mfcc ? n_mfcc : 1)) * 4);   // per-warp max/min, then (mean, 1/sd) per coefficient
-    L.off_bar = take((kMaxRaw + 2 * NPOW) * 8);
+    L.off_bar = take((kMaxRaw + 2 * NPOW) * 8 + kMaxRaw * 4);       // mbarriers, then each raw slot's shift
     L.off_db = take(mfcc ? n_mels * F * 4 : 0);       // [n_mels][16] dB tile feeding the in-tile DCT
     L.off_dct = take(mfcc ? n_mels * n_mfcc * 4 : 0); // DCT-II basis as [band][coefficient]
     L.gh = (n_mfcc + kStreams - 1) / kStreams;        // coefficients per stream
@@ -93,6 +93,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
     float2* const s_xch = reinterpret_cast<float2*>(smem + L.off_xch);
     float* const s_pow = reinterpret_cast<float*>(smem + L.off_pow);
     float2* const s_tw2 = reinterpret_cast<float2*>(smem + L.off_tw2);
+    float2* const s_tw1 = reinterpret_cast<float2*>(smem + L.off_tw1);
     float2* const s_twc = reinterpret_cast<float2*>(smem + L.off_twc);
     float* const s_melw = reinterpret_cast<float*>(smem + L.off_melw);
     int4* const s_desc = reinterpret_cast<int4*>(smem + L.off_melk);
@@ -104,6 +105,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
     uint64_t* const bar_raw_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
     uint64_t* const bar_pow_full = bar_raw_full + kMaxRaw;
     uint64_t* const bar_pow_empty = bar_pow_full + NPOW;
+    int* const s_sft = reinterpret_cast<int*>(bar_pow_empty + NPOW);      // tile sample c0 + i sits at slot element i + s_sft[slot]
 
     constexpr int NRAW = nraw(I16, MFCC);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -115,6 +117,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
         const int r = i >> 4, jj = i & 15;                   // conflict-free 128-bit load (logmel512.cu layout)
         s_tw2[(r >> 1) * 32 + jj * 2 + (r & 1)] = p.tw[jj + 16 * r];
     }
+    for (int i = tid; i < 15 * 16; i += kThreads) s_tw1[i] = p.tw[2 * ((i >> 4) + 1) * (i & 15)];
     for (int i = tid; i < 257; i += kThreads) s_twc[i] = p.tw2[i];
     for (int i = tid; i < p.mel_wpad; i += kThreads) s_melw[i] = p.mel_wq[i];
     for (int i = tid; i < n_mels; i += kThreads) {
@@ -139,7 +142,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
 
     if (warp < kFftWarps) {
         // =========================== FFT warps: one frame per warp per tile ===============================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kFftRegs));
+        // (no setmaxnreg here: with the pass-2 twiddles in shared memory this role fits the launch allocation of
+        //  96 registers, and the mel warps keep theirs — setmaxnreg.inc could only be funded by a .dec of the
+        //  mel warps to 64, which made them spill, and with this much shared memory there is no L1 to spill into)
         const int j = lane & 15, h = lane >> 4;
         float2 win[16];
 #pragma unroll
@@ -148,9 +153,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
             const float sc = I16 ? (1.0f / 32768.0f) : 1.0f;     // librosa.load's exact 1/32768 rides on the window
             win[t] = make_float2(__ldg(p.window + 4 * q + h) * sc, __ldg(p.window + 4 * q + 2 + h) * sc);
         }
-        float2 tw1[15];
-#pragma unroll
-        for (int t = 1; t < 16; ++t) tw1[t - 1] = p.tw[2 * t * j];   // exp(-2 pi i t j / 256)
+        // (the pass-2 twiddles exp(-2 pi i t j / 256) come from shared memory here: with 225 KB of it the L1 has
+        //  no room for spills, and win[] + v[] + a register copy of the 15 twiddles do not fit 104 registers
+        //  next to the combine step's operands)
+        const float2* const tw1 = s_tw1 + j;
         float2* const xs = s_xch + (2 * warp + h) * XSLOT;
         float2* const x1 = xs + XS * j;
         float2* const x2 = xs + j;
@@ -172,30 +178,50 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                 const int f = warp;
                 if (t0 + f < nfr) {
                     float2 v[16];
+                    const int sft = s_sft[rb];                          // (visible: written before the slot's barrier completed)
                     if constexpr (I16) {
                         // 64 bits = samples 4q .. 4q+3; this half takes (4q + h, 4q + 2 + h)
-                        const uint32_t ra = smem_u32(reinterpret_cast<const int16_t*>(cur) + f * hop + 4 * j);
-                        // two batches of eight loads: sixteen 64-bit words would hold 32 registers at once
+                        const uint32_t ra = smem_u32(reinterpret_cast<const int16_t*>(cur) + f * hop + 4 * j + sft);
+                        if ((sft & 3) == 0) {
+                            // two batches of eight loads: sixteen 64-bit words would hold 32 registers at once
 #define B2A_LDR(T) asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+%3];" : "=r"(rw[(T) & 7].x), "=r"(rw[(T) & 7].y) : "r"(ra), "n"((T) * 128))
 #pragma unroll
-                        for (int hb = 0; hb < 2; ++hb) {
-                            uint2 rw[8];
-                            if (hb == 0) { B2A_LDR(0); B2A_LDR(1); B2A_LDR(2); B2A_LDR(3); B2A_LDR(4); B2A_LDR(5); B2A_LDR(6); B2A_LDR(7); }
-                            else { B2A_LDR(8); B2A_LDR(9); B2A_LDR(10); B2A_LDR(11); B2A_LDR(12); B2A_LDR(13); B2A_LDR(14); B2A_LDR(15); }
+                            for (int hb = 0; hb < 2; ++hb) {
+                                uint2 rw[8];
+                                if (hb == 0) { B2A_LDR(0); B2A_LDR(1); B2A_LDR(2); B2A_LDR(3); B2A_LDR(4); B2A_LDR(5); B2A_LDR(6); B2A_LDR(7); }
+                                else { B2A_LDR(8); B2A_LDR(9); B2A_LDR(10); B2A_LDR(11); B2A_LDR(12); B2A_LDR(13); B2A_LDR(14); B2A_LDR(15); }
 #pragma unroll
-                            for (int t = 0; t < 8; ++t) {
-                                const float a = __int2float_rn((int)(rw[t].x << sh) >> 16);
-                                const float b = __int2float_rn((int)(rw[t].y << sh) >> 16);
-                                v[8 * hb + t] = __fmul2_rn(make_float2(a, b), win[8 * hb + t]);
+                                for (int t = 0; t < 8; ++t) {
+                                    const float a = __int2float_rn((int)(rw[t].x << sh) >> 16);
+                                    const float b = __int2float_rn((int)(rw[t].y << sh) >> 16);
+                                    v[8 * hb + t] = __fmul2_rn(make_float2(a, b), win[8 * hb + t]);
+                                }
+                            }
+#undef B2A_LDR
+                        } else {
+                            // clip whose start is 4 (not 8) bytes off the 16-byte grid: the same words as two 32-bit loads
+#pragma unroll
+                            for (int t = 0; t < 16; ++t) {
+                                uint32_t w0, w1;
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(ra + 128 * t));
+                                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(ra + 128 * t + 4));
+                                const float a = __int2float_rn((int)(w0 << sh) >> 16);
+                                const float b = __int2float_rn((int)(w1 << sh) >> 16);
+                                v[t] = __fmul2_rn(make_float2(a, b), win[t]);
                             }
                         }
-#undef B2A_LDR
                     } else {
-                        const float* a = reinterpret_cast<const float*>(cur) + f * hop + 4 * j;
+                        const float* a = reinterpret_cast<const float*>(cur) + f * hop + 4 * j + sft;
+                        if (sft == 0) {
 #pragma unroll
-                        for (int t = 0; t < 16; ++t) {
-                            const float4 q4 = *reinterpret_cast<const float4*>(a + 64 * t);
-                            v[t] = __fmul2_rn(h ? make_float2(q4.y, q4.w) : make_float2(q4.x, q4.z), win[t]);
+                            for (int t = 0; t < 16; ++t) {
+                                const float4 q4 = *reinterpret_cast<const float4*>(a + 64 * t);
+                                v[t] = __fmul2_rn(h ? make_float2(q4.y, q4.w) : make_float2(q4.x, q4.z), win[t]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int t = 0; t < 16; ++t)
+                                v[t] = __fmul2_rn(make_float2(a[64 * t + h], a[64 * t + 2 + h]), win[t]);
                         }
                     }
                     Dft<16>::run(v);
@@ -204,7 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                     __syncwarp();
                     v[0] = x2[0];
 #pragma unroll
-                    for (int t = 1; t < 16; ++t) v[t] = cmul(x2[XS * t], tw1[t - 1]);
+                    for (int t = 1; t < 16; ++t) v[t] = cmul(x2[XS * t], tw1[16 * (t - 1)]);
                     Dft<16>::run(v);                                   // v[t] = Z_h[j + 16 t]
                     __syncwarp();
 #pragma unroll
@@ -281,7 +307,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
         }
     } else {
         // =========================== mel warps (warp 0 of them also stages the raw tiles) =========
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMelRegs));
         const int mw = warp - kFftWarps, mtid = tid - 32 * kFftWarps;
         const int l16 = lane & 15, par = lane >> 4;
         constexpr int V = 16 / (int)sizeof(E);
@@ -301,28 +326,46 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
             const int nfr = 1 + n / hop;
             const int vf = nfr - t0 < F ? nfr - t0 : F;
             const int need = ((vf - 1) * hop + NFFT + V - 1) & ~(V - 1);      // <= chunk
-            const bool ok = p.pad_mode == 0 && base_aligned && hi > lo && (((e0 + lo) & (V - 1)) == 0) &&
-                            (((lo - c0) & (V - 1)) == 0);
-            const int nb = ok ? ((hi - lo) / V) * V : 0;
-            if (nb == 0) {
+            // The clip's own 16-byte grid decides where the tile sits in the slot: tile sample c0 + i goes to
+            // dst[i + sft], sft < V chosen so that the first sample on a 16-byte boundary of GLOBAL memory lands on a
+            // 16-byte boundary of the slot (110 250-sample int16 clips start 0 / 4 / 8 / 12 bytes off the grid).
+            // The aligned interior is one TMA bulk copy; up to V - 1 samples on either side, the centre padding
+            // and whatever the valid frames read past the clip go by plain stores.
+            const int mis = (int)((e0 + lo) & (V - 1));
+            const int lead = (V - mis) & (V - 1);
+            const int lo_a = lo + lead;                                       // first sample of the bulk copy
+            const bool ok = p.pad_mode == 0 && base_aligned && hi > lo && (!I16 || (mis & 1) == 0);
+            if (!ok) {
                 for (int i = lane; i < need; i += 32) dst[i] = raw_sample<E>(cptr, c0 + i, n, p.pad_mode);
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar);
+                if (lane == 0) { s_sft[slot] = 0; mbar_arrive(bar); }
                 return;
             }
-            const int head = lo - c0, tb = head + nb;
+            const int sft = (V - ((lo_a - c0) & (V - 1))) & (V - 1);
+            const int nb = hi > lo_a ? ((hi - lo_a) / V) * V : 0;            // bulk part, whole 16-byte units
+            const int d_lo = lo - c0 + sft;                                   // slot index of sample lo
+            const int d_a = lo_a - c0 + sft;                                  // ... of the bulk copy (multiple of V)
+            const int d_tb = d_a + nb;                                        // ... of the first sample behind it
+            const int d_end = (need + sft + V - 1) & ~(V - 1);                // <= chunk + V
             const int4 z4 = make_int4(0, 0, 0, 0);
-            for (int i = lane * V; i < head; i += 32 * V) *reinterpret_cast<int4*>(dst + i) = z4;
-            if (tb < need) {
-                if (lane < V) dst[tb + lane] = raw_sample<E>(cptr, c0 + tb + lane, n, 0);
-                for (int i = tb + V + lane * V; i < need; i += 32 * V) *reinterpret_cast<int4*>(dst + i) = z4;
-            }
+            // zeros: [0, d_a) (centre padding + the 16 bytes the lead samples share) and [d_tb, d_end)
+            for (int i = lane * V; i < d_a; i += 32 * V) *reinterpret_cast<int4*>(dst + i) = z4;
+            for (int i = d_tb + lane * V; i < d_end; i += 32 * V) *reinterpret_cast<int4*>(dst + i) = z4;
+            __syncwarp();
+            if (lane < lead && lo + lane < hi) dst[d_lo + lane] = cptr[lo + lane];
+            if (lane < V && lo_a + nb + lane < hi && d_tb + lane < d_end) dst[d_tb + lane] = cptr[lo_a + nb + lane];
             __syncwarp();
             if (lane == 0) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                const int cb = (nb < need - head ? nb : need - head) * (int)sizeof(E);
-                mbar_expect_tx(bar, (uint32_t)cb);
-                bulk_g2s(dst + head, cptr + lo, (uint32_t)cb, bar);
+                s_sft[slot] = sft;
+                if (nb > 0) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses -> async write
+                    const int room = d_end - d_a;
+                    const int cb = (nb < room ? nb : room) * (int)sizeof(E);          // never more than the frames read
+                    mbar_expect_tx(bar, (uint32_t)cb);
+                    bulk_g2s(dst + d_a, cptr + lo_a, (uint32_t)cb, bar);
+                } else {
+                    mbar_arrive(bar);
+                }
             }
         };
         long long pclip = blockIdx.x;
@@ -399,33 +442,39 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                     const bool valid = t < nfr;
                     float* const outp = inter + t;
                     const float2* pl = reinterpret_cast<const float2*>(s_pow + pb * (PROWS * PROW)) + l16;
-                    for (int pp = mw; 2 * pp < n_mels; pp += kMelWarps) {
-                        const int i = 2 * pp + par;
-                        const int4 d = i < n_mels ? s_desc[i] : make_int4(0, 0, 0, 0);
-                        const int steps = max(d.y, __shfl_xor_sync(0xffffffffu, d.y, 16));
-                        const float2* pr = pl + d.x;
-                        const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 1
+                    // Two band pairs in flight per warp (pairs pp and pp + 4: each half-warp then has two independent
+                    // dot products, six loads per step) — this warp shares its scheduler with four FFT warps and a
+                    // single dependent load -> FMA chain left it at ~0.1 instructions per cycle.
+                    for (int pp = mw; 2 * pp < n_mels; pp += 2 * kMelWarps) {
+                        const int iA = 2 * pp + par, iB = 2 * (pp + kMelWarps) + par;
+                        const int4 dA = iA < n_mels ? s_desc[iA] : make_int4(0, 0, 0, 0);
+                        const int4 dB = iB < n_mels ? s_desc[iB] : make_int4(0, 0, 0, 0);
+                        const int mine = max(dA.y, dB.y);
+                        const int steps = max(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
+                        const float2* prA = pl + dA.x;
+                        const float2* prB = pl + dB.x;
+                        const float4* wA = reinterpret_cast<const float4*>(s_melw + dA.z);
+                        const float4* wB = reinterpret_cast<const float4*>(s_melw + dB.z);
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll 2
                         for (int q4 = 0; q4 < steps; ++q4) {
-                            if (q4 < d.y) {
-                                const float4 w = wq[q4];
-                                const float2 p0 = pr[0], p1 = pr[PROW / 2];
-                                a0 = fmaf(w.x, p0.x, a0);
-                                a1 = fmaf(w.y, p0.y, a1);
-                                a2 = fmaf(w.z, p1.x, a2);
-                                a3 = fmaf(w.w, p1.y, a3);
-                            }
-                            pr += PROW;
+                            float4 w = make_float4(0.f, 0.f, 0.f, 0.f), u = make_float4(0.f, 0.f, 0.f, 0.f);
+                            float2 p0 = make_float2(0.f, 0.f), p1 = p0, r0 = p0, r1 = p0;
+                            if (q4 < dA.y) { w = wA[q4]; p0 = prA[0]; p1 = prA[PROW / 2]; }
+                            if (q4 < dB.y) { u = wB[q4]; r0 = prB[0]; r1 = prB[PROW / 2]; }
+                            a0 = fmaf(w.x, p0.x, a0); a1 = fmaf(w.y, p0.y, a1); a2 = fmaf(w.z, p1.x, a2); a3 = fmaf(w.w, p1.y, a3);
+                            b0 = fmaf(u.x, r0.x, b0); b1 = fmaf(u.y, r0.y, b1); b2 = fmaf(u.z, r1.x, b2); b3 = fmaf(u.w, r1.y, b3);
+                            prA += PROW; prB += PROW;
                         }
-                        if (i < n_mels) {
+                        if (iA < n_mels) {
                             const float vv = db10((a0 + a1) + (a2 + a3));
-                            if (MFCC) s_db[d.w * F + l16] = vv;
-                            if (valid) {
-                                outp[(size_t)d.w * nfr] = vv;
-                                vmax = fmaxf(vmax, vv);
-                                vmin = fminf(vmin, vv);
-                            }
+                            if (MFCC) s_db[dA.w * F + l16] = vv;
+                            if (valid) { outp[(size_t)dA.w * nfr] = vv; vmax = fmaxf(vmax, vv); vmin = fminf(vmin, vv); }
+                        }
+                        if (iB < n_mels) {
+                            const float vv = db10((b0 + b1) + (b2 + b3));
+                            if (MFCC) s_db[dB.w * F + l16] = vv;
+                            if (valid) { outp[(size_t)dB.w * nfr] = vv; vmax = fmaxf(vmax, vv); vmin = fminf(vmin, vv); }
                         }
                     }
                 }
@@ -464,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                     for (int g = 0; g < kMaxGh; ++g) a[g] = 0.f;
                     const float* dbl = s_db + l16;
                     const float* bs = s_dct + s0;
-#pragma unroll 2
+#pragma unroll 4
                     for (int m = 0; m < n_mels; ++m) {
                         const float dv = dbl[m * F];
 #pragma unroll

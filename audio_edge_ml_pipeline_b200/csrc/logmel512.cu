@@ -315,7 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel512_kernel(FrontParams p) {
         }
     } else {
         // =========================== mel warps (warp 0 of them also stages the raw tiles) =========
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMelRegs));
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kMelRegs));   // (this .dec is what funds the FFT warps' .inc)
         const int mw = warp - kFftWarps, mtid = tid - 32 * kFftWarps;
         constexpr int V = 16 / (int)sizeof(E);                   // samples per 16 bytes
         const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;

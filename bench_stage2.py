@@ -76,6 +76,50 @@ def run(classes: int = 27, per_class: int = 260, devices: str = "all", dir: str 
     return line
 
 
+def run_device_augmented(classes: int = 27, per_class: int = 52, n_augments: int = 4, devices: str = "0",
+                         out_dir: str = "/dev/shm/b2a_stage2_aug") -> dict:
+    """Config 5 without the WAV round trip: the 27 x 52 originals are augmented on the device (Stage 1b,
+    augment.py's chain minus the two librosa-backed steps, host-drawn reference RNG), quantised like the
+    PCM16 files the reference writes, and go straight into audio_mel_spec -> features.npy."""
+    import audio_edge_ml_pipeline_b200 as P
+    from audio_edge_ml_pipeline_b200 import augment as G
+    from audio_edge_ml_pipeline_b200 import synth
+    rng = np.random.default_rng(2026)
+    pool = np.stack([synth.pad_or_trim_pcm(synth.to_pcm16(synth.make_clip(rng, k % 5, 16000, 80000)), 80000)
+                     for k in range(40)])
+    originals = np.stack([np.roll(pool[(c + i) % len(pool)], 37 * i) for c in range(classes) for i in range(per_class)])
+    chain = [{"type": "volume_scale", "min_gain": 0.7, "max_gain": 1.3},
+             {"type": "gaussian_noise", "min_amplitude": 0.001, "max_amplitude": 0.004},
+             {"type": "time_shift", "max_fraction": 0.2}]
+    ext = P.get("audio_mel_spec")(duration=5.0, n_mels=40, sample_rate=16000, n_fft=512, hop_length=160, devices=devices)
+    dev0 = ext.devices[0]
+    best = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        src_clip, steps, noise, max_steps = G.plan([80000] * len(originals), [chain] * len(originals), n_augments, 42)
+        t1 = time.perf_counter()
+        rows = len(src_clip)
+        aug = np.empty((rows, 80000), dtype=np.int16)
+        G._run_host(dev0, originals.reshape(-1), np.ascontiguousarray(src_clip * 80000), np.full(rows, 80000, np.int32),
+                    np.arange(rows, dtype=np.int64) * 80000, steps, max_steps, noise, aug.reshape(-1))
+        t2 = time.perf_counter()
+        feats = ext.extract_batch(aug)
+        t3 = time.perf_counter()
+        Path(out_dir).mkdir(parents=True, exist_ok=True)
+        np.save(Path(out_dir) / "features.npy", feats)
+        t4 = time.perf_counter()
+        cur = (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t4 - t0)
+        best = cur if best is None or cur[4] < best[4] else best
+    ext.close()
+    shutil.rmtree(out_dir, ignore_errors=True)
+    return {"metric": "Stage 1b + 2 without the WAV round trip: clips/sec (originals in memory -> features.npy)",
+            "value": rows / best[4], "unit": "clips/s", "clips": rows, "originals": len(originals),
+            "seconds": {"host_rng_plan (numpy default_rng, the reference's sequence)": best[0],
+                        "device_augment (H2D + kernel + D2H int16)": best[1], "log-mel (host buffers)": best[2],
+                        "np.save": best[3], "total": best[4]},
+            "chain": [c["type"] for c in chain], "features_shape": list(feats.shape)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--classes", type=int, default=27)
@@ -83,7 +127,11 @@ def main():
     ap.add_argument("--devices", default="all")
     ap.add_argument("--dir", default="/dev/shm/b2a_stage2")
     ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--device-augmented", action="store_true", help="config 5 without the WAV round trip (Stage 1b on the device)")
     a = ap.parse_args()
+    if a.device_augmented:
+        print(json.dumps(run_device_augmented(a.classes, devices=a.devices if a.devices != "all" else "0")), flush=True)
+        return
     print(json.dumps(run(a.classes, a.per_class, a.devices, a.dir, a.repeat)), flush=True)
 
 

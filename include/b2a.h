@@ -200,12 +200,13 @@ const char* b2a_resampler_last_error(void);   /* same text b2a_last_error() retu
  * src_off[r] of `src` and writes lengths[r] samples at element offset out_off[r] of `out`
  * (_preserve_length, augment.py:206-212, is the identity for these length-preserving steps).
  *   B2A_AUG_GAIN      y * a                               volume_scale :88-93 and the level match :344-345
- *   B2A_AUG_NOISE     clip(y + noise[noise_off + i] * a)  gaussian_noise :96-102 (noise = float32 of the host's draws)
+ *   B2A_AUG_NOISE     clip(y + noise[noise_off + i] * a)  gaussian_noise :96-102 (noise = float32 of the host's draws) and
+ *                                                         pdm_hiss :135-167 (noise = the host-synthesised pink row)
  *   B2A_AUG_ROLL      np.roll(y, shift)                   time_shift :121-126
  *   B2A_AUG_POLARITY  -y                                  polarity_inversion :129-132
  * A row's chain is steps[r * max_steps ...] up to the first op < 0.  out_dtype B2A_IN_F32 gives y_aug;
  * B2A_IN_I16 quantises it the way soundfile writes PCM_16 (lrintf(x * 32768), saturated) — the samples
- * Stage 2 reads back after the reference's WAV round trip.  time_stretch / pitch_shift / pdm_hiss are not built. */
+ * Stage 2 reads back after the reference's WAV round trip.  time_stretch / pitch_shift are not built. */
 #define B2A_AUG_END      -1
 #define B2A_AUG_GAIN      0
 #define B2A_AUG_NOISE     1
