@@ -229,7 +229,7 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
         CU_TRY_H(upload(h->mel.w, &h->d_w));
         h->grid_cap = h->sm_count * b2a::front_ctas_per_sm(h->log2nc);
         const bool try512 = n_fft == 512 && (cfg->hop_length % 2) == 0;
-        const bool try1024 = n_fft == 1024 && b2a::logmel1024_supports(cfg->hop_length, mfcc ? cfg->n_mfcc : 0);
+        const bool try1024 = n_fft == 1024 && b2a::logmel1024_supports(cfg->hop_length, cfg->n_mels, mfcc ? cfg->n_mfcc : 0);
         if (try512 || try1024) {
             // tables of the specialised kernel: bands padded to float4 groups, |X|^2 -> 4|X|^2 folded
             // into the weights (x0.25 is exact), bands dealt to the mel warps in snake order by size

@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(kBankThreads, 6) cqt_bank_kernel(const __grid_
 
     const int nvalid = min(kBankFrames, p.n_frames - t0);       // frames of this block inside the clip
     const bool vec4 = !i16 && (hop & 3) == 0 && ((N / 2) & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
+    const bool vec2 = i16 && (hop & 3) == 0 && ((N / 2) & 3) == 0 && (reinterpret_cast<uintptr_t>(base) & 7) == 0;
     const int n_items = nvalid * (kBankSlice / 4);              // item = (frame f, 4 consecutive n), frame-major
     for (int n0 = 0; n0 < N; n0 += kBankSlice) {
         __syncthreads();                                       // the previous slice has been consumed
@@ -352,6 +353,10 @@ __global__ void __launch_bounds__(kBankThreads, 6) cqt_bank_kernel(const __grid_
                 if (it >= n_items) continue;
                 if (vec4 && s0 >= 0 && s0 + 4 <= L) {
                     v[u] = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + s0));
+                } else if (vec2 && s0 >= 0 && s0 + 4 <= L) {
+                    const uint2 w = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const int16_t*>(base) + s0));
+                    v[u] = make_float4((float)(short)(w.x & 0xffffu) * (1.0f / 32768.0f), (float)((int)w.x >> 16) * (1.0f / 32768.0f),
+                                       (float)(short)(w.y & 0xffffu) * (1.0f / 32768.0f), (float)((int)w.y >> 16) * (1.0f / 32768.0f));
                 } else {
                     float e4[4];
 #pragma unroll

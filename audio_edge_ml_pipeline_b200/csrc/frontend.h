@@ -47,10 +47,10 @@ int logmel512_ctas_per_sm();     // persistent warp-specialised CTAs per SM (1)
 int logmel512_mel_warps();       // mel (consumer) warps per CTA: table-driven bands are dealt round-robin to them
 cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st);
 
-// specialised n_fft = 1024 kernel (logmel1024.cu): one warp per frame, two interleaved 512-sample real FFTs;
-// needs hop % 4 == 0 and the same padded mel tables as the 512 kernel (bands in descending width order)
+// specialised n_fft = 1024 kernel (logmel1024.cu): one warp per frame (two interleaved 512-sample real FFTs, then
+// the frame's mel bands and DCT in parallel lanes); needs hop % 4 == 0; mel_order deals the bands to lanes by width
 size_t logmel1024_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc);  // n_mfcc = 0: mel
-bool logmel1024_supports(int hop, int n_mfcc);
+bool logmel1024_supports(int hop, int n_mels, int n_mfcc);
 cudaError_t launch_logmel1024(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st);
 
 }  // namespace b2a

@@ -1,26 +1,31 @@
-// logmel1024.cu — n_fft = 1024 fused log-mel / MFCC front end, warp-specialised like logmel512.cu.
+// logmel1024.cu — n_fft = 1024 fused log-mel / MFCC front end, sm_100a only.
 //
 // n_fft 1024 / hop 512 is the reference default of audio_mfcc_seq (deep.py:290-297) and of every
 // non-Nicla experiment (experiments/birdeep_feature_extraction.yaml:31-47).  A 1024-sample frame is the
 // radix-2 combination of two 512-sample real FFTs, one over its even and one over its odd samples:
 //     X[k] = E0[k] + W^k E1[k],   X[512 - k] = conj(E0[k] - W^k E1[k]),   W = exp(-2 pi i / 1024), k = 0..256
-// so the per-frame work is exactly the half-warp machinery of logmel512.cu twice: ONE WARP PER FRAME,
-// half-warp h transforms samples 4q + h and 4q + 2 + h as the packed complex sequence of its 512-sample
-// real FFT (both radix-16 passes in registers, packed FP32), and after the split step the two halves swap
-// one operand per bin through warp shuffles and finish with a twiddle butterfly each.
+// so the transform is the half-warp machinery of logmel512.cu twice: ONE WARP PER FRAME, half-warp h
+// transforms samples 4q + h and 4q + 2 + h as the packed complex sequence of its 512-sample real FFT
+// (both radix-16 passes in registers, packed FP32), and after the split step the two halves swap one
+// operand per bin through warp shuffles and finish with a twiddle butterfly each.
 //
-// One persistent CTA per SM (640 threads):
-//   * 16 FFT warps (setmaxnreg 104): a tile is 16 frames, one per warp.  Raw PCM comes from the TMA-staged
-//     ring (64-bit shared loads, the half picks its two of the four samples), 4|X|^2 goes to a
-//     [bin pair][frame] power tile.
-//   * 4 mel warps (setmaxnreg 64), warp 0 also the TMA producer.  A tile has 16 frames, so a half-warp
-//     sweeps one band while the other half sweeps the next (lane & 15 = frame): table-driven banded dot
-//     products with 4-bin steps, 10 log10, raw dB to the output / scratch (L2), running max / min.
-//     mel: the clip is normalised in place during the NEXT clip's tiles (prefetched slices).
-//     mfcc: DCT-II of each tile from a [band][frame] dB tile in shared memory, eight coefficient streams
-//     ((mel warp, half) takes coefficients s, s + 8, ...), per-row sums kept per (coefficient, frame lane)
-//     in shared memory; rows are z-scored by the same deferred pass (deep.py:326-328).
-//   * mbarriers only: raw_full (TMA bytes) -> FFT; pow_full (16 arrivals) -> mel; pow_empty (4) -> FFT.
+// One persistent CTA per SM, 640 threads, 96 registers each (no setmaxnreg):
+//   * 16 FRAME warps.  A tile is 16 frames, one per warp, and the warp takes its frame all the way:
+//     FFT -> 4|X|^2 into its own 513-bin column -> the mel bands (lane = band, bands dealt to lanes by
+//     width so the ragged dot products balance; 2 loads + 1 FMA per filter tap) -> 10 log10 -> (mfcc)
+//     the DCT-II (lane = coefficient block, dB broadcast 4 bands at a time, basis as 128-bit loads) ->
+//     its column of the [row][16 frames] tile.  Raw PCM comes from the TMA-staged ring.
+//     (The first version of this kernel gave the band sweep and the DCT to four separate warps as
+//     logmel512.cu does; sharing a scheduler with four FFT warps each, their dependent load -> FMA
+//     chains ran at ~0.1 instructions per cycle and the FFT warps spent 39 % of their time waiting for
+//     them — profiles/r2_ncu_1024_summary.txt.  Sixteen warps doing a frame's bands in parallel lanes
+//     need ~150 instructions per frame instead.)
+//   * 4 EPILOGUE warps, warp 0 also the TMA producer: move finished tiles to global memory with
+//     coalesced stores, track the clip's max / min, and rewrite the PREVIOUS clip in place during the
+//     current clip's tiles — power_to_db(ref=max, top_db) + min-max for mel, the per-row z-score
+//     (deep.py:326-328) from per-thread running sums for mfcc.
+//   * mbarriers only: raw_full (TMA bytes) -> frame warps; tile_full (16 arrivals) -> epilogue;
+//     tile_empty (4 arrivals) -> frame warps.
 //
 // Reference arithmetic: deep.py:126-134 (mel), :318-328 (mfcc) via librosa 0.11.0.
 #include "frontend.h"
@@ -41,49 +46,52 @@ constexpr int kThreads = 32 * (kFftWarps + kMelWarps);
 constexpr int kMelThreads = 32 * kMelWarps;
 constexpr int NFFT = 1024, F = 16;              // frame length (two 512-sample sub-FFTs of 256 complex points), frames per tile
 constexpr int kMaxRaw = 3;
-__host__ __device__ constexpr int nraw(bool i16, bool mfcc) { return i16 ? (mfcc ? 2 : 3) : (mfcc ? 1 : 2); }
-constexpr int NPOW = 2;
+__host__ __device__ constexpr int nraw(bool i16, bool mfcc) { return i16 ? 3 : 2; }
+constexpr int NTILE = 2;                        // ring of finished [row][16] tiles
 constexpr int XS = 17;                          // exchange row stride (float2), as in logmel512.cu
 constexpr int XSLOT = 16 * XS + 2;
 constexpr int PROW = 2 * F + 4;                 // power tile: row = 2 adjacent bins x (16 frames + 2 pad)
 constexpr int PROWS = 260;                      // bin pairs (0,1)..(512,513) + 3 zero rows for 8-bin padding
-constexpr int kStreams = 2 * kMelWarps;         // mfcc: coefficient streams (mel warp, half)
+constexpr int kMaxCoefPerLane = 2;              // n_mfcc <= 64
 
 __device__ __forceinline__ void mel_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kMelThreads) : "memory");
 }
+// barrier among the 16 frame warps only (named barrier 2)
+__device__ __forceinline__ void frame_warps_sync() {
+    asm volatile("bar.sync 2, %0;" ::"n"(32 * kFftWarps) : "memory");
+}
 
 struct Layout {
-    int chunk, raw_bytes, gh;
-    int off_raw, off_xch, off_pow, off_tw2, off_tw1, off_twc, off_melw, off_melk, off_red, off_bar, off_db, off_dct, off_zacc, total;
+    int chunk, raw_bytes, rows;                  // rows of a tile: n_mels (+ n_mfcc)
+    int off_raw, off_xch, off_pow, off_tile, off_win, off_tw2, off_tw1, off_twc, off_melw, off_melk, off_red, off_bar, off_dbc, off_dct, total;
 };
 
 __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc) {
     const bool mfcc = n_mfcc > 0;
     Layout L;
     L.chunk = (hop * (F - 1) + NFFT + 7) & ~7;
+    L.rows = n_mels + (mfcc ? n_mfcc : 0);
     int o = 0;
     auto take = [&](int bytes) { int r = o; o += (bytes + 15) & ~15; return r; };
     L.raw_bytes = ((L.chunk + 8) * (i16 ? 2 : 4) + 15) & ~15;      // + 8: a tile may sit up to 7 elements into its slot
     L.off_raw = take(nraw(i16, mfcc) * L.raw_bytes);
     L.off_xch = take(2 * kFftWarps * XSLOT * 8);
-    L.off_pow = take(NPOW * PROWS * PROW * 4);
+    L.off_pow = take(PROWS * PROW * 4);               // power tile of the current 16 frames: [bin pair][frame]
+    L.off_tile = take(NTILE * L.rows * F * 4);        // finished tiles: [row][16 frames]
+    L.off_win = take(16 * 32 * 8);                    // window pairs (w[4q + h], w[4q + 2 + h]) as [t][lane], q = j + 16 t
     L.off_tw2 = take(8 * 16 * 8);                     // split twiddles of the 512-sample sub-FFTs
     L.off_tw1 = take(15 * 16 * 8);                    // pass-2 twiddles exp(-2 pi i t j / 256) as [t - 1][j]
     L.off_twc = take(257 * 8);                        // combine twiddles W_1024^k, k = 0..256
-    L.off_melw = take(mel_wpad * 4);
-    L.off_melk = take(n_mels * 16);
-    L.off_red = take((64 + 2 * (mfcc ? n_mfcc : 1)) * 4);   // per-warp max/min, then (mean, 1/sd) per coefficient
-    L.off_bar = take((kMaxRaw + 2 * NPOW) * 8 + kMaxRaw * 4);       // mbarriers, then each raw slot's shift
-    L.off_db = take(mfcc ? n_mels * F * 4 : 0);       // [n_mels][16] dB tile feeding the in-tile DCT
-    L.off_dct = take(mfcc ? n_mels * n_mfcc * 4 : 0); // DCT-II basis as [band][coefficient]
-    L.gh = (n_mfcc + kStreams - 1) / kStreams;        // coefficients per stream
-    L.off_zacc = take(mfcc ? 3 * n_mfcc * F * 4 : 0); // per (coefficient, frame lane): sum, sum of squares, first value
+    L.off_melw = take(mel_wpad * 4);                  // banded weights in 4-bin steps, x 0.25 (the tile holds 4|X|^2)
+    L.off_melk = take(n_mels * 16);                   // per position: {pair-row offset, 4-bin steps, weight offset, band}
+    L.off_red = take((64 + 2 * (mfcc ? n_mfcc : 1)) * 4);
+    L.off_bar = take((kMaxRaw + 2 * NTILE) * 8 + kMaxRaw * 4);
+    L.off_dbc = take(mfcc ? F * (n_mels + 4) * 4 : 0);        // mfcc: dB of the tile as [frame][band] rows (stride n_mels + 4)
+    L.off_dct = take(mfcc ? n_mels * n_mfcc * 4 : 0);        // DCT-II basis as [band / 4][coefficient][4]
     L.total = o;
     return L;
 }
-
-constexpr int kMaxGh = 8;                              // up to 64 coefficients
 
 template <bool I16, int KIND, bool RAG>
 __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) {
@@ -92,6 +100,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
     const Layout L = make_layout(p.hop, p.n_mels, p.mel_wpad, I16, MFCC ? p.n_mfcc : 0);
     float2* const s_xch = reinterpret_cast<float2*>(smem + L.off_xch);
     float* const s_pow = reinterpret_cast<float*>(smem + L.off_pow);
+    float* const s_tile = reinterpret_cast<float*>(smem + L.off_tile);
+    float2* const s_win = reinterpret_cast<float2*>(smem + L.off_win);
     float2* const s_tw2 = reinterpret_cast<float2*>(smem + L.off_tw2);
     float2* const s_tw1 = reinterpret_cast<float2*>(smem + L.off_tw1);
     float2* const s_twc = reinterpret_cast<float2*>(smem + L.off_twc);
@@ -99,23 +109,27 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
     int4* const s_desc = reinterpret_cast<int4*>(smem + L.off_melk);
     float* const s_red = reinterpret_cast<float*>(smem + L.off_red);
     float* const s_zs = s_red + 64;
-    float* const s_db = reinterpret_cast<float*>(smem + L.off_db);
+    float* const s_dbc = reinterpret_cast<float*>(smem + L.off_dbc);
     float* const s_dct = reinterpret_cast<float*>(smem + L.off_dct);
-    float* const s_zacc = reinterpret_cast<float*>(smem + L.off_zacc);
     uint64_t* const bar_raw_full = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-    uint64_t* const bar_pow_full = bar_raw_full + kMaxRaw;
-    uint64_t* const bar_pow_empty = bar_pow_full + NPOW;
-    int* const s_sft = reinterpret_cast<int*>(bar_pow_empty + NPOW);      // tile sample c0 + i sits at slot element i + s_sft[slot]
+    uint64_t* const bar_tile_full = bar_raw_full + kMaxRaw;
+    uint64_t* const bar_tile_empty = bar_tile_full + NTILE;
+    int* const s_sft = reinterpret_cast<int*>(bar_tile_empty + NTILE);    // tile sample c0 + i sits at slot element i + s_sft[slot]
 
     constexpr int NRAW = nraw(I16, MFCC);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int hop = p.hop, n_mels = p.n_mels, chunk = L.chunk;
+    const int hop = p.hop, n_mels = p.n_mels, chunk = L.chunk, rows = L.rows;
     using E = typename std::conditional<I16, int16_t, float>::type;
 
     // ---- per-CTA tables (p.tw = exp(-2 pi i k / 512), p.tw2 = exp(-2 pi i k / 1024)) ---------------------
     for (int i = tid; i < 128; i += kThreads) {              // split twiddles exp(-i pi (j + 16 r) / 256), two per
         const int r = i >> 4, jj = i & 15;                   // conflict-free 128-bit load (logmel512.cu layout)
         s_tw2[(r >> 1) * 32 + jj * 2 + (r & 1)] = p.tw[jj + 16 * r];
+    }
+    for (int i = tid; i < 16 * 32; i += kThreads) {          // librosa.load's exact 1/32768 rides on the window (int16 input)
+        const int t = i >> 5, l = i & 31, q = (l & 15) + 16 * t, hh = l >> 4;
+        const float sc = I16 ? (1.0f / 32768.0f) : 1.0f;
+        s_win[i] = make_float2(p.window[4 * q + hh] * sc, p.window[4 * q + 2 + hh] * sc);
     }
     for (int i = tid; i < 15 * 16; i += kThreads) s_tw1[i] = p.tw[2 * ((i >> 4) + 1) * (i & 15)];
     for (int i = tid; i < 257; i += kThreads) s_twc[i] = p.tw2[i];
@@ -124,38 +138,29 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
         const int m = p.mel_order[i];                        // positions in descending band width: neighbours pair up
         s_desc[i] = make_int4((p.mel_k0e[m] >> 1) * (PROW / 2), p.mel_cnt4[m], p.mel_off4[m], m);
     }
+    for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[256 * PROW + i] = 0.f;   // bins 512..519 (512 is rewritten per tile)
     if constexpr (MFCC) {
-        for (int i = tid; i < n_mels * p.n_mfcc; i += kThreads) {
-            const int k = i % p.n_mfcc, m = i / p.n_mfcc;
-            s_dct[i] = p.dct[(size_t)k * n_mels + m];
+        for (int i = tid; i < n_mels * p.n_mfcc; i += kThreads) {         // [m / 4][k][m & 3] (n_mels % 4 == 0)
+            const int e = i & 3, k = (i >> 2) % p.n_mfcc, m4 = (i >> 2) / p.n_mfcc;
+            s_dct[i] = p.dct[(size_t)k * n_mels + 4 * m4 + e];
         }
     }
-    for (int b = 0; b < NPOW; ++b)                           // bins 512..519 of every power tile (512 is rewritten
-        for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[b * PROWS * PROW + 256 * PROW + i] = 0.f;   // per tile, 513.. stay 0)
     if (tid == 0) {
         for (int i = 0; i < NRAW; ++i) mbar_init(bar_raw_full + i, 1);
-        for (int i = 0; i < NPOW; ++i) { mbar_init(bar_pow_full + i, kFftWarps); mbar_init(bar_pow_empty + i, kMelWarps); }
+        for (int i = 0; i < NTILE; ++i) { mbar_init(bar_tile_full + i, kFftWarps); mbar_init(bar_tile_empty + i, kMelWarps); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     if (blockIdx.x >= p.n_clips) return;
 
     if (warp < kFftWarps) {
-        // =========================== FFT warps: one frame per warp per tile ===============================
-        // (no setmaxnreg here: with the pass-2 twiddles in shared memory this role fits the launch allocation of
-        //  96 registers, and the mel warps keep theirs — setmaxnreg.inc could only be funded by a .dec of the
-        //  mel warps to 64, which made them spill, and with this much shared memory there is no L1 to spill into)
+        // =========================== frame warps: one frame per warp per tile ==============================
+        // (no setmaxnreg: every role fits the launch allocation of 96 registers — an .inc here could only be
+        //  funded by a .dec of the other warps, and with this much shared memory there is no L1 to spill into)
         const int j = lane & 15, h = lane >> 4;
-        float2 win[16];
-#pragma unroll
-        for (int t = 0; t < 16; ++t) {
-            const int q = j + 16 * t;
-            const float sc = I16 ? (1.0f / 32768.0f) : 1.0f;     // librosa.load's exact 1/32768 rides on the window
-            win[t] = make_float2(__ldg(p.window + 4 * q + h) * sc, __ldg(p.window + 4 * q + 2 + h) * sc);
-        }
-        // (the pass-2 twiddles exp(-2 pi i t j / 256) come from shared memory here: with 225 KB of it the L1 has
-        //  no room for spills, and win[] + v[] + a register copy of the 15 twiddles do not fit 104 registers
-        //  next to the combine step's operands)
+        // (window pairs and pass-2 twiddles come from shared memory: sixteen + fifteen register pairs next to
+        //  v[] and the band / DCT loops do not fit 96 registers, and spills have no L1 to land in)
+        const float2* const win = s_win + lane;
         const float2* const tw1 = s_tw1 + j;
         float2* const xs = s_xch + (2 * warp + h) * XSLOT;
         float2* const x1 = xs + XS * j;
@@ -171,10 +176,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
             const int tiles = (nfr + F - 1) / F;
             for (int tile = 0; tile < tiles; ++tile, ++it) {
                 const int t0 = tile * F;
-                const uint32_t rb = it % NRAW, pb = it % NPOW;
+                const uint32_t rb = it % NRAW, pb = it % NTILE;
                 mbar_wait(bar_raw_full + rb, (it / NRAW) & 1);
                 const E* const cur = reinterpret_cast<const E*>(smem + L.off_raw + rb * L.raw_bytes);
-                float* const pw = s_pow + pb * (PROWS * PROW);
                 const int f = warp;
                 if (t0 + f < nfr) {
                     float2 v[16];
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                                 for (int t = 0; t < 8; ++t) {
                                     const float a = __int2float_rn((int)(rw[t].x << sh) >> 16);
                                     const float b = __int2float_rn((int)(rw[t].y << sh) >> 16);
-                                    v[8 * hb + t] = __fmul2_rn(make_float2(a, b), win[8 * hb + t]);
+                                    v[8 * hb + t] = __fmul2_rn(make_float2(a, b), win[32 * (8 * hb + t)]);
                                 }
                             }
 #undef B2A_LDR
@@ -207,7 +211,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(ra + 128 * t + 4));
                                 const float a = __int2float_rn((int)(w0 << sh) >> 16);
                                 const float b = __int2float_rn((int)(w1 << sh) >> 16);
-                                v[t] = __fmul2_rn(make_float2(a, b), win[t]);
+                                v[t] = __fmul2_rn(make_float2(a, b), win[32 * t]);
                             }
                         }
                     } else {
@@ -216,12 +220,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
 #pragma unroll
                             for (int t = 0; t < 16; ++t) {
                                 const float4 q4 = *reinterpret_cast<const float4*>(a + 64 * t);
-                                v[t] = __fmul2_rn(h ? make_float2(q4.y, q4.w) : make_float2(q4.x, q4.z), win[t]);
+                                v[t] = __fmul2_rn(h ? make_float2(q4.y, q4.w) : make_float2(q4.x, q4.z), win[32 * t]);
                             }
                         } else {
 #pragma unroll
                             for (int t = 0; t < 16; ++t)
-                                v[t] = __fmul2_rn(make_float2(a[64 * t + h], a[64 * t + 2 + h]), win[t]);
+                                v[t] = __fmul2_rn(make_float2(a[64 * t + h], a[64 * t + 2 + h]), win[32 * t]);
                         }
                     }
                     Dft<16>::run(v);
@@ -267,9 +271,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                     // ---- radix-2 combination of the two halves -------------------------------------------
                     // half 0 finishes bins k = j + 16 r2 (and 512 - k), half 1 bins k = 256 - j - 16 r2 (and 512 - k):
                     // each lane hands its partner (lane ^ 16) the operand it does not use itself
-                    mbar_wait(bar_pow_empty + pb, ((it / NPOW) & 1) ^ 1);     // the mel warps are done with this slot
                     const float2* const wc = s_twc + (h ? 256 - j : j);
-                    float* const pcol = pw + 2 * f;
+                    float* const pcol = s_pow + 2 * f;                  // element (bin, frame): word (bin >> 1) PROW + 2 frame + (bin & 1)
 #pragma unroll
                     for (int r2 = 0; r2 < 8; ++r2) {
                         const float2 send = h ? v[r2] : Bm[r2];
@@ -297,23 +300,80 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                             pcol[192 * PROW] = x2c.x * x2c.x + x2c.y * x2c.y;
                         }
                     }
-                } else {
-                    // a warp with no frame in this tile still takes its turn on both barriers
-                    mbar_wait(bar_pow_empty + pb, ((it / NPOW) & 1) ^ 1);
+                }
+                // ---- the tile's mel bands, by all sixteen warps: lane & 15 = frame, the two halves of a warp take
+                // neighbouring bands (pairs pp = warp, warp + 16, ...); broadcast weights, conflict-free powers ------
+                mbar_wait(bar_tile_empty + pb, ((it / NTILE) & 1) ^ 1);       // the epilogue warps are done with this tile slot
+                frame_warps_sync();                                           // every frame's powers are in the tile
+                {
+                    const int l16 = lane & 15, par = lane >> 4;
+                    float* const trow = s_tile + pb * (rows * F) + l16;        // element (row, frame l16)
+                    float* const dbt = s_dbc + l16 * (n_mels + 4);             // mfcc: this frame's dB row
+                    const float2* pl = reinterpret_cast<const float2*>(s_pow) + l16;
+                    for (int pp = warp; 2 * pp < n_mels; pp += kFftWarps) {
+                        const int i = 2 * pp + par;
+                        const int4 d = i < n_mels ? s_desc[i] : make_int4(0, 0, 0, 0);
+                        const int steps = max(d.y, __shfl_xor_sync(0xffffffffu, d.y, 16));
+                        const float2* pr = pl + d.x;
+                        const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
+                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 2
+                        for (int q4 = 0; q4 < steps; ++q4) {
+                            if (q4 < d.y) {
+                                const float4 w = wq[q4];
+                                const float2 p0 = pr[0], p1 = pr[PROW / 2];
+                                a0 = fmaf(w.x, p0.x, a0); a1 = fmaf(w.y, p0.y, a1);
+                                a2 = fmaf(w.z, p1.x, a2); a3 = fmaf(w.w, p1.y, a3);
+                            }
+                            pr += PROW;
+                        }
+                        if (i < n_mels) {
+                            const float vv = db10((a0 + a1) + (a2 + a3));
+                            trow[d.w * F] = vv;
+                            if (MFCC) dbt[d.w] = vv;
+                        }
+                    }
+                }
+                frame_warps_sync();                                           // all dB written; the power tile may be refilled
+                if constexpr (MFCC) {
+                    // ---- DCT-II of this warp's frame, assuming the top_db clip (known only after the clip's last
+                    // tile) will not engage; checked at clip end.  Lane l owns coefficients cpl l .. cpl l + cpl - 1;
+                    // dB broadcast four bands at a time, basis as conflict-free 128-bit loads.
+                    if (t0 + f < nfr) {
+                        const int cpl = (p.n_mfcc + 31) / 32;
+                        const int k0 = lane * cpl;
+                        if (k0 < p.n_mfcc) {
+                            const bool two = cpl > 1 && k0 + 1 < p.n_mfcc;
+                            const float4* d4 = reinterpret_cast<const float4*>(s_dbc + f * (n_mels + 4));
+                            const float4* b4 = reinterpret_cast<const float4*>(s_dct) + k0;
+                            float* const tcol = s_tile + pb * (rows * F) + f;
+                            float c0 = 0.f, c1 = 0.f;
+#pragma unroll 4
+                            for (int m4 = 0; m4 < n_mels / 4; ++m4) {
+                                const float4 dv = d4[m4];
+                                const float4 ba = b4[m4 * p.n_mfcc];
+                                c0 = fmaf(ba.x, dv.x, c0); c0 = fmaf(ba.y, dv.y, c0); c0 = fmaf(ba.z, dv.z, c0); c0 = fmaf(ba.w, dv.w, c0);
+                                if (two) {
+                                    const float4 bb = b4[m4 * p.n_mfcc + 1];
+                                    c1 = fmaf(bb.x, dv.x, c1); c1 = fmaf(bb.y, dv.y, c1); c1 = fmaf(bb.z, dv.z, c1); c1 = fmaf(bb.w, dv.w, c1);
+                                }
+                            }
+                            tcol[(n_mels + k0) * F] = c0;
+                            if (two) tcol[(n_mels + k0 + 1) * F] = c1;
+                        }
+                    }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_pow_full + pb);
+                if (lane == 0) mbar_arrive(bar_tile_full + pb);
             }
         }
     } else {
-        // =========================== mel warps (warp 0 of them also stages the raw tiles) =========
+        // =========================== epilogue warps (warp 0 of them also stages the raw tiles) =========
         const int mw = warp - kFftWarps, mtid = tid - 32 * kFftWarps;
-        const int l16 = lane & 15, par = lane >> 4;
+        const int ef = mtid & 15, er0 = mtid >> 4;               // this thread's frame lane and first row of a tile (rows er0 + 8 i)
         constexpr int V = 16 / (int)sizeof(E);
         const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
 
-        // Stage tile (clip, t0) into raw slot `slot` (same protocol as logmel512.cu: one TMA bulk copy for the
-        // aligned interior, plain stores for the zero padding and the unaligned tail, plain loads otherwise).
         auto stage = [&](long long clip, int t0, uint32_t slot) {
             E* const dst = reinterpret_cast<E*>(smem + L.off_raw + slot * L.raw_bytes);
             uint64_t* const bar = bar_raw_full + slot;
@@ -382,11 +442,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
             for (int i = 0; i < NRAW; ++i) stage_next();
 
         // Deferred rewrite of the PREVIOUS clip during the current clip's tiles (prefetched before the wait for
-        // the power tile): mel = power_to_db(ref=max, top_db) + min-max on float4 slices; mfcc = per-row z-score.
+        // the tile): mel = power_to_db(ref=max, top_db) + min-max on float4 slices; mfcc = per-row z-score.
         constexpr int NPF = 4;                                   // float4 (mel) / floats (mfcc) per thread per tile
         float4* nq = nullptr;
         float* nz = nullptr;
-        int nq_n = 0, nq_done = 0;                               // element count (float4 or float), elements rewritten
+        int nq_n = 0, nq_done = 0;
         float nq_vmax = 0.f, nq_lo = 0.f, nq_range = 1.f, nq_inv = 1.f, nz_inv = 1.f;
         auto nrm = [&](float x) {
             const float num = fmaxf(x - nq_vmax, -p.top_db) - nq_lo;
@@ -406,6 +466,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
             }
             nq_done = nq_n;
         };
+        // mfcc: this thread owns rows er0 + 8 i of every tile at frame lane ef: running sums about the row's first value
+        constexpr int kZR = 8;                                   // n_mfcc <= 64
+        float zS[kZR], zQ[kZR], zx0[kZR];
 
         uint32_t it = 0;
         for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
@@ -415,13 +478,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                                     : p.out + (size_t)clip * (MFCC ? p.n_mfcc : n_mels) * nfr;
             float* const inter = MFCC ? p.inter + (size_t)blockIdx.x * n_mels * p.n_frames : outb;
             float vmax = -3.0e38f, vmin = 3.0e38f;
-            if constexpr (MFCC) {
-                for (int i = mtid; i < 2 * p.n_mfcc * F; i += kMelThreads) s_zacc[i] = 0.f;    // (tile 0 fills the third plane)
-            }
+#pragma unroll
+            for (int i = 0; i < kZR; ++i) { zS[i] = 0.f; zQ[i] = 0.f; zx0[i] = 0.f; }
 
             for (int tile = 0; tile < tiles; ++tile, ++it) {
                 const int t0 = tile * F;
-                const uint32_t pb = it % NPOW;
+                const uint32_t pb = it % NTILE;
                 float4 nx[MFCC ? 1 : NPF];
                 float zx[MFCC ? NPF : 1];
                 const bool nq_live = nq_done < nq_n;
@@ -434,52 +496,39 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                         }
                     }
                 }
-                mbar_wait(bar_pow_full + pb, (it / NPOW) & 1);
+                mbar_wait(bar_tile_full + pb, (it / NTILE) & 1);
                 if (mw == 0) stage_next();                         // raw slot it % NRAW is free again
-                // ---- mel bands: lane & 15 = frame, the two halves of the warp take neighbouring bands ----------
+                // ---- tile -> global: 16 consecutive frames of a row per half-warp ---------------------------
                 {
-                    const int t = t0 + l16;
+                    const int t = t0 + ef;
                     const bool valid = t < nfr;
-                    float* const outp = inter + t;
-                    const float2* pl = reinterpret_cast<const float2*>(s_pow + pb * (PROWS * PROW)) + l16;
-                    // Two band pairs in flight per warp (pairs pp and pp + 4: each half-warp then has two independent
-                    // dot products, six loads per step) — this warp shares its scheduler with four FFT warps and a
-                    // single dependent load -> FMA chain left it at ~0.1 instructions per cycle.
-                    for (int pp = mw; 2 * pp < n_mels; pp += 2 * kMelWarps) {
-                        const int iA = 2 * pp + par, iB = 2 * (pp + kMelWarps) + par;
-                        const int4 dA = iA < n_mels ? s_desc[iA] : make_int4(0, 0, 0, 0);
-                        const int4 dB = iB < n_mels ? s_desc[iB] : make_int4(0, 0, 0, 0);
-                        const int mine = max(dA.y, dB.y);
-                        const int steps = max(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
-                        const float2* prA = pl + dA.x;
-                        const float2* prB = pl + dB.x;
-                        const float4* wA = reinterpret_cast<const float4*>(s_melw + dA.z);
-                        const float4* wB = reinterpret_cast<const float4*>(s_melw + dB.z);
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-#pragma unroll 2
-                        for (int q4 = 0; q4 < steps; ++q4) {
-                            float4 w = make_float4(0.f, 0.f, 0.f, 0.f), u = make_float4(0.f, 0.f, 0.f, 0.f);
-                            float2 p0 = make_float2(0.f, 0.f), p1 = p0, r0 = p0, r1 = p0;
-                            if (q4 < dA.y) { w = wA[q4]; p0 = prA[0]; p1 = prA[PROW / 2]; }
-                            if (q4 < dB.y) { u = wB[q4]; r0 = prB[0]; r1 = prB[PROW / 2]; }
-                            a0 = fmaf(w.x, p0.x, a0); a1 = fmaf(w.y, p0.y, a1); a2 = fmaf(w.z, p1.x, a2); a3 = fmaf(w.w, p1.y, a3);
-                            b0 = fmaf(u.x, r0.x, b0); b1 = fmaf(u.y, r0.y, b1); b2 = fmaf(u.z, r1.x, b2); b3 = fmaf(u.w, r1.y, b3);
-                            prA += PROW; prB += PROW;
+                    const float* tl = s_tile + pb * (rows * F) + ef;
+                    for (int r = er0; r < n_mels; r += 8) {            // raw dB rows
+                        const float vv = tl[r * F];
+                        if (valid) {
+                            inter[(size_t)r * nfr + t] = vv;
+                            vmax = fmaxf(vmax, vv);
+                            vmin = fminf(vmin, vv);
                         }
-                        if (iA < n_mels) {
-                            const float vv = db10((a0 + a1) + (a2 + a3));
-                            if (MFCC) s_db[dA.w * F + l16] = vv;
-                            if (valid) { outp[(size_t)dA.w * nfr] = vv; vmax = fmaxf(vmax, vv); vmin = fminf(vmin, vv); }
-                        }
-                        if (iB < n_mels) {
-                            const float vv = db10((b0 + b1) + (b2 + b3));
-                            if (MFCC) s_db[dB.w * F + l16] = vv;
-                            if (valid) { outp[(size_t)dB.w * nfr] = vv; vmax = fmaxf(vmax, vv); vmin = fminf(vmin, vv); }
+                    }
+                    if constexpr (MFCC) {
+#pragma unroll
+                        for (int i = 0; i < kZR; ++i) {
+                            const int k = er0 + 8 * i;
+                            const float a = k < p.n_mfcc ? tl[(n_mels + k) * F] : 0.f;
+                            const float first = __shfl_sync(0xffffffffu, a, lane & 16);           // (outside the per-half condition)
+                            if (k < p.n_mfcc) {
+                                if (valid) outb[(size_t)k * nfr + t] = a;
+                                if (tile == 0) zx0[i] = first;                                    // frame 0 of the clip
+                                const float dd = valid ? a - zx0[i] : 0.f;
+                                zS[i] += dd;
+                                zQ[i] = fmaf(dd, dd, zQ[i]);
+                            }
                         }
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_pow_empty + pb);
+                if (lane == 0) mbar_arrive(bar_tile_empty + pb);
                 if (nq_live) {
 #pragma unroll
                     for (int k = 0; k < NPF; ++k) {
@@ -500,48 +549,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                     }
                     if (tile + 1 == tiles) nq_finish();
                 }
-                if constexpr (MFCC) {
-                    // DCT-II of this tile from the dB tile, assuming the top_db clip (known only after the clip's
-                    // last tile) will not engage; checked at clip end.  Stream s = 2 mw + par owns coefficients
-                    // s, s + 8, ...; lane & 15 = frame.  Per band one dB load and gh basis loads (uniform per half).
-                    mel_sync();
-                    const int t = t0 + l16;
-                    const bool valid = t < nfr;
-                    const int s0 = 2 * mw + par;
-                    float a[kMaxGh];
-#pragma unroll
-                    for (int g = 0; g < kMaxGh; ++g) a[g] = 0.f;
-                    const float* dbl = s_db + l16;
-                    const float* bs = s_dct + s0;
-#pragma unroll 4
-                    for (int m = 0; m < n_mels; ++m) {
-                        const float dv = dbl[m * F];
-#pragma unroll
-                        for (int g = 0; g < kMaxGh; ++g)
-                            if (g < L.gh && s0 + kStreams * g < p.n_mfcc) a[g] = fmaf(bs[m * p.n_mfcc + kStreams * g], dv, a[g]);
-                    }
-#pragma unroll
-                    for (int g = 0; g < kMaxGh; ++g) {
-                        const int k = s0 + kStreams * g;
-                        const float first = __shfl_sync(0xffffffffu, a[g], par * 16);   // (outside the per-half condition)
-                        if (g < L.gh && k < p.n_mfcc) {
-                            if (valid) outb[(size_t)k * nfr + t] = a[g];
-                            // running sums about the row's first sample (frame 0 of the clip), per frame lane
-                            float* za = s_zacc + k * F + l16;
-                            if (tile == 0) za[2 * p.n_mfcc * F] = first;
-                            const float dd = valid ? a[g] - za[2 * p.n_mfcc * F] : 0.f;
-                            za[0] += dd;
-                            za[p.n_mfcc * F] = fmaf(dd, dd, za[p.n_mfcc * F]);
-                        }
-                    }
-                    mel_sync();                                    // s_db is rewritten by the next tile
-                }
             }
 
-            // ---- per-clip reductions (mel warps only) ------------------------------------------------
+            // ---- per-clip reductions (epilogue warps only) --------------------------------------------
             vmax = warp_max(vmax); vmin = warp_min(vmin);
             if (lane == 0) { s_red[mw] = vmax; s_red[32 + mw] = vmin; }
-            mel_sync();
+            mel_sync();                                            // also: every warp's stores of this clip are visible
             {
                 const float a = (lane < kMelWarps) ? s_red[lane] : -3.0e38f;
                 const float b = (lane < kMelWarps) ? s_red[32 + lane] : 3.0e38f;
@@ -566,36 +579,23 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                 float* outc = outb;
                 const float thr = vmax - p.top_db;
                 const bool clipped = vmin < thr;
-                if (clipped) {
-                    // rare: a band fell more than top_db below the clip's peak, so the clipped dB differ from what
-                    // the in-tile DCT saw -> recompute from the raw-dB scratch (L2 resident), 16 frames at a time
-                    for (int t0 = 0; t0 < nfr; t0 += F) {
-                        mel_sync();
-                        for (int i = mtid; i < n_mels * F; i += kMelThreads) {
-                            const int m = i / F, f = i % F, t = t0 + f;
-                            s_db[i] = (t < nfr) ? fmaxf(inter[(size_t)m * nfr + t], thr) : 0.f;
-                        }
-                        mel_sync();
-                        for (int i = mtid; i < p.n_mfcc * F; i += kMelThreads) {
-                            const int k = i / F, f = i % F, t = t0 + f;
-                            float acc = 0.f;
-                            for (int m = 0; m < n_mels; ++m) acc = fmaf(s_dct[m * p.n_mfcc + k], s_db[m * F + f], acc);
-                            if (t < nfr) outc[(size_t)k * nfr + t] = acc;
-                        }
-                    }
-                }
                 nq_finish();                                          // the previous clip's z-score, if any is left
                 mel_sync();                                           // ... by every warp, before s_zs changes
                 const float fn = (float)nfr;
                 if (!clipped) {
-                    // mean and variance from the per-lane running sums; rows rewritten during the next clip's tiles
-                    for (int k = mw; k < p.n_mfcc; k += kMelWarps) {
-                        const float* za = s_zacc + k * F;
-                        float S = lane < F ? za[lane] : 0.f, Q = lane < F ? za[p.n_mfcc * F + lane] : 0.f;
-                        S = warp_sum(S); Q = warp_sum(Q);
-                        if (lane == 0) {
+                    // mean and variance from the running sums of the 16 frame lanes (a half-warp holds one row set)
+#pragma unroll
+                    for (int i = 0; i < kZR; ++i) {
+                        float S = zS[i], Q = zQ[i];
+#pragma unroll
+                        for (int o = 8; o > 0; o >>= 1) {
+                            S += __shfl_xor_sync(0xffffffffu, S, o);
+                            Q += __shfl_xor_sync(0xffffffffu, Q, o);
+                        }
+                        const int k = er0 + 8 * i;
+                        if (ef == 0 && k < p.n_mfcc) {
                             const float md = __fdiv_rn(S, fn);
-                            s_zs[2 * k] = za[2 * p.n_mfcc * F] + md;
+                            s_zs[2 * k] = zx0[i] + md;
                             s_zs[2 * k + 1] = __fdiv_rn(1.0f, sqrtf(fmaxf(fmaf(-md, md, __fdiv_rn(Q, fn)), 0.f)) + 1e-8f);
                         }
                     }
@@ -606,7 +606,16 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                     mel_sync();
                     continue;
                 }
+                // rare: a band fell more than top_db below the clip's peak, so the clipped dB differ from what the
+                // frame warps' DCT saw -> recompute from the raw-dB scratch (L2 resident), then the three-sweep z-score
                 nq_n = nq_done = 0;
+                for (int i = mtid; i < p.n_mfcc * nfr; i += kMelThreads) {
+                    const int k = i / nfr, t = i - k * nfr;
+                    const float* bk = p.dct + (size_t)k * n_mels;
+                    float acc = 0.f;
+                    for (int m = 0; m < n_mels; ++m) acc = fmaf(__ldg(bk + m), fmaxf(inter[(size_t)m * nfr + t], thr), acc);
+                    outc[i] = acc;
+                }
                 mel_sync();
                 for (int k = mw; k < p.n_mfcc; k += kMelWarps) {      // deep.py:326-328, three sweeps over an L2-resident row
                     float* row = outc + (size_t)k * nfr;
@@ -632,8 +641,9 @@ size_t logmel1024_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, int n_
     return (size_t)make_layout(hop, n_mels, mel_wpad, i16, n_mfcc).total + 128;
 }
 
-bool logmel1024_supports(int hop, int n_mfcc) {
-    return hop > 0 && (hop % 4) == 0 && n_mfcc <= kStreams * kMaxGh;
+bool logmel1024_supports(int hop, int n_mels, int n_mfcc) {
+    return hop > 0 && (hop % 4) == 0 && n_mels <= 512 && n_mfcc <= 32 * kMaxCoefPerLane &&
+           (n_mfcc == 0 || (n_mels % 4) == 0);
 }
 
 template <bool I16, int KIND, bool RAG>

@@ -24,7 +24,9 @@ sys.path.insert(0, str(ROOT))
 
 
 def run(classes: int = 27, per_class: int = 260, devices: str = "all", dir: str = "/dev/shm/b2a_stage2",
-        repeat: int = 3) -> dict:
+        repeat: int = 3, file_rate: int = 16000) -> dict:
+    """file_rate != 16000 writes the same clips as files recorded at another rate (5 s each): Stage 2 then
+    decodes them natively at that rate and resamples on the device (deep.py:44-50 -> librosa.load)."""
     args = argparse.Namespace(classes=classes, per_class=per_class, devices=devices, dir=dir, repeat=repeat)
     import audio_edge_ml_pipeline_b200 as P
     from audio_edge_ml_pipeline_b200 import _lib as B
@@ -36,14 +38,15 @@ def run(classes: int = 27, per_class: int = 260, devices: str = "all", dir: str 
         shutil.rmtree(root)
     ds = root / "fsc22_device_augmented"
     rng = np.random.default_rng(2026)
-    pool = [synth.pad_or_trim_pcm(synth.to_pcm16(synth.make_clip(rng, k % 5, 16000, 80000)), 80000) for k in range(40)]
+    n_file = 5 * file_rate
+    pool = [synth.pad_or_trim_pcm(synth.to_pcm16(synth.make_clip(rng, k % 5, file_rate, n_file)), n_file) for k in range(40)]
     t0 = time.perf_counter()
     n = 0
     for c in range(args.classes):
         d = ds / f"class_{c:02d}"
         d.mkdir(parents=True)
         for i in range(args.per_class):
-            wavio.write_wav_pcm16(d / f"clip_{i:04d}.wav", np.roll(pool[(c + i) % len(pool)], 37 * i), 16000)
+            wavio.write_wav_pcm16(d / f"clip_{i:04d}.wav", np.roll(pool[(c + i) % len(pool)], 37 * i), file_rate)
             n += 1
     gen_s = time.perf_counter() - t0
 
@@ -68,7 +71,7 @@ def run(classes: int = 27, per_class: int = 260, devices: str = "all", dir: str 
         "seconds": {"loader_scan": best[0], "decode+h2d+kernel+d2h": best[1], "np.save": best[2], "total": best[3]},
         "extract_only_clips_per_s": n / best[1], "features_bytes": int(fs.features.nbytes),
         "decode_workers": P.extractors.DECODE_WORKERS, "host_cores": os.cpu_count(),
-        "dataset": f"{args.classes} classes x {args.per_class} PCM16 5 s 16 kHz WAVs on {root}",
+        "dataset": f"{args.classes} classes x {args.per_class} PCM16 5 s {file_rate} Hz WAVs on {root}", "file_rate": file_rate,
         "dataset_write_s": gen_s, "device_count_visible": B.device_count(),
     }
     ext.close()
@@ -127,12 +130,13 @@ def main():
     ap.add_argument("--devices", default="all")
     ap.add_argument("--dir", default="/dev/shm/b2a_stage2")
     ap.add_argument("--repeat", type=int, default=3)
+    ap.add_argument("--file-rate", type=int, default=16000, help="rate the WAV files are written at (!= 16000: device resampling)")
     ap.add_argument("--device-augmented", action="store_true", help="config 5 without the WAV round trip (Stage 1b on the device)")
     a = ap.parse_args()
     if a.device_augmented:
         print(json.dumps(run_device_augmented(a.classes, devices=a.devices if a.devices != "all" else "0")), flush=True)
         return
-    print(json.dumps(run(a.classes, a.per_class, a.devices, a.dir, a.repeat)), flush=True)
+    print(json.dumps(run(a.classes, a.per_class, a.devices, a.dir, a.repeat, a.file_rate)), flush=True)
 
 
 if __name__ == "__main__":
