@@ -380,14 +380,14 @@ def run_ours(args):
 
 def _secondary(torch, dev, local, peak):
     """Driver-visible secondary numbers (N = 1 only): the other two extractors device-resident at their
-    BASELINE shapes, the reference-default mfcc shape (generic kernel), and config 5 end to end."""
+    BASELINE shapes, the reference-default mfcc shape (n_fft 1024 kernel), and config 5 end to end."""
     import audio_edge_ml_pipeline_b200 as P
     out = {}
     stream = torch.cuda.current_stream().cuda_stream
     jobs = [("mfcc", EXTRA["mfcc"], 50000), ("cqt", EXTRA["cqt"], 16384),
             ("mfcc_reference_defaults", dict(sr=22050, n=110250, rows=40, hop=512, bytes=110250 * 2 + 40 * 216 * 4,
                                              name="audio_mfcc_seq", params=dict(duration=5.0),
-                                             workload="audio_mfcc_seq reference defaults 22050/1024/512/128 mels -> 40 (generic kernel)"),
+                                             workload="audio_mfcc_seq reference defaults 22050/1024/512/128 mels -> 40 (logmel1024 kernel)"),
              20000)]
     for key, x, n in jobs:
         try:
