@@ -62,6 +62,9 @@ __device__ __forceinline__ void frame_warps_sync() {
     asm volatile("bar.sync 2, %0;" ::"n"(32 * kFftWarps) : "memory");
 }
 
+// floats between the dB blocks of two frame quads: + 4 keeps a half-warp's sixteen frames on sixteen banks
+__host__ __device__ constexpr int dbc_quad(int n_mels) { return 4 * n_mels + 4; }
+
 struct Layout {
     int chunk, raw_bytes, rows;                  // rows of a tile: n_mels (+ n_mfcc)
     int off_raw, off_xch, off_pow, off_tile, off_win, off_tw2, off_tw1, off_twc, off_melw, off_melk, off_red, off_bar, off_dbc, off_dct, total;
@@ -87,8 +90,8 @@ __host__ __device__ inline Layout make_layout(int hop, int n_mels, int mel_wpad,
     L.off_melk = take(n_mels * 16);                   // per position: {pair-row offset, 4-bin steps, weight offset, band}
     L.off_red = take((64 + 2 * (mfcc ? n_mfcc : 1)) * 4);
     L.off_bar = take((kMaxRaw + 2 * NTILE) * 8 + kMaxRaw * 4);
-    L.off_dbc = take(mfcc ? F * (n_mels + 4) * 4 : 0);        // mfcc: dB of the tile as [frame][band] rows (stride n_mels + 4)
-    L.off_dct = take(mfcc ? n_mels * n_mfcc * 4 : 0);        // DCT-II basis as [band / 4][coefficient][4]
+    L.off_dbc = take(mfcc ? 4 * dbc_quad(n_mels) * 4 : 0);   // mfcc: dB of the tile as [frame quad][band][4 frames]
+    L.off_dct = take(mfcc ? n_mels * ((n_mfcc + 3) & ~3) * 4 : 0);   // DCT-II basis as [coefficient / 4][band][4], zero rows past n_mfcc
     L.total = o;
     return L;
 }
@@ -140,9 +143,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
     }
     for (int i = tid; i < 4 * PROW; i += kThreads) s_pow[256 * PROW + i] = 0.f;   // bins 512..519 (512 is rewritten per tile)
     if constexpr (MFCC) {
-        for (int i = tid; i < n_mels * p.n_mfcc; i += kThreads) {         // [m / 4][k][m & 3] (n_mels % 4 == 0)
-            const int e = i & 3, k = (i >> 2) % p.n_mfcc, m4 = (i >> 2) / p.n_mfcc;
-            s_dct[i] = p.dct[(size_t)k * n_mels + 4 * m4 + e];
+        for (int i = tid; i < n_mels * ((p.n_mfcc + 3) & ~3); i += kThreads) {   // [k / 4][m][k & 3]
+            const int e = i & 3, m = (i >> 2) % n_mels, k = 4 * ((i >> 2) / n_mels) + e;
+            s_dct[i] = k < p.n_mfcc ? p.dct[(size_t)k * n_mels + m] : 0.f;
         }
     }
     if (tid == 0) {
@@ -308,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                 {
                     const int l16 = lane & 15, par = lane >> 4;
                     float* const trow = s_tile + pb * (rows * F) + l16;        // element (row, frame l16)
-                    float* const dbt = s_dbc + l16 * (n_mels + 4);             // mfcc: this frame's dB row
+                    float* const dbt = s_dbc + (l16 >> 2) * dbc_quad(n_mels) + (l16 & 3);   // mfcc: (quad, band 0, frame)
                     const float2* pl = reinterpret_cast<const float2*>(s_pow) + l16;
                     for (int pp = warp; 2 * pp < n_mels; pp += kFftWarps) {
                         const int i = 2 * pp + par;
@@ -330,37 +333,58 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                         if (i < n_mels) {
                             const float vv = db10((a0 + a1) + (a2 + a3));
                             trow[d.w * F] = vv;
-                            if (MFCC) dbt[d.w] = vv;
+                            if (MFCC) dbt[4 * d.w] = vv;
                         }
                     }
                 }
                 frame_warps_sync();                                           // all dB written; the power tile may be refilled
                 if constexpr (MFCC) {
-                    // ---- DCT-II of this warp's frame, assuming the top_db clip (known only after the clip's last
-                    // tile) will not engage; checked at clip end.  Lane l owns coefficients cpl l .. cpl l + cpl - 1;
-                    // dB broadcast four bands at a time, basis as conflict-free 128-bit loads.
-                    if (t0 + f < nfr) {
-                        const int cpl = (p.n_mfcc + 31) / 32;
-                        const int k0 = lane * cpl;
-                        if (k0 < p.n_mfcc) {
-                            const bool two = cpl > 1 && k0 + 1 < p.n_mfcc;
-                            const float4* d4 = reinterpret_cast<const float4*>(s_dbc + f * (n_mels + 4));
-                            const float4* b4 = reinterpret_cast<const float4*>(s_dct) + k0;
-                            float* const tcol = s_tile + pb * (rows * F) + f;
-                            float c0 = 0.f, c1 = 0.f;
+                    // ---- DCT-II of the tile as a 16 frames x n_mfcc x n_mels product, assuming the top_db clip (known
+                    // only after the clip's last tile) will not engage; checked at clip end.  A warp takes four
+                    // coefficients at a time (kc = warp, warp + 16, ...); lane >> 3 = frame quad, lane & 7 strides the
+                    // bands, so a lane accumulates a 4 frames x 4 coefficients block from two conflict-free 128-bit
+                    // loads per band (16 FMA per 32 bytes of shared memory), and the eight band lanes are folded
+                    // with a transposing shuffle reduction (14 shuffles for 16 sums).
+                    const int fq = lane >> 3, ml = lane & 7;
+                    const float4* const d4 = reinterpret_cast<const float4*>(s_dbc + fq * dbc_quad(n_mels));
+                    float* const tq = s_tile + pb * (rows * F) + n_mels * F + 4 * fq + (ml >> 1);
+                    for (int kc = warp; 4 * kc < p.n_mfcc; kc += kFftWarps) {
+                        const float4* const b4 = reinterpret_cast<const float4*>(s_dct) + kc * n_mels;
+                        float2 acc[8];                                       // [frame of the quad][coefficient pair]
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i] = make_float2(0.f, 0.f);
 #pragma unroll 4
-                            for (int m4 = 0; m4 < n_mels / 4; ++m4) {
-                                const float4 dv = d4[m4];
-                                const float4 ba = b4[m4 * p.n_mfcc];
-                                c0 = fmaf(ba.x, dv.x, c0); c0 = fmaf(ba.y, dv.y, c0); c0 = fmaf(ba.z, dv.z, c0); c0 = fmaf(ba.w, dv.w, c0);
-                                if (two) {
-                                    const float4 bb = b4[m4 * p.n_mfcc + 1];
-                                    c1 = fmaf(bb.x, dv.x, c1); c1 = fmaf(bb.y, dv.y, c1); c1 = fmaf(bb.z, dv.z, c1); c1 = fmaf(bb.w, dv.w, c1);
-                                }
-                            }
-                            tcol[(n_mels + k0) * F] = c0;
-                            if (two) tcol[(n_mels + k0 + 1) * F] = c1;
+                        for (int m = ml; m < n_mels; m += 8) {
+                            const float4 dv = d4[m], bv = b4[m];
+                            const float2 b01 = make_float2(bv.x, bv.y), b23 = make_float2(bv.z, bv.w);
+                            acc[0] = __ffma2_rn(bc2(dv.x), b01, acc[0]); acc[1] = __ffma2_rn(bc2(dv.x), b23, acc[1]);
+                            acc[2] = __ffma2_rn(bc2(dv.y), b01, acc[2]); acc[3] = __ffma2_rn(bc2(dv.y), b23, acc[3]);
+                            acc[4] = __ffma2_rn(bc2(dv.z), b01, acc[4]); acc[5] = __ffma2_rn(bc2(dv.z), b23, acc[5]);
+                            acc[6] = __ffma2_rn(bc2(dv.w), b01, acc[6]); acc[7] = __ffma2_rn(bc2(dv.w), b23, acc[7]);
                         }
+                        float a[16];                                         // a[4 f + k]
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { a[2 * i] = acc[i].x; a[2 * i + 1] = acc[i].y; }
+                        const bool h4 = ml & 4, h2 = ml & 2, h1 = ml & 1;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float keep = h4 ? a[j + 8] : a[j], send = h4 ? a[j] : a[j + 8];
+                            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float keep = h2 ? a[j + 4] : a[j], send = h2 ? a[j] : a[j + 4];
+                            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const float keep = h1 ? a[j + 2] : a[j], send = h1 ? a[j] : a[j + 2];
+                            a[j] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+                        }
+                        // a[j] is now the full sum of block element j + 2 ml: frame ml >> 1, coefficient 2 (ml & 1) + j
+                        const int k = 4 * kc + 2 * (ml & 1);
+                        if (k < p.n_mfcc) tq[k * F] = a[0];
+                        if (k + 1 < p.n_mfcc) tq[(k + 1) * F] = a[1];
                     }
                 }
                 __syncwarp();
