@@ -262,7 +262,32 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
                 for (int v : order) { if (seen[v]++) perm = false; }
                 if (!perm) order = idx;
             }
-            if (try1024) order = idx;        // 1024 kernel: descending width, neighbours share a warp's two halves
+            if (try1024) {
+                // 1024 kernel: positions in descending width; positions 2i and 2i + 1 share a warp's two halves and
+                // run the same number of 4-bin steps, so the narrower band is padded with zero weights to its
+                // neighbour's length (leading zeros where trailing ones would read past the power tile)
+                order = idx;
+                std::vector<float> wq2;
+                const int prow_cap = b2a::logmel1024_pow_rows();
+                for (size_t i = 0; i < idx.size(); i += 2) {
+                    const int steps = cnt4[idx[i]];
+                    for (size_t e = i; e < std::min(i + 2, idx.size()); ++e) {
+                        const int m = idx[e];
+                        int start = k0e[m];
+                        if (start / 2 + 2 * steps > prow_cap) start = 2 * (prow_cap - 2 * steps);
+                        const int lead = h->mel.k0[m] - start;
+                        off4[m] = (int)wq2.size();
+                        for (int q = 0; q < 4 * steps; ++q) {
+                            const int src = q - lead;
+                            wq2.push_back(src >= 0 && src < h->mel.cnt[m] ? 0.25f * h->mel.w[h->mel.off[m] + src] : 0.f);
+                        }
+                        k0e[m] = start;
+                        cnt4[m] = steps;
+                    }
+                }
+                if (wq2.empty()) wq2.assign(4, 0.f);
+                wq.swap(wq2);
+            }
             h->mel_wpad = (int)wq.size();
             const size_t smem512 = try512
                 ? b2a::logmel512_smem_bytes(cfg->hop_length, cfg->n_mels, h->mel_wpad, cfg->input_dtype == B2A_IN_I16, mfcc ? cfg->n_mfcc : 0)

@@ -51,6 +51,7 @@ cudaError_t launch_logmel512(const FrontParams& p, bool i16, int kind, int grid,
 // the frame's mel bands and DCT in parallel lanes); needs hop % 4 == 0; mel_order deals the bands to lanes by width
 size_t logmel1024_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc);  // n_mfcc = 0: mel
 bool logmel1024_supports(int hop, int n_mels, int n_mfcc);
+int logmel1024_pow_rows();       // bin-pair rows of the power tile (513 bins + padding): reads must stay below it
 cudaError_t launch_logmel1024(const FrontParams& p, bool i16, int kind, int grid, cudaStream_t st);
 
 }  // namespace b2a

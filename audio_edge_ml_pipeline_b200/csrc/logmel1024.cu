@@ -57,6 +57,18 @@ constexpr int kMaxCoefPerLane = 2;              // n_mfcc <= 64
 __device__ __forceinline__ void mel_sync() {
     asm volatile("bar.sync 1, %0;" ::"n"(kMelThreads) : "memory");
 }
+// one int16 of a 32-bit word, sign-extended: sel = 0x9910 (low) / 0xBB32 (high)
+__device__ __forceinline__ int pcm_pick(uint32_t w, uint32_t sel) {
+    int r;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "r"(sel));
+    return r;
+}
+// (e + w conj(o), e - w conj(o)); the second as 2e - first like bfly_w
+__device__ __forceinline__ void bfly_wc(float2 e, float2 o, float2 w, float2& a, float2& b) {
+    a = __ffma2_rn(make_float2(o.y, o.x), bc2(w.y), __ffma2_rn(o, make_float2(w.x, -w.x), e));
+    b = __ffma2_rn(e, bc2(2.0f), make_float2(-a.x, -a.y));
+}
+
 // barrier among the 16 frame warps only (named barrier 2)
 __device__ __forceinline__ void frame_warps_sync() {
     asm volatile("bar.sync 2, %0;" ::"n"(32 * kFftWarps) : "memory");
@@ -132,7 +144,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
     for (int i = tid; i < 16 * 32; i += kThreads) {          // librosa.load's exact 1/32768 rides on the window (int16 input)
         const int t = i >> 5, l = i & 31, q = (l & 15) + 16 * t, hh = l >> 4;
         const float sc = I16 ? (1.0f / 32768.0f) : 1.0f;
-        s_win[i] = make_float2(p.window[4 * q + hh] * sc, p.window[4 * q + 2 + hh] * sc);
+        // half 1 (odd samples) is modulated by (-1)^m, m its sub-sequence index: its sub-FFT then holds
+        // Y[k] = E1[k + 256], so that its "v" is conj(E1[256 - k]) and its mirror operand conj(E1[k]) — the
+        // two halves hand each other the same-named register in the combination step
+        s_win[i] = make_float2(p.window[4 * q + hh] * sc, p.window[4 * q + 2 + hh] * (hh ? -sc : sc));
     }
     for (int i = tid; i < 15 * 16; i += kThreads) s_tw1[i] = p.tw[2 * ((i >> 4) + 1) * (i & 15)];
     for (int i = tid; i < 257; i += kThreads) s_twc[i] = p.tw2[i];
@@ -171,7 +186,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
         float2* const mst = xs + j;
         const float2* const mld = xs + (j ? 16 - j : 16);
         const float4* const t2 = reinterpret_cast<const float4*>(s_tw2) + j;
-        const int sh = h ? 0 : 16;                               // int16: the half's sample of each 32-bit word
+        const uint32_t psel = h ? 0xBB32u : 0x9910u;             // int16: prmt selector of the half's sample of each 32-bit
+                                                                 // word, sign-extended (nibble msb = replicate the sign)
 
         uint32_t it = 0;
         for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
@@ -199,8 +215,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                                 else { B2A_LDR(8); B2A_LDR(9); B2A_LDR(10); B2A_LDR(11); B2A_LDR(12); B2A_LDR(13); B2A_LDR(14); B2A_LDR(15); }
 #pragma unroll
                                 for (int t = 0; t < 8; ++t) {
-                                    const float a = __int2float_rn((int)(rw[t].x << sh) >> 16);
-                                    const float b = __int2float_rn((int)(rw[t].y << sh) >> 16);
+                                    const float a = __int2float_rn(pcm_pick(rw[t].x, psel));
+                                    const float b = __int2float_rn(pcm_pick(rw[t].y, psel));
                                     v[8 * hb + t] = __fmul2_rn(make_float2(a, b), win[32 * (8 * hb + t)]);
                                 }
                             }
@@ -212,8 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                                 uint32_t w0, w1;
                                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w0) : "r"(ra + 128 * t));
                                 asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w1) : "r"(ra + 128 * t + 4));
-                                const float a = __int2float_rn((int)(w0 << sh) >> 16);
-                                const float b = __int2float_rn((int)(w1 << sh) >> 16);
+                                const float a = __int2float_rn(pcm_pick(w0, psel));
+                                const float b = __int2float_rn(pcm_pick(w1, psel));
                                 v[t] = __fmul2_rn(make_float2(a, b), win[32 * t]);
                             }
                         }
@@ -272,33 +288,37 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                     // E_h[128] = conj(Z_h[128]) lives in lane j == 0 only (v[8] is untouched by the split)
                     const float2 e128 = make_float2(2.0f * v[8].x, -2.0f * v[8].y);
                     // ---- radix-2 combination of the two halves -------------------------------------------
-                    // half 0 finishes bins k = j + 16 r2 (and 512 - k), half 1 bins k = 256 - j - 16 r2 (and 512 - k):
-                    // each lane hands its partner (lane ^ 16) the operand it does not use itself
-                    const float2* const wc = s_twc + (h ? 256 - j : j);
-                    float* const pcol = s_pow + 2 * f;                  // element (bin, frame): word (bin >> 1) PROW + 2 frame + (bin & 1)
+                    // half 0 finishes bins kk = j + 16 r2 (and 512 - kk) from v = 2 E0[kk] and the partner's mirror
+                    // operand conj(2 E1[kk]); half 1 finishes kk = 256 - j - 16 r2 (and 512 - kk) from v = conj(2 E1[kk])
+                    // and the partner's mirror operand 2 E0[kk].  |E0 + W E1| = |v + W conj(recv)| in both (for half 1:
+                    // conjugate, then multiply by the unit W), so every lane runs the same code on the same registers.
+                    {
+                        const int kk0 = h ? 256 - j : j;
+                        const float2* wc = s_twc + kk0;
+                        const int wstep = h ? -16 : 16, pstep = h ? -8 * PROW : 8 * PROW;
+                        float* p1 = s_pow + 2 * f + (kk0 >> 1) * PROW + (kk0 & 1);              // bin kk: word (kk >> 1) PROW + 2 frame + (kk & 1)
+                        float* p2 = s_pow + 2 * f + ((512 - kk0) >> 1) * PROW + (kk0 & 1);      // bin 512 - kk (same parity)
 #pragma unroll
-                    for (int r2 = 0; r2 < 8; ++r2) {
-                        const float2 send = h ? v[r2] : Bm[r2];
-                        float2 recv;
-                        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 16);
-                        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 16);
-                        const float2 a = h ? recv : v[r2];              // 2 E0[k]
-                        const float2 b = h ? Bm[r2] : recv;             // 2 E1[k]
-                        const int k = h ? 256 - j - 16 * r2 : j + 16 * r2;
-                        const float2 w = h ? wc[-16 * r2] : wc[16 * r2];
-                        float2 x1c, x2c;
-                        bfly_w(a, b, w.x, w.y, x1c, x2c);               // 2 X[k], conj(2 X[512 - k])
-                        pcol[(k >> 1) * PROW + (k & 1)] = x1c.x * x1c.x + x1c.y * x1c.y;       // 4|X|^2: the 1/4 lives
-                        const int kn = 512 - k;                                                // in the mel weights
-                        pcol[(kn >> 1) * PROW + (kn & 1)] = x2c.x * x2c.x + x2c.y * x2c.y;
+                        for (int r2 = 0; r2 < 8; ++r2) {
+                            float2 recv;
+                            recv.x = __shfl_xor_sync(0xffffffffu, Bm[r2].x, 16);
+                            recv.y = __shfl_xor_sync(0xffffffffu, Bm[r2].y, 16);
+                            float2 x1c, x2c;
+                            bfly_wc(v[r2], recv, *wc, x1c, x2c);
+                            *p1 = x1c.x * x1c.x + x1c.y * x1c.y;          // 4|X|^2: the 1/4 lives in the mel weights
+                            *p2 = x2c.x * x2c.x + x2c.y * x2c.y;
+                            wc += wstep; p1 += pstep; p2 -= pstep;
+                        }
                     }
-                    {   // bins 128 and 384 (lane j == 0 of half 0 has both operands after one more exchange)
+                    {   // bins 128 and 384 (lane j == 0 of half 0 has both operands after one more exchange;
+                        // half 1's is conj(2 E1[128]) under its modulation)
                         float2 r128;
                         r128.x = __shfl_xor_sync(0xffffffffu, e128.x, 16);
-                        r128.y = __shfl_xor_sync(0xffffffffu, e128.y, 16);
+                        r128.y = -__shfl_xor_sync(0xffffffffu, e128.y, 16);
                         if (lane == 0) {
                             float2 x1c, x2c;
                             bfly_p(e128, r128, x1c, x2c);               // W^128 = s (1 - i)
+                            float* const pcol = s_pow + 2 * f;
                             pcol[64 * PROW] = x1c.x * x1c.x + x1c.y * x1c.y;
                             pcol[192 * PROW] = x2c.x * x2c.x + x2c.y * x2c.y;
                         }
@@ -315,23 +335,20 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
                     const float2* pl = reinterpret_cast<const float2*>(s_pow) + l16;
                     for (int pp = warp; 2 * pp < n_mels; pp += kFftWarps) {
                         const int i = 2 * pp + par;
-                        const int4 d = i < n_mels ? s_desc[i] : make_int4(0, 0, 0, 0);
-                        const int steps = max(d.y, __shfl_xor_sync(0xffffffffu, d.y, 16));
+                        const int4 d = s_desc[min(i, n_mels - 1)];             // (an odd last band pairs with itself)
                         const float2* pr = pl + d.x;
                         const float4* wq = reinterpret_cast<const float4*>(s_melw + d.z);
-                        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 2
-                        for (int q4 = 0; q4 < steps; ++q4) {
-                            if (q4 < d.y) {
-                                const float4 w = wq[q4];
-                                const float2 p0 = pr[0], p1 = pr[PROW / 2];
-                                a0 = fmaf(w.x, p0.x, a0); a1 = fmaf(w.y, p0.y, a1);
-                                a2 = fmaf(w.z, p1.x, a2); a3 = fmaf(w.w, p1.y, a3);
-                            }
+                        float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+#pragma unroll 4
+                        for (int q4 = 0; q4 < d.y; ++q4) {                      // d.y is the pair's: api.cu pads the narrower band
+                            const float4 w = wq[q4];
+                            const float2 p0 = pr[0], p1 = pr[PROW / 2];
+                            a01 = __ffma2_rn(make_float2(w.x, w.y), p0, a01);
+                            a23 = __ffma2_rn(make_float2(w.z, w.w), p1, a23);
                             pr += PROW;
                         }
                         if (i < n_mels) {
-                            const float vv = db10((a0 + a1) + (a2 + a3));
+                            const float vv = db10((a01.x + a01.y) + (a23.x + a23.y));
                             trow[d.w * F] = vv;
                             if (MFCC) dbt[4 * d.w] = vv;
                         }
@@ -664,6 +681,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel1024_kernel(FrontParams p) 
 size_t logmel1024_smem_bytes(int hop, int n_mels, int mel_wpad, bool i16, int n_mfcc) {
     return (size_t)make_layout(hop, n_mels, mel_wpad, i16, n_mfcc).total + 128;
 }
+
+int logmel1024_pow_rows() { return PROWS; }
 
 bool logmel1024_supports(int hop, int n_mels, int n_mfcc) {
     return hop > 0 && (hop % 4) == 0 && n_mels <= 512 && n_mfcc <= 32 * kMaxCoefPerLane &&

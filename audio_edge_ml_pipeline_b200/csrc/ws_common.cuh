@@ -8,6 +8,9 @@
 #ifndef B2A_AB_LOG2F
 #define B2A_AB_LOG2F 0
 #endif
+#ifndef B2A_MBAR_HINT
+#define B2A_MBAR_HINT 100000
+#endif
 
 namespace b2a {
 namespace ws {
@@ -66,6 +69,17 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#if B2A_MBAR_HINT
+    // with a suspend-time hint (ns): the waiting warp stays parked until the phase completes or the hint
+    // expires instead of re-issuing the try_wait / branch pair every few cycles next to the working warps
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)B2A_MBAR_HINT) : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"
@@ -73,6 +87,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+#endif
 }
 // 1-D TMA bulk copy global -> shared, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
