@@ -19,10 +19,11 @@ PKG = Path(__file__).resolve().parent
 # B2A_LIBRARY: another build of the same library (build.build_variant: numerics A/B experiments)
 LIB_PATH = Path(os.environ["B2A_LIBRARY"]) if os.environ.get("B2A_LIBRARY") else PKG / "libb2a.so"
 
-KIND_MEL, KIND_MFCC, KIND_CQT = 0, 1, 2
+KIND_MEL, KIND_MFCC, KIND_CQT, KIND_CLASSICAL = 0, 1, 2, 3
 IN_I16, IN_F32 = 0, 1
 PAD_CONSTANT, PAD_REFLECT = 0, 1
 TABLE_WINDOW, TABLE_MEL_DENSE, TABLE_DCT, TABLE_DECIM_TAPS, TABLE_CQT_LENGTHS, TABLE_CQT_BASIS = range(6)
+TABLE_CHROMA, TABLE_TONNETZ, TABLE_CONTRAST_BANDS = 6, 7, 8
 
 EXPORTED_SYMBOLS = [
     "b2a_default_config", "b2a_create", "b2a_destroy", "b2a_out_shape", "b2a_run_device",
@@ -31,7 +32,7 @@ EXPORTED_SYMBOLS = [
     "b2a_resampler_create", "b2a_resampler_destroy", "b2a_resampler_out_len", "b2a_resampler_geometry",
     "b2a_resampler_design", "b2a_resampler_run_host", "b2a_resampler_run_device", "b2a_resampler_last_error",
     "b2a_resampler_run_device_batch", "b2a_resampler_rates", "b2a_run_host_resampled",
-    "b2a_augment_host", "b2a_augment_device",
+    "b2a_augment_host", "b2a_augment_device", "b2a_classical_tunings",
 ]
 
 
@@ -89,6 +90,8 @@ def load_library() -> C.CDLL:
     lib.b2a_run_host_resampled.restype = C.c_int
     lib.b2a_last_launch_count.argtypes = [vp]
     lib.b2a_last_launch_count.restype = i64
+    lib.b2a_classical_tunings.argtypes = [vp, C.POINTER(C.c_float), i64]
+    lib.b2a_classical_tunings.restype = C.c_int
     lib.b2a_alloc_pinned.argtypes = [C.c_size_t, C.POINTER(vp)]
     lib.b2a_free_pinned.argtypes = [vp]
     lib.b2a_get_table.argtypes = [vp, i32, vp, C.POINTER(i64)]
@@ -321,6 +324,12 @@ class Engine:
         """Raw device pointers (e.g. torch ``tensor.data_ptr()``); asynchronous on ``stream``."""
         _check(self._lib.b2a_run_device(self._h, C.c_void_p(d_clips), n_clips, C.c_void_p(d_out),
                                         C.c_void_p(stream)))
+
+    def classical_tunings(self, n: int) -> np.ndarray:
+        """Tuning estimate (fractions of a semitone) of clips [0, n) of the last device launch (classical handles)."""
+        out = np.empty(n, dtype=np.float32)
+        _check(self._lib.b2a_classical_tunings(self._h, out.ctypes.data_as(C.POINTER(C.c_float)), n))
+        return out
 
     @property
     def last_launch_count(self) -> int:

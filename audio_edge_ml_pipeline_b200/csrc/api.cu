@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 
+#include "classical.h"
 #include "cqt.h"
 #include "frontend.h"
 #include "tables.h"
@@ -86,6 +87,16 @@ struct b2a_handle {
     float* d_dct = nullptr;
     float* d_inter = nullptr;
     int grid_cap = 0;
+    // classical
+    b2a::ClassicalTables cls;
+    float* d_chroma = nullptr;
+    float* d_tonnetz = nullptr;
+    int* d_bands = nullptr;          // [3][7]: start, count, q
+    float* d_cls_scratch = nullptr;
+    float* d_cls_tuning = nullptr;   // [cls_tuning_cap] tuning estimate of every clip of the last run
+    int64_t cls_tuning_cap = 0, cls_last_n = 0;
+    size_t cls_scratch_per_cta = 0;
+    int cls_frames = 0, cls_cand_cap = 0;
     // cqt
     b2a::CqtPlan cqt;
     b2a::CqtDevice cqtdev;
@@ -131,6 +142,8 @@ int b2a_default_config(int32_t kind, b2a_config* c) {
             c->sample_rate = 22050; c->n_mfcc = 40; c->n_fft = 1024; c->hop_length = 512; c->n_mels = 128; break;
         case B2A_KIND_CQT:   // deep.py:219-227
             c->sample_rate = 22050; c->hop_length = 512; c->n_bins = 84; c->bins_per_octave = 12; c->fmin = 0.0; break;
+        case B2A_KIND_CLASSICAL:   // classical.py:139-150
+            c->sample_rate = 22050; c->n_mfcc = 40; c->n_mels = 128; c->n_fft = 1024; c->hop_length = 512; break;
         default: return fail(B2A_EINVAL, "unknown kind");
     }
     return B2A_OK;
@@ -151,6 +164,7 @@ int b2a_destroy(b2a_handle* h) {
     cudaFree(h->d_k0); cudaFree(h->d_cnt); cudaFree(h->d_off); cudaFree(h->d_w);
     cudaFree(h->d_wq); cudaFree(h->d_k0e); cudaFree(h->d_cnt4); cudaFree(h->d_off4); cudaFree(h->d_order);
     cudaFree(h->d_dct); cudaFree(h->d_inter);
+    cudaFree(h->d_chroma); cudaFree(h->d_tonnetz); cudaFree(h->d_bands); cudaFree(h->d_cls_scratch); cudaFree(h->d_cls_tuning);
     b2a::cqt_device_free(&h->cqtdev);
     delete h;
     return B2A_OK;
@@ -321,6 +335,53 @@ int b2a_create(const b2a_config* cfg, int32_t device, b2a_handle** out) {
         const int rc = b2a::cqt_device_init(h->cqt, *cfg, h->sm_count, (size_t)prop.sharedMemPerBlockOptin,
                                             &h->cqtdev, &cerr);
         if (rc != 0) return bail(rc, cerr);
+    } else if (cfg->kind == B2A_KIND_CLASSICAL) {
+        const int n_fft = cfg->n_fft;
+        if (n_fft != 512 && n_fft != 1024 && n_fft != 2048) return bail(B2A_EINVAL, "classical: n_fft must be one of 512, 1024, 2048");
+        // classical.py:262-270 pads every segment to max(min_duration * sr, n_fft, 8 * hop) samples (delta width 9)
+        if (cfg->n_samples < std::max(n_fft, 8 * cfg->hop_length))
+            return bail(B2A_EINVAL, "classical: n_samples must be >= max(n_fft, 8 * hop_length) (classical.py pads to it)");
+        if (cfg->n_mels <= 0 || cfg->n_mels > 512) return bail(B2A_EINVAL, "n_mels out of range");
+        if (cfg->n_mfcc <= 0 || cfg->n_mfcc > cfg->n_mels) return bail(B2A_EINVAL, "n_mfcc must be in [1, n_mels]");
+        if (cfg->pad_mode != B2A_PAD_CONSTANT) return bail(B2A_EINVAL, "classical: pad_mode must be constant (librosa default)");
+        h->log2nc = ilog2(n_fft / 2);
+        h->rows = 6 * cfg->n_mfcc + 62;
+        h->cls_frames = h->frames;
+        h->frames = 1;
+        const int NC = n_fft / 2, n_bins = NC + 1;
+        h->window = b2a::hann_periodic(n_fft);
+        h->mel_dense = b2a::mel_filterbank(cfg->sample_rate, n_fft, cfg->n_mels);
+        h->mel = b2a::band_mel(h->mel_dense, cfg->n_mels, n_bins);
+        h->dct = b2a::dct2_ortho(cfg->n_mfcc, cfg->n_mels);
+        const char* perr = nullptr;
+        if (!b2a::build_classical_tables(cfg->sample_rate, n_fft, &h->cls, &perr))
+            return bail(B2A_EINVAL, perr ? perr : "classical tables failed");
+        if (h->mel.w.empty()) h->mel.w.push_back(0.f);
+        const size_t smem = b2a::classical_smem_bytes(h->log2nc, cfg->hop_length, cfg->n_mels, (int)h->mel.w.size());
+        if (smem > (size_t)prop.sharedMemPerBlockOptin)
+            return bail(B2A_EINVAL, "classical: hop_length/n_fft/n_mels combination exceeds shared memory");
+        std::vector<float> tw = b2a::twiddles(NC, NC);
+        std::vector<float> tw2 = b2a::twiddles(2 * NC, NC / 2 + 1);
+        CU_TRY_H(upload(h->window, &h->d_window));
+        CU_TRY_H(upload(tw, (float**)&h->d_tw));
+        CU_TRY_H(upload(tw2, (float**)&h->d_tw2));
+        CU_TRY_H(upload(h->mel.k0, &h->d_k0));
+        CU_TRY_H(upload(h->mel.cnt, &h->d_cnt));
+        CU_TRY_H(upload(h->mel.off, &h->d_off));
+        CU_TRY_H(upload(h->mel.w, &h->d_w));
+        CU_TRY_H(upload(h->dct, &h->d_dct));
+        CU_TRY_H(upload(h->cls.chroma, &h->d_chroma));
+        CU_TRY_H(upload(h->cls.tonnetz, &h->d_tonnetz));
+        std::vector<int> bands;
+        bands.insert(bands.end(), h->cls.band_start.begin(), h->cls.band_start.end());
+        bands.insert(bands.end(), h->cls.band_cnt.begin(), h->cls.band_cnt.end());
+        bands.insert(bands.end(), h->cls.band_q.begin(), h->cls.band_q.end());
+        CU_TRY_H(upload(bands, &h->d_bands));
+        // persistent CTAs (one clip at a time each); local maxima cannot be adjacent: at most every other piptrack bin
+        h->grid_cap = h->sm_count;     // ~240 registers x 256 threads: one resident CTA per SM
+        h->cls_cand_cap = h->cls_frames * ((h->cls.pip_k1 - h->cls.pip_k0 + 1) / 2 + 1);
+        h->cls_scratch_per_cta = b2a::classical_scratch_floats(n_fft, h->cls_frames, cfg->n_mels, cfg->n_mfcc, h->cls_cand_cap);
+        CU_TRY_H(cudaMalloc((void**)&h->d_cls_scratch, h->cls_scratch_per_cta * sizeof(float) * h->grid_cap));
     } else {
         return bail(B2A_EINVAL, "unknown kind");
     }
@@ -338,6 +399,16 @@ int b2a_out_shape(const b2a_handle* h, int32_t* rows, int32_t* frames) {
 
 int64_t b2a_last_launch_count(const b2a_handle* h) { return h ? h->last_launches : 0; }
 
+int b2a_classical_tunings(b2a_handle* h, float* out, int64_t n) {
+    if (!h || !out) return fail(B2A_EINVAL, "handle/out is NULL");
+    if (h->cfg.kind != B2A_KIND_CLASSICAL) return fail(B2A_EINVAL, "not a classical handle");
+    if (n < 0 || n > h->cls_last_n) return fail(B2A_EINVAL, "n exceeds the clips of the last launch");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaDeviceSynchronize());
+    if (n > 0) CU_TRY(cudaMemcpy(out, h->d_cls_tuning, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    return B2A_OK;
+}
+
 static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, float* d_out,
                            cudaStream_t st, int64_t* launches, const long long* rag_in = nullptr,
                            const int* rag_len = nullptr, const long long* rag_out = nullptr) {
@@ -346,6 +417,32 @@ static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, 
         std::string cerr;
         const int rc = b2a::cqt_run(h->cqt, h->cfg, &h->cqtdev, d_clips, n_clips, d_out, st, launches, &cerr);
         if (rc != 0) return fail(rc, cerr);
+        return B2A_OK;
+    }
+    if (h->cfg.kind == B2A_KIND_CLASSICAL) {
+        if (rag_len) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
+        if (n_clips > h->cls_tuning_cap) {           // (grow-only; the previous run on this handle is ordered before by the caller)
+            cudaFree(h->d_cls_tuning);
+            h->d_cls_tuning = nullptr; h->cls_tuning_cap = 0;
+            CU_TRY(cudaMalloc((void**)&h->d_cls_tuning, (size_t)n_clips * sizeof(float)));
+            h->cls_tuning_cap = n_clips;
+        }
+        b2a::ClassicalParams c{};
+        c.clips = d_clips; c.out = d_out;
+        c.window = h->d_window; c.tw = h->d_tw; c.tw2 = h->d_tw2;
+        c.mel_k0 = h->d_k0; c.mel_cnt = h->d_cnt; c.mel_off = h->d_off; c.mel_w = h->d_w;
+        c.dct = h->d_dct; c.chroma = h->d_chroma; c.tonnetz = h->d_tonnetz;
+        c.band_start = h->d_bands; c.band_cnt = h->d_bands + 7; c.band_q = h->d_bands + 14;
+        c.scratch = h->d_cls_scratch; c.scratch_per_cta = h->cls_scratch_per_cta;
+        c.tuning_out = h->d_cls_tuning;
+        c.n_clips = n_clips; c.n_samples = h->cfg.n_samples; c.hop = h->cfg.hop_length; c.n_frames = h->cls_frames;
+        c.n_mels = h->cfg.n_mels; c.mel_nnz = (int)h->mel.w.size(); c.n_mfcc = h->cfg.n_mfcc;
+        c.sample_rate = h->cfg.sample_rate; c.pip_k0 = h->cls.pip_k0; c.pip_k1 = h->cls.pip_k1;
+        c.cand_cap = h->cls_cand_cap; c.top_db = h->cfg.top_db;
+        const int grid = (int)std::min<int64_t>(n_clips, h->grid_cap);
+        CU_TRY(b2a::launch_classical(c, h->log2nc, h->cfg.input_dtype == B2A_IN_I16, grid, st));
+        h->cls_last_n = n_clips;
+        *launches += 1;
         return B2A_OK;
     }
     b2a::FrontParams p{};
@@ -554,7 +651,7 @@ int b2a_run_device_ragged(b2a_handle* h, const void* d_clips, const int64_t* d_i
                           const int32_t* d_lengths, const int64_t* d_out_offsets, int64_t n_clips,
                           float* d_out, void* stream) {
     if (!h) return fail(B2A_EINVAL, "handle is NULL");
-    if (h->cfg.kind == B2A_KIND_CQT) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
+    if (h->cfg.kind != B2A_KIND_MEL && h->cfg.kind != B2A_KIND_MFCC) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
     if (n_clips < 0) return fail(B2A_EINVAL, "n_clips < 0");
     if (n_clips > 0 && (!d_clips || !d_out || !d_in_offsets || !d_lengths || !d_out_offsets))
         return fail(B2A_EINVAL, "NULL buffer");
@@ -569,7 +666,7 @@ int b2a_run_host_ragged(b2a_handle* h, const void* clips, int64_t total_in, cons
                         const int32_t* lengths, const int64_t* out_offsets, int64_t n_clips,
                         float* out, int64_t total_out) {
     if (!h) return fail(B2A_EINVAL, "handle is NULL");
-    if (h->cfg.kind == B2A_KIND_CQT) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
+    if (h->cfg.kind != B2A_KIND_MEL && h->cfg.kind != B2A_KIND_MFCC) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
     if (n_clips < 0 || total_in < 0 || total_out < 0) return fail(B2A_EINVAL, "negative size");
     if (n_clips == 0) { h->last_launches = 0; return B2A_OK; }
     if (!clips || !out || !in_offsets || !lengths || !out_offsets) return fail(B2A_EINVAL, "NULL buffer");
@@ -654,6 +751,15 @@ int b2a_get_table(const b2a_handle* h, int32_t which, float* dst, int64_t* count
         }
         case B2A_TABLE_CQT_BASIS: {
             for (const auto& o : h->cqt.oct) tmp.insert(tmp.end(), o.basis.begin(), o.basis.end());
+            src = &tmp; break;
+        }
+        case B2A_TABLE_CHROMA: src = &h->cls.chroma; break;
+        case B2A_TABLE_TONNETZ: src = &h->cls.tonnetz; break;
+        case B2A_TABLE_CONTRAST_BANDS: {
+            for (int v : h->cls.band_start) tmp.push_back((float)v);
+            for (int v : h->cls.band_cnt) tmp.push_back((float)v);
+            for (int v : h->cls.band_q) tmp.push_back((float)v);
+            tmp.push_back((float)h->cls.pip_k0); tmp.push_back((float)h->cls.pip_k1);
             src = &tmp; break;
         }
         default: return fail(B2A_EINVAL, "unknown table");

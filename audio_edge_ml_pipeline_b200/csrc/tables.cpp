@@ -294,4 +294,93 @@ bool build_cqt_plan(int sr_in, int hop_in, int n_bins, int bpo, double fmin, int
     return true;
 }
 
+// ---- audio_classical tables ---------------------------------------------------------------------------
+static std::vector<float> chroma_bank(int sr, int n_fft, double tuning) {
+    const int nc = 12, nb = 1 + n_fft / 2;
+    std::vector<double> frq(n_fft), bw(n_fft);
+    const double a440 = 440.0 * std::pow(2.0, tuning / nc);
+    const double step = (double)sr / n_fft;                      // np.linspace(0, sr, n_fft, endpoint=False)
+    for (int i = 1; i < n_fft; ++i) frq[i] = nc * std::log2((i * step) / (a440 / 16));
+    frq[0] = frq[1] - 1.5 * nc;                                  // "make up a value for the 0 Hz bin"
+    for (int i = 0; i + 1 < n_fft; ++i) bw[i] = std::max(frq[i + 1] - frq[i], 1.0);
+    bw[n_fft - 1] = 1.0;
+    std::vector<double> w((size_t)nc * n_fft);
+    const double half = std::nearbyint(nc / 2.0);
+    for (int i = 0; i < n_fft; ++i) {
+        double nrm = 0.0;
+        for (int c = 0; c < nc; ++c) {
+            double d = frq[i] - c + half + 10 * nc;
+            d = d - nc * std::floor(d / nc) - half;              // np.remainder(., n_chroma) - n_chroma2
+            const double g = std::exp(-0.5 * std::pow(2 * d / bw[i], 2));
+            w[(size_t)c * n_fft + i] = g;
+            nrm += g * g;
+        }
+        nrm = std::sqrt(nrm);
+        if (nrm < 2.2250738585072014e-308) nrm = 1.0;
+        const double oct = std::exp(-0.5 * std::pow((frq[i] / nc - 5.0) / 2.0, 2));
+        for (int c = 0; c < nc; ++c) w[(size_t)c * n_fft + i] = w[(size_t)c * n_fft + i] / nrm * oct;
+    }
+    std::vector<float> out((size_t)nc * nb);
+    for (int c = 0; c < nc; ++c)                                 // np.roll(wts, -3, axis=0): row c <- row c + 3
+        for (int k = 0; k < nb; ++k) out[(size_t)c * nb + k] = (float)w[(size_t)((c + 3) % nc) * n_fft + k];
+    return out;
+}
+
+bool build_classical_tables(int sr, int n_fft, ClassicalTables* t, const char** err) {
+    const int nb = 1 + n_fft / 2, n_bands = 6;
+    const double fmin = 200.0, quantile = 0.02;
+    const double val = 1.0 / (n_fft * (1.0 / sr));               // np.fft.rfftfreq
+    std::vector<double> freq(nb);
+    for (int k = 0; k < nb; ++k) freq[k] = k * val;
+    // spectral_contrast bands
+    std::vector<double> octa(n_bands + 2, 0.0);
+    for (int i = 0; i <= n_bands; ++i) octa[i + 1] = fmin * std::pow(2.0, i);
+    for (int i = 0; i <= n_bands; ++i)
+        if (octa[i] >= 0.5 * sr) { *err = "spectral_contrast: a frequency band exceeds Nyquist (sample_rate too low)"; return false; }
+    t->band_start.clear(); t->band_cnt.clear(); t->band_q.clear();
+    for (int b = 0; b <= n_bands; ++b) {
+        int first = -1, last = -1;
+        for (int k = 0; k < nb; ++k)
+            if (freq[k] >= octa[b] && freq[k] <= octa[b + 1]) { if (first < 0) first = k; last = k; }
+        if (first < 0) { *err = "spectral_contrast: empty frequency band (n_fft too small)"; return false; }
+        if (b > 0) first -= 1;
+        if (b == n_bands) last = nb - 1;
+        const int n_in = last - first + 1;
+        int cnt = n_in;
+        if (b < n_bands) cnt -= 1;
+        if (first < 0 || cnt < 1) { *err = "spectral_contrast: degenerate frequency band"; return false; }
+        const int q = (int)std::max(std::nearbyint(quantile * n_in), 1.0);
+        if (q > cnt) { *err = "spectral_contrast: quantile exceeds the band"; return false; }
+        t->band_start.push_back(first); t->band_cnt.push_back(cnt); t->band_q.push_back(q);
+    }
+    // piptrack: fmin = 150, fmax = min(4000, sr / 2)
+    const double pmin = 150.0, pmax = std::min(4000.0, sr / 2.0);
+    t->pip_k0 = nb; t->pip_k1 = 0;
+    for (int k = 0; k < nb; ++k)
+        if (pmin <= freq[k] && freq[k] < pmax) { t->pip_k0 = std::min(t->pip_k0, k); t->pip_k1 = std::max(t->pip_k1, k + 1); }
+    if (t->pip_k0 >= t->pip_k1) { t->pip_k0 = t->pip_k1 = 1; }
+    if (t->pip_k0 < 1) t->pip_k0 = 1;                            // (the parabolic shift is defined as 0 on the edge bins)
+    if (t->pip_k1 > nb - 1) t->pip_k1 = nb - 1;
+    // tonnetz projection
+    const double scale[6] = {7.0 / 6, 7.0 / 6, 3.0 / 2, 3.0 / 2, 2.0 / 3, 2.0 / 3};
+    const double R[6] = {1, 1, 1, 1, 0.5, 0.5};
+    t->tonnetz.assign(72, 0.f);
+    const double pi = 3.14159265358979323846;
+    for (int p = 0; p < 6; ++p)
+        for (int c = 0; c < 12; ++c) {
+            double v = scale[p] * c;                             // dim_map = linspace(0, 12, 12, endpoint=False) = c
+            if ((p & 1) == 0) v -= 0.5;
+            t->tonnetz[p * 12 + c] = (float)(R[p] * std::cos(pi * v));
+        }
+    // chroma banks for np.linspace(-0.5, 0.5, 101)[i], i < 100
+    t->chroma.clear();
+    t->chroma.reserve((size_t)100 * 12 * nb);
+    for (int i = 0; i < 100; ++i) {
+        const double tuning = i * 0.01 + (-0.5);
+        std::vector<float> fb = chroma_bank(sr, n_fft, tuning);
+        t->chroma.insert(t->chroma.end(), fb.begin(), fb.end());
+    }
+    return true;
+}
+
 }  // namespace b2a

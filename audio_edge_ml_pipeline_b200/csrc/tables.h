@@ -75,4 +75,16 @@ struct CqtPlan {
 bool build_cqt_plan(int sr, int hop, int n_bins, int bpo, double fmin, int n_samples,
                     CqtPlan* plan, const char** err);
 
+// ---- audio_classical (classical.py:272-355) --------------------------------------------------------
+// librosa.filters.chroma(sr, n_fft, tuning, n_chroma=12, ctroct=5, octwidth=2, norm=2, base_c=True) for the 100
+// tunings estimate_tuning can return (np.linspace(-0.5, 0.5, 101)[:-1]), the spectral_contrast bands
+// (n_bands=6, fmin=200, quantile=0.02), the tonnetz projection and the piptrack bin range.
+struct ClassicalTables {
+    std::vector<float> chroma;                       // [100][12][1 + n_fft/2]
+    std::vector<int32_t> band_start, band_cnt, band_q;
+    std::vector<float> tonnetz;                      // [6][12]
+    int pip_k0 = 0, pip_k1 = 0;
+};
+bool build_classical_tables(int sr, int n_fft, ClassicalTables* t, const char** err);
+
 }  // namespace b2a

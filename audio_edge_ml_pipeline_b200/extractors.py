@@ -306,7 +306,7 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
         labels: list = []
         metas: list = []
         label_to_idx: dict = {}
-        ragged = self.duration is None and self._kind != B.KIND_CQT
+        ragged = self.duration is None and self._kind in (B.KIND_MEL, B.KIND_MFCC)
         n_fixed = int(self.duration * self.sample_rate) if self.duration is not None else 0
         native = NATIVE_DECODE and self.duration is not None and n_fixed >= self._min_samples()
         # fixed duration + a sized loader: windows land in one preallocated array (no concatenation) for as
@@ -506,3 +506,106 @@ class AudioMFCCSequence(_GpuAudioExtractor):
         cfg.n_fft, cfg.hop_length = int(self.n_fft), int(self.hop_length)
         cfg.n_mels, cfg.n_mfcc = int(self.n_mels), int(self.n_mfcc)
         cfg.pad_mode = {"constant": B.PAD_CONSTANT, "reflect": B.PAD_REFLECT}[self.pad_mode]
+
+
+_CLASSICAL_FEATURES = ["mfcc", "delta_mfcc", "delta2_mfcc", "spectral_centroid", "spectral_rolloff",
+                       "spectral_bandwidth", "spectral_contrast", "spectral_flatness", "chroma", "zcr", "rms",
+                       "tonnetz"]                                     # classical.py:61-74
+_CLASSICAL_RAW_DIMS = {"spectral_centroid": 1, "spectral_rolloff": 1, "spectral_bandwidth": 1,
+                       "spectral_contrast": 7, "spectral_flatness": 1, "chroma": 12, "zcr": 1, "rms": 1,
+                       "tonnetz": 6}                                   # classical.py:78-88
+_CLASSICAL_AGGREGATIONS = ["mean", "std"]
+
+
+@register
+class AudioClassicalExtractor(_GpuAudioExtractor):
+    """Flat classical feature vector (MFCC + deltas, spectral shape, contrast, chroma, zcr, rms, tonnetz; mean / std
+    over time) — classical.py:96-355.  The device computes every group with both aggregations in one pass over
+    the clip (``B2A_KIND_CLASSICAL``); ``features`` / ``aggregations`` select columns of that vector in the
+    reference's canonical order.  ``duration`` is an addition (the reference extractor always takes the whole
+    segment): with it set, clips are padded / trimmed to a fixed length so that a dataset runs as whole batches."""
+
+    name = "audio_classical"
+    feature_type = "classical"
+    _kind = B.KIND_CLASSICAL
+
+    def __init__(self, sample_rate: int = 22050, n_mfcc: int = 40, n_mels: int = 128, n_fft: int = 1024,
+                 hop_length: int = 512, min_duration: float = 0.1, features: Optional[list] = None,
+                 aggregations: Optional[list] = None, *, duration: Optional[float] = None,
+                 devices: Optional[Sequence[int]] = None) -> None:
+        self.sample_rate = sample_rate
+        self.n_mfcc = n_mfcc
+        self.n_mels = n_mels
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.min_duration = min_duration
+        self.duration = duration
+        if features is None:
+            self.features = list(_CLASSICAL_FEATURES)
+        else:
+            unknown = set(features) - set(_CLASSICAL_FEATURES)
+            if unknown:
+                raise ValueError(f"Unknown feature group(s): {sorted(unknown)}. Valid keys: {_CLASSICAL_FEATURES}")
+            self.features = [k for k in _CLASSICAL_FEATURES if k in set(features)]     # canonical order
+        if aggregations is None:
+            self.aggregations = list(_CLASSICAL_AGGREGATIONS)
+        else:
+            unknown = set(aggregations) - set(_CLASSICAL_AGGREGATIONS)
+            if unknown:
+                raise ValueError(f"Unknown aggregation(s): {sorted(unknown)}. Valid values: {_CLASSICAL_AGGREGATIONS}")
+            if not aggregations:
+                raise ValueError("aggregations must contain at least one value.")
+            self.aggregations = [a for a in _CLASSICAL_AGGREGATIONS if a in set(aggregations)]
+        self._columns = self._column_index()
+        self._init_common(devices)
+
+    @property
+    def feature_dim(self) -> int:
+        """classical.py:197-207."""
+        return len(self._columns)
+
+    def _column_index(self) -> np.ndarray:
+        """Columns of the device vector (every group: [means..., stds...]) that this configuration keeps."""
+        cols, pos = [], 0
+        for key in _CLASSICAL_FEATURES:
+            dim = self.n_mfcc if key in ("mfcc", "delta_mfcc", "delta2_mfcc") else _CLASSICAL_RAW_DIMS[key]
+            if key in self.features:
+                for a, agg in enumerate(_CLASSICAL_AGGREGATIONS):
+                    if agg in self.aggregations:
+                        cols.extend(range(pos + a * dim, pos + (a + 1) * dim))
+            pos += 2 * dim
+        return np.asarray(cols, dtype=np.int64)
+
+    def _min_samples(self) -> int:
+        # classical.py:262-270: one STFT frame and nine MFCC frames for the width-9 delta
+        return max(int(self.min_duration * self.sample_rate), self.n_fft, 8 * self.hop_length)
+
+    def _fill_config(self, cfg) -> None:
+        cfg.n_fft, cfg.hop_length = int(self.n_fft), int(self.hop_length)
+        cfg.n_mels, cfg.n_mfcc = int(self.n_mels), int(self.n_mfcc)
+
+    def _select(self, full: np.ndarray) -> np.ndarray:
+        full = full.reshape(full.shape[0], -1)
+        if len(self._columns) == full.shape[1]:
+            return full
+        return np.ascontiguousarray(full[:, self._columns])
+
+    def extract_batch(self, clips: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
+        """(N, n_samples) equal-length clips -> (N, feature_dim) float32."""
+        full = super().extract_batch(clips)
+        if getattr(self, "_raw_rows", False):       # inside extract_dataset: rows stay device vectors until the end
+            return full
+        got = self._select(full)
+        if out is not None:
+            out[...] = got
+            return out
+        return got
+
+    def extract_dataset(self, loader, max_samples: Optional[int] = None) -> FeatureSet:
+        self._raw_rows = True
+        try:
+            fs = super().extract_dataset(loader, max_samples)
+        finally:
+            self._raw_rows = False
+        fs.features = self._select(fs.features)    # (N, rows, 1) device vectors -> (N, feature_dim)
+        return fs

@@ -388,7 +388,11 @@ def _secondary(torch, dev, local, peak):
             ("mfcc_reference_defaults", dict(sr=22050, n=110250, rows=40, hop=512, bytes=110250 * 2 + 40 * 216 * 4,
                                              name="audio_mfcc_seq", params=dict(duration=5.0),
                                              workload="audio_mfcc_seq reference defaults 22050/1024/512/128 mels -> 40 (logmel1024 kernel)"),
-             20000)]
+             20000),
+            ("classical", dict(sr=22050, n=110250, rows=302, hop=512, bytes=110250 * 2 + 302 * 4,
+                               name="audio_classical", params=dict(duration=5.0),
+                               workload="audio_classical (SURVEY 8f N4) reference defaults 22050/1024/512: 302-value vector per 5 s clip"),
+             4096)]
     for key, x, n in jobs:
         try:
             ext = P.get(x["name"])(**x["params"], devices=[local])

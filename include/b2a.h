@@ -48,6 +48,15 @@ extern "C" {
 #define B2A_KIND_MEL      0   /* AudioMelSpectrogram.extract  deep.py:112-134 */
 #define B2A_KIND_MFCC     1   /* AudioMFCCSequence.extract    deep.py:304-328 */
 #define B2A_KIND_CQT      2   /* AudioCQT.extract             deep.py:235-260 */
+#define B2A_KIND_CLASSICAL 3  /* AudioClassicalExtractor._compute_features  classical.py:272-355:
+                               * rows = 6 n_mfcc + 62, frames = 1.  A clip's vector holds EVERY feature group with
+                               * both aggregations in the reference's canonical order — mfcc, delta_mfcc, delta2_mfcc
+                               * (n_mfcc means then n_mfcc stds each), spectral_centroid, spectral_rolloff,
+                               * spectral_bandwidth (mean, std), spectral_contrast (7 + 7), spectral_flatness (2),
+                               * chroma (12 + 12), zcr (2), rms (2), tonnetz (6 + 6); a caller configured with a
+                               * subset of `features` / `aggregations` (classical.py:152-180) selects columns.
+                               * n_fft in {512, 1024, 2048}; n_samples >= max(n_fft, 8 hop_length)
+                               * (classical.py:262-270 pads to that); constant padding only. */
 
 /* b2a_config.input_dtype */
 #define B2A_IN_I16        0
@@ -62,10 +71,10 @@ typedef struct b2a_config {
     int32_t input_dtype;      /* B2A_IN_*                                                     */
     int32_t sample_rate;      /* Hz                                   (all kinds)             */
     int32_t n_samples;        /* samples per clip, = int(duration*sr) (all kinds)             */
-    int32_t n_fft;            /* 256|512|1024|2048                    (mel, mfcc)             */
+    int32_t n_fft;            /* 256|512|1024|2048                    (mel, mfcc, classical)  */
     int32_t hop_length;       /*                                      (all kinds)             */
-    int32_t n_mels;           /* mel bands (mfcc: librosa default 128)(mel, mfcc)             */
-    int32_t n_mfcc;           /* DCT rows kept                        (mfcc)                  */
+    int32_t n_mels;           /* mel bands (mfcc: librosa default 128)(mel, mfcc, classical)  */
+    int32_t n_mfcc;           /* DCT rows kept                        (mfcc, classical)       */
     int32_t n_bins;           /* CQT bins                             (cqt)                   */
     int32_t bins_per_octave;  /*                                      (cqt)                   */
     double  fmin;             /* CQT lowest frequency; <=0 -> C1 = 32.7032 Hz   (cqt)         */
@@ -87,6 +96,12 @@ int b2a_destroy(b2a_handle* h);
 
 /* rows = n_mels | n_mfcc | n_bins; frames = 1 + n_samples / hop_length  (CLAUDE.md:90) */
 int b2a_out_shape(const b2a_handle* h, int32_t* rows, int32_t* frames);
+
+/* classical handles: the tuning (in fractions of a semitone, -0.5 .. 0.49) that chroma_stft's estimate_tuning
+ * step found for clips [0, n) of the LAST device launch on this handle (b2a_run_device, or the last chunk of
+ * b2a_run_host) — a diagnostic: the estimate is the arg-max of a 100-bin histogram and therefore the one
+ * discontinuous step of the extractor.  Synchronises the device. */
+int b2a_classical_tunings(b2a_handle* h, float* out, int64_t n);
 
 /* Device-resident path: d_clips and d_out are device pointers on the handle's device; the work
  * is enqueued on `stream` (a cudaStream_t, NULL = legacy default stream) and the call returns
@@ -244,6 +259,9 @@ int b2a_free_pinned(void* p);
 #define B2A_TABLE_DECIM_TAPS  3   /* [383]                       2:1 decimator (cqt)         */
 #define B2A_TABLE_CQT_LENGTHS 4   /* [n_bins]                    wavelet lengths (cqt)       */
 #define B2A_TABLE_CQT_BASIS   5   /* [n_octaves][n_filters][1+n_fft_o/2][2] re,im; dense     */
+#define B2A_TABLE_CHROMA      6   /* [100][12][1+n_fft/2]        chroma banks, tuning -0.5 + 0.01 i (classical) */
+#define B2A_TABLE_TONNETZ     7   /* [6][12]                     tonnetz projection (classical) */
+#define B2A_TABLE_CONTRAST_BANDS 8 /* [7] first bin, [7] bins, [7] q, then piptrack k0, k1 (classical) */
 int b2a_get_table(const b2a_handle* h, int32_t which, float* dst, int64_t* count);
 
 /* CQT geometry: per-octave FFT size / hop / signal length (cqt handles only). */

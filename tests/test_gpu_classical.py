@@ -1,0 +1,128 @@
+"""GPU parity of `audio_classical` (classical.py:272-355): the CUDA path through the C ABI against
+oracle/classical_restated.py on seeded synthetic clips.
+
+Tolerances, relative to the largest magnitude of the group's block in the clip's vector (floor 1e-3; Hz-valued
+groups: floor 1 Hz) — the groups are aggregates over ~200 frames of fp32 spectra and sit near 1e-6; first run on
+the B200 (tools/classical_check.py, 35 clips, two configurations) in brackets:
+  mfcc / delta / delta2 (mean, std)   2e-5 of the clip's largest |mean MFCC| [2e-6]: deltas of a steady clip are
+                                      pure float32 rounding noise of MFCC values in the hundreds, so the three groups
+                                      share the MFCC scale
+  centroid / bandwidth / rms          1e-5  [2e-6]
+  flatness                            5e-4  [1.2e-4 of the 1e-3 floor: values ~1e-7 on tonal clips]
+  zcr, rolloff                        exact on every clip so far; 2e-3 allowed for rolloff (a frame whose cumulative
+                                      magnitude passes 0.85 of the total within fp32 rounding of a bin edge moves a bin)
+  contrast                            1e-2  [3.7e-3 = 0.07 dB]: the valley is the SMALLEST magnitude of a band, bins
+                                      ~100 dB under the frame's peak, where an fp32 FFT is good to a few per cent
+  chroma / tonnetz                    1e-4 on clips whose tuning estimate agrees [1.3e-5; all 35 agreed]; the estimate
+                                      is the arg-max of a 100-bin histogram — the extractor's one discontinuous step —
+                                      and must agree on at least 90 % of the clips.
+The oracle restates librosa 0.11.0, which is not installable here: parity unpinned against librosa itself."""
+import numpy as np
+import pytest
+
+from audio_edge_ml_pipeline_b200 import _lib as B
+from audio_edge_ml_pipeline_b200 import get, synth, wavio
+from oracle import classical_restated as C
+from oracle import librosa_restated as L
+
+pytestmark = pytest.mark.gpu
+
+GROUPS = [("mfcc", 40, 2e-5), ("delta_mfcc", 40, 2e-5), ("delta2_mfcc", 40, 2e-5), ("spectral_centroid", 1, 1e-5),
+          ("spectral_rolloff", 1, 2e-3), ("spectral_bandwidth", 1, 1e-5), ("spectral_contrast", 7, 1e-2),
+          ("spectral_flatness", 1, 5e-4), ("chroma", 12, 1e-4), ("zcr", 1, 1e-6), ("rms", 1, 1e-5), ("tonnetz", 6, 1e-4)]
+HZ = ("spectral_centroid", "spectral_rolloff", "spectral_bandwidth")
+
+
+def _engine(n, sr=22050, n_fft=1024, hop=512, n_mfcc=40, dtype=B.IN_I16):
+    cfg = B.default_config(B.KIND_CLASSICAL)
+    cfg.n_samples, cfg.sample_rate, cfg.n_fft, cfg.hop_length, cfg.n_mfcc, cfg.input_dtype = n, sr, n_fft, hop, n_mfcc, dtype
+    return B.Engine(cfg, 0)
+
+
+def _check(got, ref, same_tuning, n_mfcc=40):
+    pos = 0
+    for name, dim, tol in GROUPS:
+        dim = n_mfcc if dim == 40 else dim
+        for _agg in ("mean", "std"):
+            g, r = got[:, pos:pos + dim], ref[:, pos:pos + dim]
+            scale = np.maximum(np.abs(r).max(axis=1, keepdims=True), 1.0 if name in HZ else 1e-3)
+            if name.endswith("mfcc"):
+                scale = np.maximum(np.abs(ref[:, :n_mfcc]).max(axis=1, keepdims=True), 1.0)
+            err = (np.abs(g - r) / scale).max(axis=1)
+            rows = same_tuning if name in ("chroma", "tonnetz") else np.ones(len(got), bool)
+            assert err[rows].max() <= tol, (name, _agg, float(err[rows].max()), int(err.argmax()))
+            pos += dim
+    assert pos == got.shape[1]
+
+
+@pytest.mark.parametrize("sr,n_fft,hop,secs,n_clips", [(22050, 1024, 512, 5.0, 21), (16000, 512, 160, 2.0, 14)])
+def test_classical_suite(sr, n_fft, hop, secs, n_clips):
+    n = int(sr * secs)
+    pcm = synth.make_suite(n_clips, sr, n, seed=4321)
+    with _engine(n, sr, n_fft, hop) as e:
+        assert (e.rows, e.frames) == (302, 1)
+        got = e.run_host(pcm)[:, :, 0]
+        tun = e.classical_tunings(n_clips)
+        assert e.last_launch_count >= 1
+    assert got.dtype == np.float32 and np.isfinite(got).all()
+    ref = np.stack([C.audio_classical(L.pcm16_to_float(c), sr=sr, n_fft=n_fft, hop=hop) for c in pcm])
+    rtun = np.array([C.frame_features(L.pcm16_to_float(c), sr=sr, n_fft=n_fft, hop=hop)["_tuning"] for c in pcm])
+    same = np.abs(tun - rtun) < 1e-6
+    assert same.mean() >= 0.9, (tun, rtun)
+    _check(got, ref, same)
+
+
+def test_classical_float_input_short_clip_and_other_n_mfcc():
+    """float32 clips, the minimum length the reference pads to (8 hops: nine frames for the width-9 delta), 13 MFCCs."""
+    sr, n = 22050, 4096
+    pcm = synth.make_suite(7, sr, n, seed=77)
+    x = L.pcm16_to_float(pcm)
+    with _engine(n, n_mfcc=13, dtype=B.IN_F32) as e:
+        assert e.rows == 6 * 13 + 62
+        got = e.run_host(x)[:, :, 0]
+        tun = e.classical_tunings(7)
+    ref = np.stack([C.audio_classical(c, n_mfcc=13) for c in x])
+    rtun = np.array([C.frame_features(c, n_mfcc=13)["_tuning"] for c in x])
+    _check(got, ref, np.abs(tun - rtun) < 1e-6, n_mfcc=13)
+
+
+def test_classical_silence_and_full_scale():
+    """All-zero clips (every normalisation falls back to 'leave undivided', tuning 0.0) and a clipped square wave."""
+    n = 22050
+    pcm = np.zeros((3, n), dtype=np.int16)
+    pcm[1] = np.where((np.arange(n) // 25) % 2 == 0, 32767, -32768)
+    pcm[2, ::2] = 1
+    with _engine(n) as e:
+        got = e.run_host(pcm)[:, :, 0]
+        tun = e.classical_tunings(3)
+    assert np.isfinite(got).all()
+    ref = np.stack([C.audio_classical(L.pcm16_to_float(c)) for c in pcm])
+    rtun = np.array([C.frame_features(L.pcm16_to_float(c))["_tuning"] for c in pcm])
+    assert tun[0] == 0.0 and rtun[0] == 0.0
+    _check(got, ref, np.abs(tun - rtun) < 1e-6)
+
+
+def test_classical_extractor_mirror(tmp_path):
+    """The reference-facing class: extract(path), feature subsets, fixed-duration batches."""
+    sr = 22050
+    pcm = synth.make_suite(5, sr, 3 * sr, seed=9)
+    paths = []
+    for i, c in enumerate(pcm):
+        p = tmp_path / f"c{i}.wav"
+        wavio.write_wav_pcm16(p, c, sr)
+        paths.append(p)
+    ex = get("audio_classical")()
+    v = ex.extract(paths[0])
+    assert v.shape == (302,) and v.dtype == np.float32
+    ref = C.audio_classical(L.pcm16_to_float(pcm[0]))
+    full = ex.extract_batch(pcm)
+    assert full.shape == (5, 302) and np.array_equal(full[0], v)
+    lean = get("audio_classical")(features=["mfcc", "zcr", "rms"], aggregations=["mean"])
+    got = lean.extract_batch(pcm)
+    assert got.shape == (5, 42) and np.array_equal(got, full[:, lean._columns])
+    assert np.allclose(got[0], C.audio_classical(L.pcm16_to_float(pcm[0]), features=["mfcc", "zcr", "rms"], aggregations=["mean"]),
+                       rtol=1e-5, atol=2e-5 * float(np.abs(ref[:40]).max()))
+    seg = ex.extract(paths[1], start_time=0.5, end_time=2.0)              # classical.py:243-259 segment slicing
+    ref_seg = C.audio_classical(L.pcm16_to_float(pcm[1][int(0.5 * sr):int(0.5 * sr) + int(1.5 * sr)]))
+    assert np.allclose(seg[:40], ref_seg[:40], rtol=1e-5, atol=2e-5 * float(np.abs(ref_seg[:40]).max()))
+    ex.close(); lean.close()

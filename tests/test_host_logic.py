@@ -45,7 +45,7 @@ def _make_dataset(root: Path, sr=16000, n=8000, classes=("bird", "axe", "rain"),
 # ---- registry / constructors -------------------------------------------------------------------
 
 def test_registry_semantics_match_reference():
-    assert P.list_extractors() == ["audio_cqt", "audio_mel_spec", "audio_mfcc_seq"]
+    assert P.list_extractors() == ["audio_classical", "audio_cqt", "audio_mel_spec", "audio_mfcc_seq"]
     assert P.get("audio_mel_spec") is P.AudioMelSpectrogram
     with pytest.raises(KeyError):
         P.get("nope")
