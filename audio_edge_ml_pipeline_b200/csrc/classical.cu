@@ -27,14 +27,15 @@ namespace b2a {
 namespace {
 
 constexpr int kBands = 7;
-constexpr int kWarps = kThreads / 32;
+constexpr int kCT = 512;                       // threads per CTA: sixteen warps, one resident CTA per SM
+constexpr int kWarps = kCT / 32;
 constexpr float kTiny = 1.17549435e-38f;        // np.finfo(float32).tiny (librosa.util.normalize threshold)
 constexpr int kZcrFrame = 2048;                 // librosa.feature.zero_crossing_rate default frame_length
 
 template <int LOG2NC> struct ClsCfg {
     using G = FftGeom<LOG2NC>;
     static constexpr int F = (LOG2NC <= 8) ? 32 : 16;
-    static constexpr int FR = kThreads / G::T;
+    static constexpr int FR = kCT / G::T;
     static constexpr int ROUNDS = (F + FR - 1) / FR;
     static constexpr int CH = G::NC / 32 + 1;   // contiguous bins per lane (odd: conflict-free stride)
 };
@@ -87,7 +88,7 @@ __device__ __forceinline__ void row_stats(int n, int lane, Fn f, float* mean_out
 }
 
 template <int LOG2NC, bool I16>
-__global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams p) {
+__global__ void __launch_bounds__(kCT, 1) classical_kernel(ClassicalParams p) {
     using G = FftGeom<LOG2NC>;
     using C = ClsCfg<LOG2NC>;
     constexpr int NC = G::NC, NFFT = G::NFFT, T = G::T, F = C::F, FR = C::FR, NB = NC + 1, CH = C::CH;
@@ -112,19 +113,14 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
     double* s_acc = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(s_misc + 8) + 7) & ~(uintptr_t)7);   // [kWarps][18][2] chroma / tonnetz partial sums
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < NC; i += kThreads) s_tw[i] = p.tw[i];
-    for (int i = tid; i < NC / 2 + 1; i += kThreads) s_tw2[i] = p.tw2[i];
-    FftTwp<LOG2NC>::fill(s_twp, p.tw, tid, kThreads);
-    for (int i = tid; i < p.n_mels; i += kThreads) { s_k0[i] = p.mel_k0[i]; s_cnt[i] = p.mel_cnt[i]; s_off[i] = p.mel_off[i]; }
-    for (int i = tid; i < p.mel_nnz; i += kThreads) s_w[i] = p.mel_w[i];
+    for (int i = tid; i < NC; i += kCT) s_tw[i] = p.tw[i];
+    for (int i = tid; i < NC / 2 + 1; i += kCT) s_tw2[i] = p.tw2[i];
+    FftTwp<LOG2NC>::fill(s_twp, p.tw, tid, kCT);
+    for (int i = tid; i < p.n_mels; i += kCT) { s_k0[i] = p.mel_k0[i]; s_cnt[i] = p.mel_cnt[i]; s_off[i] = p.mel_off[i]; }
+    for (int i = tid; i < p.mel_nnz; i += kCT) s_w[i] = p.mel_w[i];
 
     const int j = tid % T, slot = tid / T;
-    float2 win[16];
-#pragma unroll
-    for (int t = 0; t < 16; ++t) {
-        const int n = j + T * t;
-        win[t] = make_float2(__ldg(p.window + 2 * n), __ldg(p.window + 2 * n + 1));
-    }
+    const float2* const win = reinterpret_cast<const float2*>(p.window) + j;   // pairs (w[2n], w[2n+1]), n = j + T t: L1-resident
     __syncthreads();
 
     const int n = p.n_samples, nfr = p.n_frames, n_mels = p.n_mels, K = p.n_mfcc, hop = p.hop;
@@ -144,7 +140,7 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
         __syncthreads();
 
         for (int t0 = 0; t0 < nfr; t0 += F) {
-            stage_audio<I16>(s_audio, cptr, clip_elem0, t0 * hop - NFFT / 2, cl, n, 0, base_aligned);
+            stage_audio<I16, kCT>(s_audio, cptr, clip_elem0, t0 * hop - NFFT / 2, cl, n, 0, base_aligned);
             __syncthreads();
 #pragma unroll 1
             for (int r = 0; r < C::ROUNDS; ++r) {
@@ -157,12 +153,15 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
 #pragma unroll
                         for (int t = 0; t < 16; ++t) {
                             const float2 x = *reinterpret_cast<const float2*>(a + 2 * T * t);
-                            v[t] = make_float2(x.x * win[t].x, x.y * win[t].y);
+                            const float2 w = __ldg(win + T * t);
+                            v[t] = make_float2(x.x * w.x, x.y * w.y);
                         }
                     } else {
 #pragma unroll
-                        for (int t = 0; t < 16; ++t)
-                            v[t] = make_float2(a[2 * T * t] * win[t].x, a[2 * T * t + 1] * win[t].y);
+                        for (int t = 0; t < 16; ++t) {
+                            const float2 w = __ldg(win + T * t);
+                            v[t] = make_float2(a[2 * T * t] * w.x, a[2 * T * t + 1] * w.y);
+                        }
                     }
                     Dft<16>::run(v);
 #pragma unroll
@@ -192,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
             __syncthreads();
 
             // ---- mel bands -> dB (librosa.feature.mfcc: power_to_db(melspectrogram)) -------------------
-            for (int i = tid; i < n_mels * F; i += kThreads) {
+            for (int i = tid; i < n_mels * F; i += kCT) {
                 const int m = i / F, f = i % F;
                 const float* pf = s_pow + f * G::PSTRIDE + s_k0[m];
                 const float* w = s_w + s_off[m];
@@ -208,11 +207,12 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
                 }
             }
             // ---- power rows -> scratch (chroma product after the tuning estimate) ----------------------
-            for (int i = tid; i < F * NB; i += kThreads) {
+            for (int i = tid; i < F * NB; i += kCT) {
                 const int f = i / NB, k = i - f * NB;
                 if (t0 + f < nfr) S.P[(size_t)(t0 + f) * NB + k] = s_pow[f * G::PSTRIDE + k];
             }
-            // ---- one warp per frame: every spectral scalar, contrast, piptrack, rms, zcr --------------
+            __syncthreads();                                   // the per-frame pass below rewrites its rows in place
+            // ---- one warp per frame: every spectral scalar, piptrack, contrast, rms, zcr --------------
             for (int f = warp; f < F; f += kWarps) {
                 const int t = t0 + f;
                 if (t >= nfr) break;
@@ -269,44 +269,6 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
                     kro = warp_min_i(kro);
                     if (kro == 0x7fffffff) kro = NB - 1;
                 }
-                // spectral_contrast: mean of the q smallest / largest magnitudes of every band, in dB
-                double pkv = 0.0, vlv = 0.0;                                   // lane b < 7 keeps band b's pair
-#pragma unroll 1
-                for (int b = 0; b < kBands; ++b) {
-                    const int bs = p.band_start[b], be = bs + p.band_cnt[b], q = p.band_q[b];
-                    double sv = 0.0, sq = 0.0;
-                    float pvv = -1.f; int pvk = -1;                            // last valley taken (value, bin)
-                    float ppv = 3.0e38f; int ppk = 0x7fffffff;                 // last peak taken
-#pragma unroll 1
-                    for (int e = 0; e < q; ++e) {
-                        float bv = 3.0e38f; int bk = 0x7fffffff;
-                        float cv = -1.f; int ck = -1;
-#pragma unroll
-                        for (int i = 0; i < CH; ++i) {
-                            const int k = CH * lane + i;
-                            if (k >= bs && k < be) {
-                                const float v = mg[i];
-                                if ((v > pvv || (v == pvv && k > pvk)) && (v < bv || (v == bv && k < bk))) { bv = v; bk = k; }
-                                if ((v < ppv || (v == ppv && k < ppk)) && (v > cv || (v == cv && k > ck))) { cv = v; ck = k; }
-                            }
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const float ov = __shfl_xor_sync(0xffffffffu, bv, o); const int ok = __shfl_xor_sync(0xffffffffu, bk, o);
-                            if (ov < bv || (ov == bv && ok < bk)) { bv = ov; bk = ok; }
-                            const float pv2 = __shfl_xor_sync(0xffffffffu, cv, o); const int pk2 = __shfl_xor_sync(0xffffffffu, ck, o);
-                            if (pv2 > cv || (pv2 == cv && pk2 > ck)) { cv = pv2; ck = pk2; }
-                        }
-                        sv += (double)bv; sq += (double)cv;
-                        pvv = bv; pvk = bk; ppv = cv; ppk = ck;
-                    }
-                    const float vmean = (float)(sv / q), pmean = (float)(sq / q);   // np.mean of float32 values
-                    if (lane == b) {
-                        vlv = 10.0 * log10(fmax(1e-10, (double)vmean));
-                        pkv = 10.0 * log10(fmax(1e-10, (double)pmean));
-                    }
-                }
-                if (lane < kBands) { S.pk[(size_t)lane * nfr + t] = (float)pkv; S.vl[(size_t)lane * nfr + t] = (float)vlv; }
                 // piptrack (estimate_tuning): thresholded local maxima of the POWER spectrum, 150 Hz <= f < 4 kHz
                 {
                     const float ref = 0.1f * mx;
@@ -324,6 +286,57 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
                         const float pitch = (float)(((double)k + (double)shift) * (double)p.sample_rate / (double)NFFT);
                         const int pos = atomicAdd(&s_misc[0], 1);
                         if (pos < p.cand_cap) { S.cp[pos] = pitch; S.cm[pos] = __fadd_rn(s0, dskew); }
+                    }
+                }
+                // spectral_contrast: mean of the q smallest / largest magnitudes of every band, in dB.  The frame's row
+                // now holds magnitudes, read lane-strided per band (ceil(cnt / 32) values a lane); a selection step is
+                // a local scan, one redux.sync on the float bits (magnitudes are >= 0: bit order = value order), a
+                // ballot to name the lane that owns the winner, which marks its entry as taken.  A band has more
+                // than 2 q bins, so the entries the valley pass took never belong to the peak set.
+                {
+                    float* const row = s_pow + f * G::PSTRIDE;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) {
+                        const int k = CH * lane + i;
+                        if (k < NB) row[k] = mg[i];
+                    }
+                    __syncwarp();
+                    constexpr uint32_t kTaken = 0xffffffffu;
+                    float vm = 0.f, pm = 0.f;                                  // lane b keeps band b's means
+#pragma unroll 1
+                    for (int b = 0; b < kBands; ++b) {
+                        const int bs = p.band_start[b], cnt = p.band_cnt[b], q = p.band_q[b];
+                        uint32_t* const col = reinterpret_cast<uint32_t*>(row) + bs + lane;
+                        const int nv = (cnt - lane + 31) >> 5;                 // this lane's entries: bs + lane + 32 i
+                        double sv = 0.0, sq = 0.0;
+#pragma unroll 1
+                        for (int e = 0; e < q; ++e) {
+                            uint32_t lm = kTaken;
+                            for (int i = 0; i < nv; ++i) lm = min(lm, col[32 * i]);
+                            const uint32_t gm = __reduce_min_sync(0xffffffffu, lm);
+                            const int owner = __ffs(__ballot_sync(0xffffffffu, lm == gm)) - 1;
+                            if (lane == owner)
+                                for (int i = 0; i < nv; ++i) if (col[32 * i] == gm) { col[32 * i] = kTaken; break; }
+                            sv += (double)__uint_as_float(gm);
+                        }
+                        __syncwarp();
+#pragma unroll 1
+                        for (int e = 0; e < q; ++e) {
+                            uint32_t lx = 0u;
+                            for (int i = 0; i < nv; ++i) { const uint32_t x = col[32 * i]; lx = max(lx, x == kTaken ? 0u : x); }
+                            const uint32_t gx = __reduce_max_sync(0xffffffffu, lx);
+                            const int owner = __ffs(__ballot_sync(0xffffffffu, lx == gx)) - 1;
+                            if (lane == owner)
+                                for (int i = 0; i < nv; ++i) if (col[32 * i] == gx) { col[32 * i] = kTaken; break; }
+                            sq += (double)__uint_as_float(gx);
+                        }
+                        __syncwarp();
+                        const float vmean = (float)(sv / q), pmean = (float)(sq / q);   // np.mean of float32 values
+                        if (lane == b) { vm = vmean; pm = pmean; }
+                    }
+                    if (lane < kBands) {                                        // power_to_db of float64 arrays (top_db at clip end)
+                        S.vl[(size_t)lane * nfr + t] = (float)(10.0 * log10(fmax(1e-10, (double)vm)));
+                        S.pk[(size_t)lane * nfr + t] = (float)(10.0 * log10(fmax(1e-10, (double)pm)));
                     }
                 }
                 // rms over the STFT frame (centre padding with zeros), zero crossings over the 2048 window (edge padding)
@@ -374,7 +387,7 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
         // ---- MFCC series: DCT-II of the clipped dB, four coefficients per thread ---------------------------
         {
             const int kq = (K + 3) / 4;
-            for (int i = tid; i < kq * nfr; i += kThreads) {
+            for (int i = tid; i < kq * nfr; i += kCT) {
                 const int kb = 4 * (i / nfr), t = i % nfr;
                 float acc[4] = {0.f, 0.f, 0.f, 0.f};
                 for (int m = 0; m < n_mels; ++m) {
@@ -392,7 +405,7 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
         }
         // contrast: power_to_db's top_db clip is relative to the maximum over the whole (band, frame) array
         float pmax = -3.0e38f, qmax = -3.0e38f;
-        for (int i = tid; i < kBands * nfr; i += kThreads) { pmax = fmaxf(pmax, S.pk[i]); qmax = fmaxf(qmax, S.vl[i]); }
+        for (int i = tid; i < kBands * nfr; i += kCT) { pmax = fmaxf(pmax, S.pk[i]); qmax = fmaxf(qmax, S.vl[i]); }
         pmax = warp_max(pmax); qmax = warp_max(qmax);
         __syncthreads();                                       // (s_red reads above are done; MFCC series visible below)
         if (lane == 0) { s_red[warp] = pmax; s_red[32 + warp] = qmax; }
@@ -451,9 +464,9 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
                 uint32_t prefix = 0, mask = 0;
                 for (int pass = 3; pass >= 0; --pass) {
                     __syncthreads();
-                    s_hist[tid] = 0;
+                    if (tid < 256) s_hist[tid] = 0;
                     __syncthreads();
-                    for (int i = tid; i < M; i += kThreads) {
+                    for (int i = tid; i < M; i += kCT) {
                         const uint32_t key = fkey(S.cm[i]);
                         if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> (8 * pass)) & 255], 1);
                     }
@@ -475,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
         __syncthreads();
         if (tid < 128) s_hist[tid] = 0;
         __syncthreads();
-        for (int i = tid; i < M; i += kThreads) {
+        for (int i = tid; i < M; i += kCT) {
             if (S.cm[i] >= med) {
                 // pitch_tuning: residual of 12 log2(f / 27.5) in float32, folded to [-0.5, 0.5), 100 bins of 0.01
                 float r = fmodf(__fmul_rn(12.0f, log2f(__fdiv_rn(S.cp[i], 27.5f))), 1.0f);
@@ -493,13 +506,19 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
             int best = 50, bc = -1;                                  // no candidates: tuning 0.0 = bank 50
             if (M > 0) { best = 0; for (int b = 0; b < 100; ++b) if (s_hist[b] > bc) { bc = s_hist[b]; best = b; } }
             s_misc[4] = best;
-            if (p.tuning_out) p.tuning_out[clip] = (float)(best * 0.01 - 0.5);
+            if (p.tuning_out) p.tuning_out[clip] = (float)__dadd_rn(__dmul_rn((double)best, 0.01), -0.5);
         }
         __syncthreads();
 
         // ---- chroma with that tuning's filterbank, tonnetz; one warp per frame ----------------------------------
         {
-            const float* fb = p.chroma + (size_t)s_misc[4] * 12 * NB;
+            // the bank of this clip's tuning, staged over the (now idle) sample / exchange / power tiles
+            float* const fb = reinterpret_cast<float*>(smem_raw);
+            {
+                const float* g = p.chroma + (size_t)s_misc[4] * 12 * NB;
+                for (int i = tid; i < 12 * NB; i += kCT) fb[i] = __ldg(g + i);
+            }
+            __syncthreads();
             double a1 = 0.0, a2 = 0.0;                               // lane c < 12: chroma class c; 12..17: tonnetz dim
             for (int t = warp; t < nfr; t += kWarps) {
                 const float* pr = S.P + (size_t)t * NB;
@@ -509,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) classical_kernel(ClassicalParams 
                 for (int k = lane; k < NB; k += 32) {
                     const float pwk = pr[k];
 #pragma unroll
-                    for (int c = 0; c < 12; ++c) acc[c] = fmaf(__ldg(fb + (size_t)c * NB + k), pwk, acc[c]);
+                    for (int c = 0; c < 12; ++c) acc[c] = fmaf(fb[c * NB + k], pwk, acc[c]);
                 }
                 float mxc = 0.f, l1 = 0.f;
 #pragma unroll
@@ -565,7 +584,7 @@ cudaError_t launch_t(const ClassicalParams& p, int grid, cudaStream_t st) {
     auto k = classical_kernel<LOG2NC, I16>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<grid, kThreads, smem, st>>>(p);
+    k<<<grid, kCT, smem, st>>>(p);
     return cudaGetLastError();
 }
 

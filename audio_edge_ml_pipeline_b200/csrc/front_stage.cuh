@@ -46,7 +46,7 @@ __device__ __forceinline__ float load_sample(const void* clip, int s, int n, int
 // clip whose start is not a multiple of 8 samples (110 250-sample clips: three out of four) still
 // streams through vector loads — only the shared-memory stores narrow to the alignment that is left.
 // The loads of a batch are issued before the first conversion (one L2/DRAM round trip per batch).
-template <bool I16>
+template <bool I16, int NT = kThreads>
 __device__ __forceinline__ void stage_audio(float* __restrict__ dst, const void* __restrict__ clip,
                                             long long clip_elem0, int c0, int len, int n, int pad_mode,
                                             bool base_aligned) {
@@ -55,15 +55,15 @@ __device__ __forceinline__ void stage_audio(float* __restrict__ dst, const void*
     // samples [c0 + head, ...) start on a 16-byte boundary of the batch (base_aligned: the batch itself does)
     const int head = base_aligned ? (int)((V - ((clip_elem0 + c0) & (V - 1))) & (V - 1)) : len;
     const int hl = head < len ? head : len;
-    for (int i = threadIdx.x; i < hl; i += kThreads) dst[i] = load_sample<I16>(clip, c0 + i, n, pad_mode);
+    for (int i = threadIdx.x; i < hl; i += NT) dst[i] = load_sample<I16>(clip, c0 + i, n, pad_mode);
     const int groups = len > hl ? (len - hl + V - 1) / V : 0;
 #pragma unroll 1
-    for (int g0 = threadIdx.x; g0 < groups; g0 += kBatch * kThreads) {
+    for (int g0 = threadIdx.x; g0 < groups; g0 += kBatch * NT) {
         int4 raw[kBatch];
         int state[kBatch];                       // 0: none, 1: vector load, 2: edge (clip boundary, padding, tail)
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
-            const int g = g0 + u * kThreads, i = hl + g * V, sidx = c0 + i;
+            const int g = g0 + u * NT, i = hl + g * V, sidx = c0 + i;
             state[u] = g < groups ? ((sidx >= 0 && sidx + V <= n && i + V <= len) ? 1 : 2) : 0;
             if (state[u] == 1)
                 raw[u] = __ldg(reinterpret_cast<const int4*>(I16 ? (const void*)((const int16_t*)clip + sidx)
@@ -72,7 +72,7 @@ __device__ __forceinline__ void stage_audio(float* __restrict__ dst, const void*
 #pragma unroll
         for (int u = 0; u < kBatch; ++u) {
             if (state[u] == 0) continue;
-            const int g = g0 + u * kThreads, i = hl + g * V, sidx = c0 + i;
+            const int g = g0 + u * NT, i = hl + g * V, sidx = c0 + i;
             if (state[u] == 2) {
 #pragma unroll
                 for (int e = 0; e < V; ++e)
