@@ -313,6 +313,8 @@ class Engine:
         for c, s, L in zip(clips, starts, lens):
             packed[s:s + L] = c
         frames = 1 + lens // self.cfg.hop_length
+        if self.cfg.kind == KIND_CLASSICAL:       # one aggregated vector per clip whatever its length
+            frames = np.ones(n, dtype=np.int32)
         sizes = self.rows * frames.astype(np.int64)
         ooff = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
         out = np.empty(int(sizes.sum()), dtype=np.float32)

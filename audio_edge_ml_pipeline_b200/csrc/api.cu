@@ -420,7 +420,6 @@ static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, 
         return B2A_OK;
     }
     if (h->cfg.kind == B2A_KIND_CLASSICAL) {
-        if (rag_len) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
         if (n_clips > h->cls_tuning_cap) {           // (grow-only; the previous run on this handle is ordered before by the caller)
             cudaFree(h->d_cls_tuning);
             h->d_cls_tuning = nullptr; h->cls_tuning_cap = 0;
@@ -435,6 +434,7 @@ static int run_device_impl(b2a_handle* h, const void* d_clips, int64_t n_clips, 
         c.band_start = h->d_bands; c.band_cnt = h->d_bands + 7; c.band_q = h->d_bands + 14;
         c.scratch = h->d_cls_scratch; c.scratch_per_cta = h->cls_scratch_per_cta;
         c.tuning_out = h->d_cls_tuning;
+        c.rag_in_off = rag_in; c.rag_len = rag_len; c.rag_out_off = rag_out;
         c.n_clips = n_clips; c.n_samples = h->cfg.n_samples; c.hop = h->cfg.hop_length; c.n_frames = h->cls_frames;
         c.n_mels = h->cfg.n_mels; c.mel_nnz = (int)h->mel.w.size(); c.n_mfcc = h->cfg.n_mfcc;
         c.sample_rate = h->cfg.sample_rate; c.pip_k0 = h->cls.pip_k0; c.pip_k1 = h->cls.pip_k1;
@@ -651,7 +651,7 @@ int b2a_run_device_ragged(b2a_handle* h, const void* d_clips, const int64_t* d_i
                           const int32_t* d_lengths, const int64_t* d_out_offsets, int64_t n_clips,
                           float* d_out, void* stream) {
     if (!h) return fail(B2A_EINVAL, "handle is NULL");
-    if (h->cfg.kind != B2A_KIND_MEL && h->cfg.kind != B2A_KIND_MFCC) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
+    if (h->cfg.kind == B2A_KIND_CQT) return fail(B2A_EINVAL, "ragged batches: mel, mfcc and classical handles only");
     if (n_clips < 0) return fail(B2A_EINVAL, "n_clips < 0");
     if (n_clips > 0 && (!d_clips || !d_out || !d_in_offsets || !d_lengths || !d_out_offsets))
         return fail(B2A_EINVAL, "NULL buffer");
@@ -666,16 +666,18 @@ int b2a_run_host_ragged(b2a_handle* h, const void* clips, int64_t total_in, cons
                         const int32_t* lengths, const int64_t* out_offsets, int64_t n_clips,
                         float* out, int64_t total_out) {
     if (!h) return fail(B2A_EINVAL, "handle is NULL");
-    if (h->cfg.kind != B2A_KIND_MEL && h->cfg.kind != B2A_KIND_MFCC) return fail(B2A_EINVAL, "ragged batches: mel and mfcc handles only");
+    if (h->cfg.kind == B2A_KIND_CQT) return fail(B2A_EINVAL, "ragged batches: mel, mfcc and classical handles only");
     if (n_clips < 0 || total_in < 0 || total_out < 0) return fail(B2A_EINVAL, "negative size");
     if (n_clips == 0) { h->last_launches = 0; return B2A_OK; }
     if (!clips || !out || !in_offsets || !lengths || !out_offsets) return fail(B2A_EINVAL, "NULL buffer");
     const int hop = h->cfg.hop_length;
+    const bool classical = h->cfg.kind == B2A_KIND_CLASSICAL;
     for (int64_t i = 0; i < n_clips; ++i) {
         const int64_t L = lengths[i];
         if (L < h->cfg.n_fft || L > h->cfg.n_samples) return fail(B2A_EINVAL, "clip length outside [n_fft, cfg.n_samples]");
+        if (classical && L < 8 * hop) return fail(B2A_EINVAL, "classical: clip shorter than 8 hops (classical.py:262-270 pads to it)");
         if (in_offsets[i] < 0 || in_offsets[i] + L > total_in) return fail(B2A_EINVAL, "input offset out of range");
-        const int64_t need = (int64_t)h->rows * (1 + L / hop);
+        const int64_t need = classical ? (int64_t)h->rows : (int64_t)h->rows * (1 + L / hop);
         if (out_offsets[i] < 0 || out_offsets[i] + need > total_out) return fail(B2A_EINVAL, "output offset out of range");
     }
     CU_TRY(cudaSetDevice(h->device));

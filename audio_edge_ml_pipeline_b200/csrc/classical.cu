@@ -123,18 +123,20 @@ __global__ void __launch_bounds__(kCT, 1) classical_kernel(ClassicalParams p) {
     const float2* const win = reinterpret_cast<const float2*>(p.window) + j;   // pairs (w[2n], w[2n+1]), n = j + T t: L1-resident
     __syncthreads();
 
-    const int n = p.n_samples, nfr = p.n_frames, n_mels = p.n_mels, K = p.n_mfcc, hop = p.hop;
+    int n = p.n_samples, nfr = p.n_frames;                  // per clip when ragged
+    const int n_mels = p.n_mels, K = p.n_mfcc, hop = p.hop;
     const bool hop_even = (hop & 1) == 0;
     const size_t esz = I16 ? 2 : 4;
     const bool base_aligned = (reinterpret_cast<uintptr_t>(p.clips) & 15) == 0;
-    const Scratch S = carve(p.scratch + (size_t)blockIdx.x * p.scratch_per_cta, nfr, NB, n_mels, K, p.cand_cap);
+    const Scratch S = carve(p.scratch + (size_t)blockIdx.x * p.scratch_per_cta, p.n_frames, NB, n_mels, K, p.cand_cap);
     const double bin_hz = (double)p.sample_rate / NFFT;
     const int rows_out = 6 * K + 62;
 
     for (long long clip = blockIdx.x; clip < p.n_clips; clip += gridDim.x) {
-        const long long clip_elem0 = clip * (long long)n;
+        if (p.rag_len) { n = p.rag_len[clip]; nfr = 1 + n / hop; }
+        const long long clip_elem0 = p.rag_len ? p.rag_in_off[clip] : clip * (long long)n;
         const void* cptr = (const unsigned char*)p.clips + (size_t)clip_elem0 * esz;
-        float* const outv = p.out + (size_t)clip * rows_out;
+        float* const outv = p.rag_len ? p.out + p.rag_out_off[clip] : p.out + (size_t)clip * rows_out;
         float vmax = -3.0e38f;
         if (tid == 0) s_misc[0] = 0;
         __syncthreads();

@@ -25,6 +25,11 @@ struct ClassicalParams {
     float* scratch;             // [grid][scratch_per_cta] floats
     size_t scratch_per_cta;
     float* tuning_out;          // [n_clips] estimated tuning of every clip (diagnostic; may be null)
+    // ragged batches (NULL for fixed-length): per-clip element offset into clips, length in samples, float offset
+    // into out; n_samples / n_frames then hold the MAXIMA (scratch sizing)
+    const long long* rag_in_off;
+    const int* rag_len;
+    const long long* rag_out_off;
     long long n_clips;
     int n_samples, hop, n_frames, n_mels, mel_nnz, n_mfcc, sample_rate;
     int pip_k0, pip_k1;         // piptrack bins: 150 Hz <= f < min(4 kHz, sr / 2)

@@ -306,7 +306,7 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
         labels: list = []
         metas: list = []
         label_to_idx: dict = {}
-        ragged = self.duration is None and self._kind in (B.KIND_MEL, B.KIND_MFCC)
+        ragged = self.duration is None and self._kind != B.KIND_CQT
         n_fixed = int(self.duration * self.sample_rate) if self.duration is not None else 0
         native = NATIVE_DECODE and self.duration is not None and n_fixed >= self._min_samples()
         # fixed duration + a sized loader: windows land in one preallocated array (no concatenation) for as

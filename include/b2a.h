@@ -122,7 +122,8 @@ int b2a_run_host(b2a_handle* h, const void* clips, int64_t n_clips, float* out);
 int b2a_run_host_copy_only(b2a_handle* h, const void* clips, int64_t n_clips, float* out);
 
 /* Ragged batches (`duration=None` in the reference: every clip keeps its own length and frame
- * count; deep.py:122-124 is skipped).  mel and mfcc handles only.  Clip i has lengths[i] samples,
+ * count; deep.py:122-124 is skipped).  mel, mfcc and classical handles (a classical clip yields its `rows`
+ * floats whatever its length and must hold at least 8 hops — the reference extractor takes whole files).  Clip i has lengths[i] samples,
  * n_fft <= lengths[i] <= cfg.n_samples (the handle's n_samples is the MAXIMUM length), stored at
  * element offset in_offsets[i] of `clips` (a multiple of 8 elements keeps the TMA staging path);
  * its (rows, 1 + lengths[i]/hop) float32 features are written at float offset out_offsets[i] of

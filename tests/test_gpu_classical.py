@@ -128,3 +128,32 @@ def test_classical_extractor_mirror(tmp_path):
     ref_seg = C.audio_classical(L.pcm16_to_float(pcm[1][int(0.5 * sr):int(0.5 * sr) + int(1.5 * sr)]))
     assert np.allclose(seg[:40], ref_seg[:40], rtol=1e-5, atol=2e-5 * float(np.abs(ref_seg[:40]).max()))
     ex.close(); lean.close()
+
+
+def test_classical_ragged_batch_and_dataset(tmp_path):
+    """The reference extractor has no `duration`: every file keeps its own length (classical.py:243-270).  One ragged
+    launch for the lot, and the dataset path over variable-length WAV files."""
+    sr = 22050
+    rng = np.random.default_rng(5)
+    lens = [4096, 22050, 30001, 66150, 110250, 5000]
+    clips = [synth.make_suite(1, sr, n, seed=100 + i)[0] for i, n in enumerate(lens)]
+    with _engine(131072) as e:
+        got = e.run_host_ragged(clips)
+        tun = e.classical_tunings(len(clips))
+    assert all(g.shape == (302, 1) for g in got)
+    got = np.stack([g[:, 0] for g in got])
+    ref = np.stack([C.audio_classical(L.pcm16_to_float(c)) for c in clips])
+    rtun = np.array([C.frame_features(L.pcm16_to_float(c))["_tuning"] for c in clips])
+    _check(got, ref, np.abs(tun - rtun) < 1e-6)
+
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    for k, c in enumerate(clips):
+        d = tmp_path / ("a" if k % 2 else "b")
+        d.mkdir(exist_ok=True)
+        wavio.write_wav_pcm16(d / f"c{k}.wav", c, sr)
+    ex = get("audio_classical")(features=["mfcc", "spectral_centroid", "zcr"])
+    fs = ex.extract_dataset(AudioFolderLoader(tmp_path))
+    assert fs.features.shape == (6, ex.feature_dim) and fs.feature_type == "classical"
+    order = sorted(range(6), key=lambda k: ("a" if k % 2 else "b", f"c{k}.wav"))     # loader order: class, then file name
+    assert np.array_equal(fs.features, got[order][:, ex._columns])
+    ex.close()
