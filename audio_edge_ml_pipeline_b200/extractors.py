@@ -592,10 +592,9 @@ class AudioClassicalExtractor(_GpuAudioExtractor):
 
     def extract_batch(self, clips: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """(N, n_samples) equal-length clips -> (N, feature_dim) float32."""
-        full = super().extract_batch(clips)
         if getattr(self, "_raw_rows", False):       # inside extract_dataset: rows stay device vectors until the end
-            return full
-        got = self._select(full)
+            return super().extract_batch(clips, out)
+        got = self._select(super().extract_batch(clips))
         if out is not None:
             out[...] = got
             return out

@@ -157,3 +157,11 @@ def test_classical_ragged_batch_and_dataset(tmp_path):
     order = sorted(range(6), key=lambda k: ("a" if k % 2 else "b", f"c{k}.wav"))     # loader order: class, then file name
     assert np.array_equal(fs.features, got[order][:, ex._columns])
     ex.close()
+    # fixed duration: the native decode front end writes whole windows (pad / trim to 1.5 s here)
+    ex2 = get("audio_classical")(duration=1.5, aggregations=["mean"])
+    fs2 = ex2.extract_dataset(AudioFolderLoader(tmp_path))
+    n15 = int(1.5 * sr)
+    fixed = np.stack([np.pad(c, (0, max(0, n15 - len(c))))[:n15] for c in clips])
+    want = ex2.extract_batch(fixed)
+    assert fs2.features.shape == (6, 151) and np.array_equal(fs2.features, want[order])
+    ex2.close()
