@@ -301,7 +301,12 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
             run(key, idxs)
         return res
 
-    def extract_dataset(self, loader, max_samples: Optional[int] = None) -> FeatureSet:
+    def extract_dataset(self, loader, max_samples: Optional[int] = None, features_out=None) -> FeatureSet:
+        """``features_out``: path of the ``features.npy`` this run will be saved as (FeaturePipeline passes it).
+        With a fixed duration and a sized loader the feature rows are then written straight into that file
+        (a memory-mapped NPY v1 array, the same bytes ``np.save`` produces) instead of into an anonymous
+        array that ``save`` copies once more; if any sample is skipped the run falls back to the in-memory
+        array and ``save`` writes the file as usual."""
         feats: list = []             # arrays (k, rows, T) (or per-clip (1, rows, T_i) when ragged), loader order
         labels: list = []
         metas: list = []
@@ -383,7 +388,12 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
                         shape = (eng.rows, eng.frames)
                         if final["arr"] is None and final["open"] and hasattr(loader, "__len__"):
                             cap = len(loader) if max_samples is None else min(len(loader), max_samples)
-                            final["arr"] = np.empty((cap,) + shape, dtype=np.float32)
+                            if features_out is not None and cap > 0:
+                                Path(features_out).parent.mkdir(parents=True, exist_ok=True)
+                                final["arr"] = np.lib.format.open_memmap(str(features_out), mode="w+", dtype=np.float32,
+                                                                         shape=(cap,) + shape)
+                            else:
+                                final["arr"] = np.empty((cap,) + shape, dtype=np.float32)
                         pos = final["pos"]
                         in_place = final["open"] and final["arr"] is not None and pos + len(items) <= len(final["arr"])
                         if in_place:
@@ -422,8 +432,17 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
                     book(items[i])
         if not metas:
             raise RuntimeError("No features were successfully extracted.")
+        mapped = isinstance(final["arr"], np.memmap)
+        if mapped and not tail and final["pos"] == len(final["arr"]):
+            fs = assemble_feature_set(self, final["arr"], labels, metas, label_to_idx)
+            fs.features_file = Path(features_out)      # save() finds the rows already in place
+            return fs
         parts = ([final["arr"][:final["pos"]]] if final["pos"] else []) + tail
-        features = parts[0] if len(parts) == 1 else np.concatenate(parts)       # ragged shapes -> ValueError
+        features = np.array(parts[0]) if (len(parts) == 1 and mapped) else \
+            (parts[0] if len(parts) == 1 else np.concatenate(parts))            # ragged shapes -> ValueError
+        if mapped:                                     # samples were skipped: the file's shape is wrong, drop it
+            final["arr"] = None
+            Path(features_out).unlink(missing_ok=True)
         return assemble_feature_set(self, features, labels, metas, label_to_idx)
 
 
@@ -600,7 +619,9 @@ class AudioClassicalExtractor(_GpuAudioExtractor):
             return out
         return got
 
-    def extract_dataset(self, loader, max_samples: Optional[int] = None) -> FeatureSet:
+    def extract_dataset(self, loader, max_samples: Optional[int] = None, features_out=None) -> FeatureSet:
+        # (features_out is not used: the rows written during the run are full device vectors, the file holds the
+        #  selected columns; save() writes it)
         self._raw_rows = True
         try:
             fs = super().extract_dataset(loader, max_samples)

@@ -14,6 +14,7 @@ into the constructor exactly like pipeline.py:524 — an unknown key is a TypeEr
 from __future__ import annotations
 
 import argparse
+import inspect
 import json
 import logging
 import shutil
@@ -35,10 +36,15 @@ class FeaturePipeline:
         self.loader = loader
         self.extractor = extractor
 
-    def run(self, max_samples: Optional[int] = None) -> FeatureSet:
+    def run(self, max_samples: Optional[int] = None, output_dir=None) -> FeatureSet:
+        """``output_dir`` (optional, an addition to the reference's signature): where ``save`` will put this run.
+        Extractors that can then write their rows straight into ``output_dir/features.npy`` (no second copy)."""
         logger.info("Starting extraction: loader=%s (%d samples), extractor=%s",
                     type(self.loader).__name__, len(self.loader), self.extractor.name)
-        fs = self.extractor.extract_dataset(self.loader, max_samples=max_samples)
+        kw = {}
+        if output_dir is not None and "features_out" in inspect.signature(self.extractor.extract_dataset).parameters:
+            kw["features_out"] = Path(output_dir) / "features.npy"
+        fs = self.extractor.extract_dataset(self.loader, max_samples=max_samples, **kw)
         logger.info("Extraction complete: %s", fs)
         return fs
 
@@ -46,7 +52,12 @@ class FeaturePipeline:
     def save(fs: FeatureSet, output_dir) -> None:
         output_dir = Path(output_dir)
         output_dir.mkdir(parents=True, exist_ok=True)
-        np.save(output_dir / "features.npy", fs.features)
+        placed = getattr(fs, "features_file", None)
+        if placed is not None and Path(placed).resolve() == (output_dir / "features.npy").resolve() \
+                and isinstance(fs.features, np.memmap):
+            fs.features.flush()                        # extract_dataset wrote the rows into this very file
+        else:
+            np.save(output_dir / "features.npy", fs.features)
         if fs.labels is not None:
             np.save(output_dir / "labels.npy", fs.labels)
         if fs.label_names is not None:
@@ -124,8 +135,8 @@ def build_loader(exp: dict) -> BaseDatasetLoader:
 def run_experiment(exp: dict, config_path: Optional[Path] = None) -> FeatureSet:
     loader = build_loader(exp)
     extractor = get(exp["extractor"])(**(exp.get("extractor_params") or {}))
-    fs = FeaturePipeline(loader, extractor).run(max_samples=exp.get("max_samples"))
     out = Path(exp["output"])
+    fs = FeaturePipeline(loader, extractor).run(max_samples=exp.get("max_samples"), output_dir=out)
     FeaturePipeline.save(fs, out)
     if config_path is not None:
         shutil.copy2(config_path, out / "config.yaml")

@@ -348,6 +348,40 @@ def test_save_layout_and_roundtrip(tmp_path, fake):
         P.FeaturePipeline.load(tmp_path / "nowhere")
 
 
+def test_features_are_written_in_place_when_the_output_is_known(tmp_path, fake, lib_built):
+    """run(output_dir=...) + save: features.npy is the memory-mapped array the run filled (no second copy), byte for
+    byte what np.save writes; a skipped sample makes the run fall back to the ordinary array + np.save."""
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    _make_dataset(tmp_path / "ds", n=8000)
+    loader = AudioFolderLoader(tmp_path / "ds")
+    ref = P.FeaturePipeline(loader, P.AudioMelSpectrogram(duration=0.5)).run()
+    P.FeaturePipeline.save(ref, tmp_path / "plain")
+    fs = P.FeaturePipeline(loader, P.AudioMelSpectrogram(duration=0.5)).run(output_dir=tmp_path / "out")
+    assert isinstance(fs.features, np.memmap) and fs.features_file == tmp_path / "out" / "features.npy"
+    P.FeaturePipeline.save(fs, tmp_path / "out")
+    assert (tmp_path / "out" / "features.npy").read_bytes() == (tmp_path / "plain" / "features.npy").read_bytes()
+    assert np.array_equal(P.FeaturePipeline.load(tmp_path / "out").features, ref.features)
+    # saving somewhere else still works (plain np.save of the mapped rows)
+    P.FeaturePipeline.save(fs, tmp_path / "elsewhere")
+    assert np.array_equal(np.load(tmp_path / "elsewhere" / "features.npy"), ref.features)
+    # a broken file: rows are compacted in memory, the half-written file is dropped and save() writes the real one
+    _make_dataset(tmp_path / "ds2", n=8000, broken={("axe", 1)})
+    loader2 = AudioFolderLoader(tmp_path / "ds2")
+    fs2 = P.FeaturePipeline(loader2, P.AudioMelSpectrogram(duration=0.5)).run(output_dir=tmp_path / "out2")
+    assert not isinstance(fs2.features, np.memmap) and not (tmp_path / "out2" / "features.npy").exists()
+    P.FeaturePipeline.save(fs2, tmp_path / "out2")
+    assert np.load(tmp_path / "out2" / "features.npy").shape[0] == len(loader2) - 1
+
+
+def test_loader_metadata_same_through_native_and_python_probe(tmp_path, lib_built, monkeypatch):
+    from audio_edge_ml_pipeline_b200 import loaders
+    _make_dataset(tmp_path / "ds", n=8000, broken={("axe", 1)})
+    a = list(loaders.AudioFolderLoader(tmp_path / "ds"))
+    monkeypatch.setattr(loaders, "_probe_all", lambda paths: [loaders.wav_info(p) for p in paths])
+    b = list(loaders.AudioFolderLoader(tmp_path / "ds"))
+    assert a == b and any(m["sample_rate"] == 0 for _p, _l, m in a)          # the broken file: zeros either way
+
+
 def test_reference_yaml_runs_unchanged(tmp_path, fake, monkeypatch):
     """config/feature_extraction.yaml:60-70, copied verbatim (keys + extractor_params)."""
     cfg = """
