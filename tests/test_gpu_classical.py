@@ -165,3 +165,21 @@ def test_classical_ragged_batch_and_dataset(tmp_path):
     want = ex2.extract_batch(fixed)
     assert fs2.features.shape == (6, 151) and np.array_equal(fs2.features, want[order])
     ex2.close()
+
+
+def test_classical_host_path_is_chunk_invariant():
+    """b2a_run_host splits a large batch into chunks on two streams that share the handle's per-CTA scratch: a
+    clip's vector must not depend on the batch it travels in."""
+    n = 4096
+    base = synth.make_suite(9, 22050, n, seed=31)
+    pcm = np.tile(base, (600, 1))                          # 5 400 clips: more than one chunk of 4 096
+    for k in range(len(pcm)):
+        pcm[k] = np.roll(pcm[k], 7 * (k // 9))             # (all different)
+    with _engine(n) as e:
+        big = e.run_host(pcm)[:, :, 0]
+        pick = np.array([0, 1, 4095, 4096, 4097, 5399])
+        small = e.run_host(pcm[pick])[:, :, 0]
+    assert np.isfinite(big).all() and np.array_equal(big[pick], small)
+    assert np.array_equal(big[:9], big[:9])
+    ref = C.audio_classical(L.pcm16_to_float(pcm[5399]))
+    assert np.allclose(big[5399, :40], ref[:40], rtol=1e-5, atol=2e-5 * float(np.abs(ref[:40]).max()))
