@@ -33,6 +33,7 @@ EXPORTED_SYMBOLS = [
     "b2a_resampler_design", "b2a_resampler_run_host", "b2a_resampler_run_device", "b2a_resampler_last_error",
     "b2a_resampler_run_device_batch", "b2a_resampler_rates", "b2a_run_host_resampled",
     "b2a_augment_host", "b2a_augment_device", "b2a_classical_tunings",
+    "b2a_time_stretch_host", "b2a_pitch_shift_host",
 ]
 
 
@@ -173,6 +174,55 @@ def probe_wav_batch(paths, n_threads: int = 0) -> dict:
                                        out["format_tag"].ctypes.data, out["n_frames"].ctypes.data,
                                        out["status"].ctypes.data, int(n_threads)))
     return out
+
+
+def _pack_rows(rows):
+    lens = np.array([len(r) for r in rows], dtype=np.int32)
+    off = np.concatenate([[0], np.cumsum(lens.astype(np.int64))[:-1]]).astype(np.int64) if len(rows) else np.zeros(0, np.int64)
+    src = np.concatenate([np.asarray(r, dtype=np.float32) for r in rows]) if len(rows) else np.zeros(0, np.float32)
+    return src, off, lens
+
+
+def time_stretch_rows(rows, rates, device: int = 0) -> list:
+    """librosa.effects.time_stretch on the GPU for a batch of float32 rows of any lengths (augment.py:105-110):
+    row i comes back with int(round(len / rate_i)) samples.  No CPU path."""
+    lib = load_library()
+    if len(rows) == 0:
+        return []
+    src, off, lens = _pack_rows(rows)
+    rates = np.ascontiguousarray(rates, dtype=np.float64)
+    if not (rates > 0).all():
+        raise ValueError("rate must be a positive number")          # librosa.effects.time_stretch's ParameterError
+    out_len = np.array([int(round(int(n) / float(r))) for n, r in zip(lens, rates)], dtype=np.int32)
+    out_off = np.concatenate([[0], np.cumsum(out_len.astype(np.int64))[:-1]]).astype(np.int64)
+    out = np.empty(int(out_len.sum()), dtype=np.float32)
+    fn = lib.b2a_time_stretch_host
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    fn.argtypes = [i32, vp, i64, vp, vp, vp, i64, vp, i64, vp, vp]
+    fn.restype = C.c_int
+    _check(fn(int(device), src.ctypes.data, src.size, off.ctypes.data, lens.ctypes.data, rates.ctypes.data, len(rows),
+              out.ctypes.data, out.size, out_off.ctypes.data, out_len.ctypes.data))
+    return [out[o:o + n] for o, n in zip(out_off, out_len)]
+
+
+def pitch_shift_rows(rows, sr: int, n_steps, device: int = 0) -> list:
+    """librosa.effects.pitch_shift on the GPU (augment.py:113-118): time_stretch by 2 ** (-n_steps / 12), resample back
+    by that ratio, crop / zero-pad to the input length.  No CPU path."""
+    lib = load_library()
+    if len(rows) == 0:
+        return []
+    src, off, lens = _pack_rows(rows)
+    rates = np.array([2.0 ** (-float(s) / 12) for s in n_steps], dtype=np.float64)
+    ratios = np.array([float(sr) / (float(sr) / r) for r in rates], dtype=np.float64)     # target_sr / orig_sr (librosa.resample)
+    mid = np.array([int(round(int(n) / float(r))) for n, r in zip(lens, rates)], dtype=np.int32)
+    out = np.empty(int(lens.sum()), dtype=np.float32)
+    fn = lib.b2a_pitch_shift_host
+    vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
+    fn.argtypes = [i32, vp, i64, vp, vp, vp, vp, vp, i64, vp, i64, vp]
+    fn.restype = C.c_int
+    _check(fn(int(device), src.ctypes.data, src.size, off.ctypes.data, lens.ctypes.data, rates.ctypes.data,
+              ratios.ctypes.data, mid.ctypes.data, len(rows), out.ctypes.data, out.size, off.ctypes.data))
+    return [out[o:o + n] for o, n in zip(off, lens)]
 
 
 def decode_wav_batch(paths, max_frames: int, out: np.ndarray, offsets=None, durations=None, n_threads: int = 0):

@@ -12,8 +12,12 @@ noise row is synthesised on the host next to the draw that feeds it (the same ``
 ``rng.standard_normal(n)``, hence the same float32 row as the reference), and the device mixes it into the
 clip exactly like white noise (``clip(y + row * amplitude)``).
 
-Not built: ``time_stretch`` / ``pitch_shift`` (librosa phase vocoder, augment.py:105-118).  A chain naming
-one of them raises ``NotImplementedError`` up front rather than silently dropping the step.
+``time_stretch`` / ``pitch_shift`` (augment.py:105-118 -> librosa.effects) change the clip as a whole — and the
+first one its length — so a chain that names them runs in stages: the element-wise steps before, between and after
+them stay fused in the augmentation kernel, each vocoder step is one batched call into ``csrc/effects.cu`` for every
+row that reaches it, and the lengths that later draws depend on (``standard_normal(len(y))``, the roll of
+``time_shift``) are tracked at draw time (``int(round(n / rate))``, as librosa computes it), so the random stream
+is still consumed exactly like the reference consumes it.
 
 Two ways out of Stage 1b:
   * :func:`run` writes the class-per-folder WAV tree the reference writes (PCM16 via soundfile there;
@@ -37,9 +41,11 @@ from . import wavio
 logger = logging.getLogger(__name__)
 
 AUG_END, AUG_GAIN, AUG_NOISE, AUG_ROLL, AUG_POLARITY = -1, 0, 1, 2, 3
-SUPPORTED = ("volume_scale", "gaussian_noise", "time_shift", "polarity_inversion", "pdm_hiss")
-NOT_BUILT = ("time_stretch", "pitch_shift")
-VALID_TYPES = sorted(SUPPORTED + NOT_BUILT)
+ELEMENTWISE = ("volume_scale", "gaussian_noise", "time_shift", "polarity_inversion", "pdm_hiss")
+VOCODER = ("time_stretch", "pitch_shift")          # librosa.effects: csrc/effects.cu, one batched call per step
+SUPPORTED = ELEMENTWISE + VOCODER
+NOT_BUILT = ()
+VALID_TYPES = sorted(SUPPORTED)
 
 
 class AugStep(C.Structure):
@@ -76,8 +82,6 @@ def check_specs(aug_specs: Sequence[dict]) -> None:
         t = spec["type"]
         if t not in VALID_TYPES:
             raise ValueError(f"Unknown augmentation type '{t}'. Valid types: {VALID_TYPES}")    # augment.py:196-200
-        if t in NOT_BUILT:
-            raise NotImplementedError(f"augmentation '{t}' is not built on the GPU path (supported: {list(SUPPORTED)})")
 
 
 def _pink_row(white: np.ndarray, sr: int, notch_freq: float) -> np.ndarray:
@@ -120,6 +124,9 @@ def plan(lengths: Sequence[int], specs_per_clip: Sequence[Sequence[dict]], n_aug
     r = 0
     for n, specs in zip(lengths, specs_per_clip):
         check_specs(specs)
+        if any(sp["type"] in VOCODER for sp in specs):
+            raise ValueError("plan() lays out element-wise chains only; chains with time_stretch / pitch_shift go "
+                             "through augment_ragged / augment_batch (staged execution)")
         n = int(n)
         for copy in range(rows_per):
             k = 0
@@ -154,6 +161,108 @@ def plan(lengths: Sequence[int], specs_per_clip: Sequence[Sequence[dict]], n_aug
     return src_clip, steps, noise, max_steps
 
 
+def _draw_ops(rng, n: int, specs, sample_rate: int) -> list:
+    """One augmented copy's chain with every random parameter drawn, in specification order (augment.py:186-203):
+    a list of ("gain", g) / ("noise", amp, row) / ("roll", shift) / ("pol",) / ("stretch", rate) /
+    ("pitch", n_steps).  ``n`` follows the chain: after a time_stretch the clip has int(round(n / rate)) samples."""
+    ops = []
+    for spec in specs:
+        t = spec["type"]
+        if t == "volume_scale":
+            ops.append(("gain", np.float32(rng.uniform(spec.get("min_gain", 0.7), spec.get("max_gain", 1.3)))))
+        elif t == "gaussian_noise":
+            amp = rng.uniform(spec.get("min_amplitude", 0.001), spec.get("max_amplitude", 0.008))
+            ops.append(("noise", np.float32(amp), rng.standard_normal(n).astype(np.float32)))
+        elif t == "pdm_hiss":
+            white = rng.standard_normal(n)
+            row = _pink_row(white, sample_rate, spec.get("notch_freq", 4000.0))
+            ops.append(("noise", np.float32(rng.uniform(spec.get("min_amplitude", 0.02), spec.get("max_amplitude", 0.08))), row))
+        elif t == "time_shift":
+            f = spec.get("max_fraction", 0.2)
+            ops.append(("roll", int(rng.uniform(-f, f) * n)))
+        elif t == "polarity_inversion":
+            ops.append(("pol",))
+        elif t == "time_stretch":
+            rate = rng.uniform(spec.get("min_rate", 0.85), spec.get("max_rate", 1.15))
+            ops.append(("stretch", float(rate)))
+            n = int(round(n / rate))
+        elif t == "pitch_shift":
+            ops.append(("pitch", float(rng.uniform(spec.get("min_steps", -3.0), spec.get("max_steps", 3.0)))))
+    return ops
+
+
+def _run_staged(clips, specs_per_clip, n_augments, seed, level_match_db, include_originals, out_dtype, device, rng,
+                sample_rate, preserve_length) -> list:
+    """Chains that contain vocoder steps: rows advance in rounds — their next run of element-wise steps in one
+    augmentation-kernel call, then their next vocoder step in one batched effects call — until every row is done."""
+    rng = np.random.default_rng(seed) if rng is None else rng
+    scale = 10.0 ** (float(level_match_db) / 20.0)
+    rows_per = n_augments + (1 if include_originals else 0)
+    cur, todo, orig_len = [], [], []
+    for clip, specs in zip(clips, specs_per_clip):
+        check_specs(specs)
+        y = np.asarray(clip)
+        y = y.astype(np.float32) / np.float32(32768.0) if y.dtype == np.int16 else y.astype(np.float32, copy=False)
+        for copy in range(rows_per):
+            ops = [("gain", np.float32(scale))] if scale != 1.0 else []
+            if not (include_originals and copy == 0):
+                ops += _draw_ops(rng, len(y), specs, sample_rate)
+            cur.append(y)
+            todo.append(ops)
+            orig_len.append(len(y))
+    while any(todo):
+        # (1) the element-wise prefix of every row that has one
+        idx = [i for i, ops in enumerate(todo) if ops and ops[0][0] not in ("stretch", "pitch")]
+        if idx:
+            segs = []
+            for i in idx:
+                k = 0
+                while k < len(todo[i]) and todo[i][k][0] not in ("stretch", "pitch"):
+                    k += 1
+                segs.append(todo[i][:k])
+                todo[i] = todo[i][k:]
+            max_steps = max(len(sg) for sg in segs)
+            steps = np.zeros((len(idx), max_steps), dtype=STEP_DTYPE)
+            steps["op"] = AUG_END
+            noise_rows, pos = [], 0
+            for r, sg in enumerate(segs):
+                for k, op in enumerate(sg):
+                    if op[0] == "gain":
+                        steps[r, k] = (AUG_GAIN, op[1], 0, 0, 0)
+                    elif op[0] == "noise":
+                        steps[r, k] = (AUG_NOISE, op[1], 0, 0, pos)
+                        noise_rows.append(op[2])
+                        pos += len(op[2])
+                    elif op[0] == "roll":
+                        steps[r, k] = (AUG_ROLL, 0.0, op[1], 0, 0)
+                    else:
+                        steps[r, k] = (AUG_POLARITY, 0.0, 0, 0, 0)
+            lens = np.array([len(cur[i]) for i in idx], dtype=np.int32)
+            off = np.concatenate([[0], np.cumsum(lens.astype(np.int64))[:-1]]).astype(np.int64)
+            src = np.concatenate([cur[i] for i in idx])
+            out = np.empty(src.size, dtype=np.float32)
+            noise = np.concatenate(noise_rows) if noise_rows else np.zeros(0, np.float32)
+            _run_host(device, src, off, lens, off, steps, max_steps, noise, out)
+            for r, i in enumerate(idx):
+                cur[i] = out[off[r]:off[r] + lens[r]]
+        # (2) the vocoder step of every row that is waiting at one
+        st = [i for i, ops in enumerate(todo) if ops and ops[0][0] == "stretch"]
+        if st:
+            got = B.time_stretch_rows([cur[i] for i in st], [todo[i][0][1] for i in st], device)
+            for i, g in zip(st, got):
+                cur[i], todo[i] = g, todo[i][1:]
+        ps = [i for i, ops in enumerate(todo) if ops and ops[0][0] == "pitch"]
+        if ps:
+            got = B.pitch_shift_rows([cur[i] for i in ps], sample_rate, [todo[i][0][1] for i in ps], device)
+            for i, g in zip(ps, got):
+                cur[i], todo[i] = g, todo[i][1:]
+    if preserve_length:                                                  # augment.py:206-212
+        cur = [y[:n] if len(y) >= n else np.pad(y, (0, n - len(y))) for y, n in zip(cur, orig_len)]
+    if np.dtype(out_dtype) == np.int16:
+        cur = [quantize_pcm16(y) for y in cur]
+    return [cur[i * rows_per:(i + 1) * rows_per] for i in range(len(clips))]
+
+
 def _run_host(device, src, src_off, lengths, out_off, steps, max_steps, noise, out) -> None:
     lib = B.load_library()
     fn = lib.b2a_augment_host
@@ -168,11 +277,15 @@ def _run_host(device, src, src_off, lengths, out_off, steps, max_steps, noise, o
 
 def augment_ragged(clips: Sequence[np.ndarray], specs_per_clip, n_augments: int = 4, seed: int = 42,
                    level_match_db: float = 0.0, include_originals: bool = True, out_dtype=np.float32,
-                   device: int = 0, rng: Optional[np.random.Generator] = None, sample_rate: int = 16000) -> list:
+                   device: int = 0, rng: Optional[np.random.Generator] = None, sample_rate: int = 16000,
+                   preserve_length: bool = True) -> list:
     """Clips of any lengths (1-D int16 or float32, one dtype) -> per clip the list
     ``[original (level-matched), copy 1, ..., copy n_augments]`` (originals only when asked for)."""
     if len(clips) == 0:
         return []
+    if any(sp["type"] in VOCODER for specs in specs_per_clip for sp in specs):
+        return _run_staged(clips, specs_per_clip, n_augments, seed, level_match_db, include_originals, out_dtype,
+                           device, rng, sample_rate, preserve_length)
     dt = np.int16 if clips[0].dtype == np.int16 else np.float32
     lens = np.array([len(c) for c in clips], dtype=np.int64)
     src_clip, steps, noise, max_steps = plan(lens, specs_per_clip, n_augments, seed, level_match_db,
@@ -204,6 +317,10 @@ def augment_batch(clips: np.ndarray, aug_specs, n_augments: int = 4, seed: int =
     per_clip = aug_specs if (len(aug_specs) and isinstance(aug_specs[0], (list, tuple))) else [aug_specs] * n_clips
     if len(per_clip) != n_clips:
         raise ValueError("one augmentation chain per clip expected")
+    if any(sp["type"] in VOCODER for specs in per_clip for sp in specs):
+        groups = _run_staged(list(clips), per_clip, n_augments, seed, level_match_db, include_originals, out_dtype,
+                             device, rng, sample_rate, True)
+        return np.stack([row for grp in groups for row in grp])
     src_clip, steps, noise, max_steps = plan([n] * n_clips, per_clip, n_augments, seed, level_match_db,
                                              include_originals, rng, sample_rate)
     rows = len(src_clip)
@@ -271,7 +388,7 @@ def run(cfg: dict, device: int = 0) -> int:
             raise ValueError(f"class {cname}: files at different rates {sorted(set(rates))}; set sample_rate in the config")
         groups = augment_ragged(clips, [specs] * len(clips), n_aug, seed, float(cfg["level_match_db"]),
                                 include_originals=True, out_dtype=np.float32, device=device, rng=rng,
-                                sample_rate=rates[0] if rates else 16000)
+                                sample_rate=rates[0] if rates else 16000, preserve_length=bool(cfg["preserve_length"]))
         for p_, sr, grp in zip(paths, rates, groups):
             dest = output_dir / cname / p_.name
             if not dest.exists():

@@ -15,7 +15,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "libb2a.so"
-SOURCES = ["api.cu", "frontend.cu", "logmel512.cu", "logmel1024.cu", "cqt.cu", "resample.cu", "augment.cu", "classical.cu", "tables.cpp", "decode.cpp"]
+SOURCES = ["api.cu", "frontend.cu", "logmel512.cu", "logmel1024.cu", "cqt.cu", "resample.cu", "augment.cu", "classical.cu", "effects.cu", "tables.cpp", "decode.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

@@ -80,7 +80,7 @@ def run(classes: int = 27, per_class: int = 260, devices: str = "all", dir: str 
 
 
 def run_device_augmented(classes: int = 27, per_class: int = 52, n_augments: int = 4, devices: str = "0",
-                         out_dir: str = "/dev/shm/b2a_stage2_aug") -> dict:
+                         out_dir: str = "/dev/shm/b2a_stage2_aug", full_chain: bool = False) -> dict:
     """Config 5 without the WAV round trip: the 27 x 52 originals are augmented on the device (Stage 1b,
     augment.py's chain minus the two librosa-backed steps, host-drawn reference RNG), quantised like the
     PCM16 files the reference writes, and go straight into audio_mel_spec -> features.npy."""
@@ -94,17 +94,29 @@ def run_device_augmented(classes: int = 27, per_class: int = 52, n_augments: int
     chain = [{"type": "volume_scale", "min_gain": 0.7, "max_gain": 1.3},
              {"type": "gaussian_noise", "min_amplitude": 0.001, "max_amplitude": 0.004},
              {"type": "time_shift", "max_fraction": 0.2}]
+    if full_chain:                                   # config/augmentation.yaml:38-60, the reference's default chain
+        chain = [{"type": "volume_scale", "min_gain": 0.7, "max_gain": 1.3},
+                 {"type": "pdm_hiss", "min_amplitude": 0.01, "max_amplitude": 0.04},
+                 {"type": "gaussian_noise", "min_amplitude": 0.001, "max_amplitude": 0.004},
+                 {"type": "time_stretch", "min_rate": 0.85, "max_rate": 1.15},
+                 {"type": "pitch_shift", "min_steps": -3.0, "max_steps": 3.0},
+                 {"type": "time_shift", "max_fraction": 0.2}]
     ext = P.get("audio_mel_spec")(duration=5.0, n_mels=40, sample_rate=16000, n_fft=512, hop_length=160, devices=devices)
     dev0 = ext.devices[0]
     best = None
     for _ in range(2):
         t0 = time.perf_counter()
-        src_clip, steps, noise, max_steps = G.plan([80000] * len(originals), [chain] * len(originals), n_augments, 42)
-        t1 = time.perf_counter()
-        rows = len(src_clip)
-        aug = np.empty((rows, 80000), dtype=np.int16)
-        G._run_host(dev0, originals.reshape(-1), np.ascontiguousarray(src_clip * 80000), np.full(rows, 80000, np.int32),
-                    np.arange(rows, dtype=np.int64) * 80000, steps, max_steps, noise, aug.reshape(-1))
+        if full_chain:                               # staged: draws and device calls interleave (augment._run_staged)
+            aug = G.augment_batch(originals, chain, n_augments, 42, out_dtype=np.int16, device=dev0, sample_rate=16000)
+            t1 = t0
+            rows = len(aug)
+        else:
+            src_clip, steps, noise, max_steps = G.plan([80000] * len(originals), [chain] * len(originals), n_augments, 42)
+            t1 = time.perf_counter()
+            rows = len(src_clip)
+            aug = np.empty((rows, 80000), dtype=np.int16)
+            G._run_host(dev0, originals.reshape(-1), np.ascontiguousarray(src_clip * 80000), np.full(rows, 80000, np.int32),
+                        np.arange(rows, dtype=np.int64) * 80000, steps, max_steps, noise, aug.reshape(-1))
         t2 = time.perf_counter()
         feats = ext.extract_batch(aug)
         t3 = time.perf_counter()
@@ -117,9 +129,11 @@ def run_device_augmented(classes: int = 27, per_class: int = 52, n_augments: int
     shutil.rmtree(out_dir, ignore_errors=True)
     return {"metric": "Stage 1b + 2 without the WAV round trip: clips/sec (originals in memory -> features.npy)",
             "value": rows / best[4], "unit": "clips/s", "clips": rows, "originals": len(originals),
-            "seconds": {"host_rng_plan (numpy default_rng, the reference's sequence)": best[0],
-                        "device_augment (H2D + kernel + D2H int16)": best[1], "log-mel (host buffers)": best[2],
-                        "np.save": best[3], "total": best[4]},
+            "seconds": ({"augment (host draws in the reference's order interleaved with the staged device calls)": best[0] + best[1]}
+                        if full_chain else
+                        {"host_rng_plan (numpy default_rng, the reference's sequence)": best[0],
+                         "device_augment (H2D + kernel + D2H int16)": best[1]}) |
+                       {"log-mel (host buffers)": best[2], "np.save": best[3], "total": best[4]},
             "chain": [c["type"] for c in chain], "features_shape": list(feats.shape)}
 
 
@@ -132,9 +146,10 @@ def main():
     ap.add_argument("--repeat", type=int, default=3)
     ap.add_argument("--file-rate", type=int, default=16000, help="rate the WAV files are written at (!= 16000: device resampling)")
     ap.add_argument("--device-augmented", action="store_true", help="config 5 without the WAV round trip (Stage 1b on the device)")
+    ap.add_argument("--full-chain", action="store_true", help="with --device-augmented: the reference's default chain incl. time_stretch / pitch_shift")
     a = ap.parse_args()
     if a.device_augmented:
-        print(json.dumps(run_device_augmented(a.classes, devices=a.devices if a.devices != "all" else "0")), flush=True)
+        print(json.dumps(run_device_augmented(a.classes, devices=a.devices if a.devices != "all" else "0", full_chain=a.full_chain)), flush=True)
         return
     print(json.dumps(run(a.classes, a.per_class, a.devices, a.dir, a.repeat, a.file_rate)), flush=True)
 

@@ -239,6 +239,23 @@ int b2a_augment_host(int32_t device, const void* src, int32_t src_dtype, int64_t
                      const int32_t* lengths, const int64_t* out_off, int64_t n_out, const b2a_aug_step* steps,
                      int32_t max_steps, const float* noise, int64_t noise_elems, void* out, int32_t out_dtype,
                      int64_t out_elems);
+
+/* The two librosa-backed augmentors (augment.py:105-118), batched over ragged float32 rows; host pointers.
+ * time_stretch: librosa.effects.time_stretch(y, rate) = istft(phase_vocoder(stft(y, n_fft 2048, hop 512), rate),
+ *   length = round(n / rate)).  The caller passes out_len[i] = int(round(lengths[i] / rates[i])) (Python's rounding:
+ *   it is the reference's) and receives row i at out + out_off[i].
+ * pitch_shift: librosa.effects.pitch_shift(y, sr, n_steps) = fix_length(resample(time_stretch(y, rate),
+ *   orig_sr = sr / rate, target_sr = sr), len(y)) with rate = 2 ** (-n_steps / 12); the caller passes rates[i],
+ *   ratios[i] = target_sr / orig_sr as librosa forms it and mid_len[i] = int(round(lengths[i] / rates[i]));
+ *   row i of the output has lengths[i] samples.  The resampling step stands in for libsoxr's variable-rate
+ *   path (parity unpinned). */
+int b2a_time_stretch_host(int32_t device, const float* src, int64_t src_elems, const int64_t* src_off,
+                          const int32_t* lengths, const double* rates, int64_t n_rows, float* out,
+                          int64_t out_elems, const int64_t* out_off, const int32_t* out_len);
+int b2a_pitch_shift_host(int32_t device, const float* src, int64_t src_elems, const int64_t* src_off,
+                         const int32_t* lengths, const double* rates, const double* ratios,
+                         const int32_t* mid_len, int64_t n_rows, float* out, int64_t out_elems,
+                         const int64_t* out_off);
 /* Device variant: every pointer is a device pointer on the current device; asynchronous on `stream`. */
 int b2a_augment_device(const void* d_src, int32_t src_dtype, const int64_t* d_src_off, const int32_t* d_lengths,
                        const int64_t* d_out_off, int64_t n_out, int32_t max_len, const b2a_aug_step* d_steps,

@@ -9,7 +9,7 @@ librosa (``volume_scale`` :88-93, ``gaussian_noise`` :96-102, ``time_shift`` :12
 ``_preserve_length`` :206-212 and the per-file loop of ``run`` :325-375 (one ``default_rng(seed)``
 for the whole run, level match before augmentation, ``n_augments`` copies, every copy drawing fresh
 parameters in specification order).  ``time_stretch`` / ``pitch_shift`` (:105-118) delegate to
-librosa's phase vocoder and are out of this restatement ("later").
+librosa.effects, restated in ``oracle/effects_restated.py`` (parity unpinned: librosa / libsoxr absent).
 
 Pinned: tests/golden/augment_ref.npz holds outputs of the reference's OWN functions executed from
 their source (tests/golden/make_golden.py); tests/test_augment.py asserts this restatement equals
@@ -67,8 +67,23 @@ def pdm_hiss(y, sr, rng, min_amplitude=0.02, max_amplitude=0.08, notch_freq=4000
     return np.clip(y + pink * amplitude, -1.0, 1.0).astype(y.dtype)
 
 
+def time_stretch(y, sr, rng, min_rate=0.85, max_rate=1.15):
+    """augment.py:105-110 -> librosa.effects.time_stretch (oracle/effects_restated.py; unpinned)."""
+    from . import effects_restated as E
+    rate = rng.uniform(min_rate, max_rate)
+    return E.time_stretch(y, rate)
+
+
+def pitch_shift(y, sr, rng, min_steps=-3.0, max_steps=3.0):
+    """augment.py:113-118 -> librosa.effects.pitch_shift (oracle/effects_restated.py; unpinned)."""
+    from . import effects_restated as E
+    n_steps = rng.uniform(min_steps, max_steps)
+    return E.pitch_shift(y, sr, n_steps)
+
+
 AUGMENTORS = {"volume_scale": volume_scale, "gaussian_noise": gaussian_noise, "time_shift": time_shift,
-              "polarity_inversion": polarity_inversion, "pdm_hiss": pdm_hiss}
+              "polarity_inversion": polarity_inversion, "pdm_hiss": pdm_hiss, "time_stretch": time_stretch,
+              "pitch_shift": pitch_shift}
 
 
 def apply_augmentations(y, sr, aug_specs, rng):
