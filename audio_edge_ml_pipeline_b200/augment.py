@@ -146,7 +146,7 @@ def plan(lengths: Sequence[int], specs_per_clip: Sequence[Sequence[dict]], n_aug
                         noise_pos += n
                     elif t == "pdm_hiss":
                         white = rng.standard_normal(n)                   # drawn BEFORE the amplitude (augment.py:146, 165)
-                        noise_rows.append(_pink_row(white, sample_rate, spec.get("notch_freq", 4000.0)))
+                        noise_rows.append(_Pink(white, sample_rate, spec.get("notch_freq", 4000.0)))
                         amp = rng.uniform(spec.get("min_amplitude", 0.02), spec.get("max_amplitude", 0.08))
                         steps[r, k] = (AUG_NOISE, np.float32(amp), 0, 0, noise_pos)
                         noise_pos += n
@@ -157,8 +157,34 @@ def plan(lengths: Sequence[int], specs_per_clip: Sequence[Sequence[dict]], n_aug
                         steps[r, k] = (AUG_POLARITY, 0.0, 0, 0, 0)
                     k += 1
             r += 1
-    noise = np.concatenate(noise_rows) if noise_rows else np.zeros(0, np.float32)
+    noise = np.concatenate(_materialise(noise_rows)) if noise_rows else np.zeros(0, np.float32)
     return src_clip, steps, noise, max_steps
+
+
+class _Pink:
+    """A pdm_hiss noise row still to be synthesised from its white draw: the draw has to happen in sequence (one
+    generator), the four FFTs behind it do not — :func:`_materialise` runs them on a thread pool."""
+    __slots__ = ("white", "sr", "notch")
+
+    def __init__(self, white, sr, notch):
+        self.white, self.sr, self.notch = white, sr, notch
+
+    def __len__(self):
+        return len(self.white)
+
+
+def _materialise(rows: list) -> list:
+    """Replace every pending :class:`_Pink` in ``rows`` by its float32 noise row (numpy's FFT releases the GIL)."""
+    todo = [i for i, r in enumerate(rows) if isinstance(r, _Pink)]
+    if not todo:
+        return rows
+    from concurrent.futures import ThreadPoolExecutor
+    import os
+    with ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as pool:
+        done = list(pool.map(lambda i: _pink_row(rows[i].white, rows[i].sr, rows[i].notch), todo))
+    for i, d in zip(todo, done):
+        rows[i] = d
+    return rows
 
 
 def _draw_ops(rng, n: int, specs, sample_rate: int) -> list:
@@ -174,9 +200,9 @@ def _draw_ops(rng, n: int, specs, sample_rate: int) -> list:
             amp = rng.uniform(spec.get("min_amplitude", 0.001), spec.get("max_amplitude", 0.008))
             ops.append(("noise", np.float32(amp), rng.standard_normal(n).astype(np.float32)))
         elif t == "pdm_hiss":
-            white = rng.standard_normal(n)
-            row = _pink_row(white, sample_rate, spec.get("notch_freq", 4000.0))
-            ops.append(("noise", np.float32(rng.uniform(spec.get("min_amplitude", 0.02), spec.get("max_amplitude", 0.08))), row))
+            white = rng.standard_normal(n)                   # drawn BEFORE the amplitude (augment.py:146, 165)
+            amp = rng.uniform(spec.get("min_amplitude", 0.02), spec.get("max_amplitude", 0.08))
+            ops.append(("noise", np.float32(amp), _Pink(white, sample_rate, spec.get("notch_freq", 4000.0))))
         elif t == "time_shift":
             f = spec.get("max_fraction", 0.2)
             ops.append(("roll", int(rng.uniform(-f, f) * n)))
@@ -241,7 +267,7 @@ def _run_staged(clips, specs_per_clip, n_augments, seed, level_match_db, include
             off = np.concatenate([[0], np.cumsum(lens.astype(np.int64))[:-1]]).astype(np.int64)
             src = np.concatenate([cur[i] for i in idx])
             out = np.empty(src.size, dtype=np.float32)
-            noise = np.concatenate(noise_rows) if noise_rows else np.zeros(0, np.float32)
+            noise = np.concatenate(_materialise(noise_rows)) if noise_rows else np.zeros(0, np.float32)
             _run_host(device, src, off, lens, off, steps, max_steps, noise, out)
             for r, i in enumerate(idx):
                 cur[i] = out[off[r]:off[r] + lens[r]]

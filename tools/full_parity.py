@@ -49,3 +49,18 @@ def run(name, kind, sr, n, fn, n_clips, **kw):
 run("1 audio_mel_spec", B.KIND_MEL, 16000, 80000, _mel, N)
 run("2 audio_mfcc_seq", B.KIND_MFCC, 16000, 80000, _mfcc, N, sample_rate=16000, n_fft=512, hop_length=160, n_mels=40, n_mfcc=13)
 run("3 audio_cqt", B.KIND_CQT, 22050, 110250, _cqt, min(N, 405))
+
+
+# the reference-default shapes (n_fft 1024 kernel, round 2): audio_mfcc_seq defaults and audio_mel_spec at 1024 / 256 / 64
+def _mfcc_def(c):
+    y = L.pcm16_to_float(c)
+    z = L.audio_mfcc_seq(y, 22050, 40, 1024, 512, 5.0, n_mels=128)
+    yy = L.prepare_audio(y, 22050, 5.0, min_samples=1024)
+    sd = L.mfcc(yy, sr=22050, n_mfcc=40, n_fft=1024, hop_length=512, n_mels=128).std(axis=1)
+    return np.concatenate([z, sd[:, None].astype(np.float32)], axis=1)
+def _mel1024(c): return L.audio_mel_spec(L.pcm16_to_float(c), 16000, 64, 1024, 256, 5.0)
+
+
+if len(sys.argv) > 2 and sys.argv[2] == "defaults":
+    run("audio_mfcc_seq reference defaults (22050/1024/512/128->40)", B.KIND_MFCC, 22050, 110250, _mfcc_def, min(N, 810))
+    run("audio_mel_spec 16000/1024/256/64", B.KIND_MEL, 16000, 80000, _mel1024, min(N, 810), n_fft=1024, hop_length=256, n_mels=64)
