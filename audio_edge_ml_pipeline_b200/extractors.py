@@ -381,7 +381,10 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
             groups: dict = {}
             for i, a in enumerate(decoded):
                 if not isinstance(a, Exception):
-                    groups.setdefault((0 if ragged else len(a), a.dtype.str), []).append(i)
+                    # ragged: clips are bucketed by the next power of two of their length, so one very long file
+                    # sizes only its own bucket's engine (and scratch), not the whole window's
+                    key = int(np.ceil(np.log2(max(len(a), 2)))) if ragged else len(a)
+                    groups.setdefault((key, a.dtype.str), []).append(i)
 
             def run(idxs):
                 try:
