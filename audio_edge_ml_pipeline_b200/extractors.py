@@ -202,11 +202,19 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
             audio = np.pad(audio, (0, self._min_samples() - len(audio)))
         if self.duration is not None:
             audio = wavio.pad_or_trim(audio, int(self.duration * self.sample_rate))
-        return self.extract_batch(audio[None, :])[0]
+        return self._extract_one(audio)
 
     def extract(self, sample_path: Path, start_time: Optional[float] = None,
                 end_time: Optional[float] = None, **_kwargs) -> np.ndarray:
-        audio = self._prepare(sample_path, start_time, end_time)
+        return self._extract_one(self._prepare(sample_path, start_time, end_time))
+
+    def _extract_one(self, audio: np.ndarray) -> np.ndarray:
+        """One prepared clip.  With ``duration=None`` every file has its own length: the clip goes through the
+        ragged entry point of an engine sized to the next power of two, so a loop over files (the reference's
+        ``extract_dataset``) touches a handful of engines instead of one per distinct length."""
+        if self.duration is None and self._kind != B.KIND_CQT:
+            cap = 1 << int(np.ceil(np.log2(max(len(audio), 2))))
+            return self._engine(cap, audio.dtype, self.devices[0]).run_host_ragged([audio])[0]
         return self.extract_batch(audio[None, :])[0]
 
     # ---- dataset extraction ------------------------------------------------------------------
@@ -649,6 +657,11 @@ class AudioClassicalExtractor(_GpuAudioExtractor):
             out[...] = got
             return out
         return got
+
+    def _extract_one(self, audio: np.ndarray) -> np.ndarray:
+        if self.duration is None:                   # ragged engine: the raw (rows, 1) device vector comes back
+            return self._select(super()._extract_one(audio)[None])[0]
+        return super()._extract_one(audio)          # fixed length: extract_batch above has already selected
 
     def extract_dataset(self, loader, max_samples: Optional[int] = None, features_out=None) -> FeatureSet:
         # (features_out is not used: the rows written during the run are full device vectors, the file holds the
