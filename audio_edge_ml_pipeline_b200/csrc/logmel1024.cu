@@ -10,16 +10,18 @@
 // operand per bin through warp shuffles and finish with a twiddle butterfly each.
 //
 // One persistent CTA per SM, 640 threads, 96 registers each (no setmaxnreg):
-//   * 16 FRAME warps.  A tile is 16 frames, one per warp, and the warp takes its frame all the way:
-//     FFT -> 4|X|^2 into its own 513-bin column -> the mel bands (lane = band, bands dealt to lanes by
-//     width so the ragged dot products balance; 2 loads + 1 FMA per filter tap) -> 10 log10 -> (mfcc)
-//     the DCT-II (lane = coefficient block, dB broadcast 4 bands at a time, basis as 128-bit loads) ->
-//     its column of the [row][16 frames] tile.  Raw PCM comes from the TMA-staged ring.
-//     (The first version of this kernel gave the band sweep and the DCT to four separate warps as
-//     logmel512.cu does; sharing a scheduler with four FFT warps each, their dependent load -> FMA
-//     chains ran at ~0.1 instructions per cycle and the FFT warps spent 39 % of their time waiting for
-//     them — profiles/r2_ncu_1024_summary.txt.  Sixteen warps doing a frame's bands in parallel lanes
-//     need ~150 instructions per frame instead.)
+//   * 16 FRAME warps.  A tile is 16 frames, one per warp: FFT -> 4|X|^2 into the tile's [bin pair][16 frames] power
+//     tile (half 1 windows its samples with (-1)^m, which turns its sub-FFT into E1[k + 256]: both halves then hand
+//     each other the same-named register in the combination step and run identical code) -> named barrier among the
+//     512 threads -> ALL sixteen warps sweep the tile's mel bands: lane & 15 = frame, the two halves of a warp take
+//     neighbouring bands of the width-sorted order (padded to the same number of 4-bin steps on the host), broadcast
+//     weights, conflict-free powers, packed FMAs -> 10 log10 into the [row][16] output tile -> named barrier ->
+//     (mfcc) the tile's DCT-II as a register-blocked 16 frames x n_mfcc x n_mels product (4 x 4 block per lane, the
+//     eight band lanes folded by a transposing shuffle reduction).  Raw PCM comes from the TMA-staged ring.
+//     (History — DESIGN.md 3.2, profiles/r2_ncu_1024_summary.txt: four dedicated mel warps as in logmel512.cu ran
+//     their dependent load -> FMA chains at ~0.1 instructions per cycle and stalled the FFT warps 39 % of the time;
+//     a per-frame sweep with lane = band put 676 shared-memory wavefronts per frame on the load pipe; a per-frame
+//     DCT with lane = coefficient was half of all shared-memory traffic.)
 //   * 4 EPILOGUE warps, warp 0 also the TMA producer: move finished tiles to global memory with
 //     coalesced stores, track the clip's max / min, and rewrite the PREVIOUS clip in place during the
 //     current clip's tiles — power_to_db(ref=max, top_db) + min-max for mel, the per-row z-score

@@ -55,7 +55,8 @@ def _check(got, ref, same_tuning, n_mfcc=40, slack=1.0):
     assert pos == got.shape[1]
 
 
-@pytest.mark.parametrize("sr,n_fft,hop,secs,n_clips", [(22050, 1024, 512, 5.0, 21), (16000, 512, 160, 2.0, 14)])
+@pytest.mark.parametrize("sr,n_fft,hop,secs,n_clips", [(22050, 1024, 512, 5.0, 21), (16000, 512, 160, 2.0, 14),
+                                                       (22050, 2048, 441, 2.0, 7)])          # (odd hop, 33 bins per lane)
 def test_classical_suite(sr, n_fft, hop, secs, n_clips):
     n = int(sr * secs)
     pcm = synth.make_suite(n_clips, sr, n, seed=4321)
