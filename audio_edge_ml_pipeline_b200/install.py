@@ -21,7 +21,8 @@ def install_into_reference(registry_module) -> dict:
     Returns the classes that were replaced (for restoring)."""
     reg = registry_module._REGISTRY
     old = {}
-    for cls in (extractors.AudioMelSpectrogram, extractors.AudioMFCCSequence, extractors.AudioCQT):
+    for cls in (extractors.AudioMelSpectrogram, extractors.AudioMFCCSequence, extractors.AudioCQT,
+                extractors.AudioClassicalExtractor):
         old[cls.name] = reg.get(cls.name)
         reg[cls.name] = cls
     return old
