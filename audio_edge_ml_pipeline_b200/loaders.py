@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import json
 import logging
+import os
 from pathlib import Path
 from typing import Iterator, Optional
 
@@ -19,16 +20,16 @@ logger = logging.getLogger(__name__)
 
 
 def _probe_all(paths: list) -> list:
-    """duration / sample_rate / n_channels of every file (audio_folder_loader.py:76-103: soundfile.info, zeros on
+    """``paths``: plain strings.  duration / sample_rate / n_channels of every file (audio_folder_loader.py:76-103: soundfile.info, zeros on
     failure).  RIFF/WAVE headers go through the library's threaded probe in one call (7 000 files: 0.03 s instead of
     0.09 s of Python open / read / parse); anything it does not recognise, or a missing library, takes the Python
     parser, which has the same zero fallback."""
     out = [None] * len(paths)
     try:
         from . import _lib
-        wav = [i for i, p in enumerate(paths) if p.suffix.lower() in (".wav", ".wave")]
+        wav = [i for i, p in enumerate(paths) if p[-4:].lower() == ".wav" or p[-5:].lower() == ".wave"]
         if wav:
-            info = _lib.probe_wav_batch([str(paths[i]) for i in wav])
+            info = _lib.probe_wav_batch([paths[i] for i in wav])
             for k, i in enumerate(wav):
                 if info["status"][k] == 0 and info["rate"][k] > 0:
                     out[i] = {"duration": int(info["n_frames"][k]) / int(info["rate"][k]),
@@ -54,16 +55,22 @@ class AudioFolderLoader(BaseDatasetLoader):
             class_dirs = sorted(p for p in eff.iterdir() if p.is_dir())
             self._class_names = [d.name for d in class_dirs]
         self._samples: list = []
+        strs: list = []                                          # the same paths as plain strings, for the header probe
         for class_dir, label in zip(class_dirs, self._class_names):
             if not class_dir.is_dir():
                 logger.warning("Class directory not found: %s (skipping)", class_dir)
                 continue
-            clips = sorted(p for p in class_dir.iterdir() if p.is_file() and p.suffix.lower() in exts)
+            # os.scandir: the entry type comes with the directory read, no stat() per file (7 000 files: 10 ms)
+            with os.scandir(class_dir) as it:
+                names = [e.name for e in it if e.is_file() and os.path.splitext(e.name)[1].lower() in exts]
+            names.sort()                                         # (plain names sort like the paths: same parent)
+            clips = [class_dir / n for n in names]
+            strs.extend(os.path.join(class_dir, n) for n in names)
             if not clips:
                 logger.warning("No audio files found in: %s", class_dir)
             for clip in clips:
                 self._samples.append((clip, label, {"filename": clip.name, "class_dir": class_dir.name}))
-        for (clip, _label, meta), info in zip(self._samples, _probe_all([s[0] for s in self._samples])):
+        for (clip, _label, meta), info in zip(self._samples, _probe_all(strs)):
             meta.update(info)
         if manifest is not None:
             if manifest_split is None:
