@@ -36,6 +36,10 @@ logger = logging.getLogger(__name__)
 HOST_BATCH_CLIPS = 4096          # clips decoded and shipped per GPU round in extract_dataset
 DECODE_WORKERS = min(16, os.cpu_count() or 1)   # file reads release the GIL; order is preserved
 NATIVE_DECODE = True             # threaded C decoder for mono PCM16 WAVs (fixed-duration windows)
+# extract_dataset: feature rows via page-locked staging + helper-thread copies instead of D2H straight into the (pageable)
+# result array.  Opt-in (B2A_OUT_STAGING=1): measured on config 5 it takes the extract step from 0.152 s to 0.138 s once
+# the two 330 MB staging buffers exist, but allocating them costs more than that on a one-shot run.
+OUT_STAGING = os.environ.get("B2A_OUT_STAGING", "0") == "1"
 
 
 def _make_engine(cfg: B.B2AConfig, device: int):
@@ -109,6 +113,9 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
         self._engines: dict = {}
         self._staging: dict = {}      # (n_samples, dtype) -> pinned (in, out) batch buffers, reused across calls
         self._lock = threading.Lock()
+        self._out_slot = 0
+        self._pending: dict = {}      # staging slot -> futures of the copies still moving its rows to the result array
+        self._copier = None
 
     # ---- per-extractor hooks -----------------------------------------------------------
     def _min_samples(self) -> int:
@@ -137,6 +144,10 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
             return eng
 
     def close(self) -> None:
+        self._wait_copies()
+        if self._copier is not None:
+            self._copier.shutdown(wait=True)
+            self._copier = None
         for e in self._engines.values():
             e.close()
         self._engines.clear()
@@ -243,6 +254,20 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
         if errs:
             raise errs[0]
 
+    def _copy_async(self, slot: int, dst: np.ndarray, src: np.ndarray, parts: int = 4) -> None:
+        from concurrent.futures import ThreadPoolExecutor
+        if self._copier is None:
+            self._copier = ThreadPoolExecutor(max_workers=parts)
+        n = len(src)
+        bounds = [n * k // parts for k in range(parts + 1)]
+        self._pending[slot] = [self._copier.submit(np.copyto, dst[a:b], src[a:b])
+                               for a, b in zip(bounds[:-1], bounds[1:]) if b > a]
+
+    def _wait_copies(self, slot: Optional[int] = None) -> None:
+        for k in ([slot] if slot is not None else list(self._pending)):
+            for fut in self._pending.pop(k, []):
+                fut.result()
+
     def _stage(self, key, shape_tail, dtype):
         """Pinned staging rows, reused across windows and calls: key -> array (HOST_BATCH_CLIPS or fewer rows)."""
         ent = self._staging.get(key)
@@ -317,7 +342,18 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
                                                       DECODE_WORKERS)
                     if status.any():
                         raise RuntimeError(f"decode failed (status {int(status.max())})")
-                    self.extract_batch(a_in[:len(idxs)], out)
+                    if contiguous and OUT_STAGING:
+                        # the engine's D2H lands in page-locked staging at link speed (into the pageable result
+                        # array it runs at the driver's single-threaded bounce-buffer rate) and helper threads move
+                        # it on while the next window is decoded and shipped; two staging buffers alternate
+                        self._out_slot ^= 1
+                        o_pin = self._stage(("o32", HOST_BATCH_CLIPS, self._out_slot) + tuple(out.shape[1:]), out.shape[1:],
+                                            np.float32)[:len(idxs)]
+                        self._wait_copies(self._out_slot)
+                        self.extract_batch(a_in[:len(idxs)], o_pin)
+                        self._copy_async(self._out_slot, out, o_pin)
+                    else:
+                        self.extract_batch(a_in[:len(idxs)], out)
                 elif rate == self.sample_rate:
                     self._float_group(sub(paths), sub(offs), sub(durs), n, out)
                 else:
@@ -444,6 +480,8 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
                     except Exception as exc:  # noqa: BLE001 — e.g. engine creation failed: per-sample policy below
                         logger.debug("native front end unavailable: %s", exc)
                         res, dst, in_place = ["py"] * len(items), None, False
+                if any(r is not None for r in res):
+                    self._wait_copies()                  # rows are about to be patched / compacted below
                 todo = [i for i, r in enumerate(res) if isinstance(r, str)]
                 if todo:
                     got = python_path([items[i] for i in todo], pool)
@@ -469,6 +507,7 @@ class _GpuAudioExtractor(BaseFeatureExtractor):
                     tail.extend(np.asarray(res[i])[None] for i in ok)
                 for i in ok:
                     book(items[i])
+        self._wait_copies()                                  # every staged row has reached the result array
         if not metas:
             raise RuntimeError("No features were successfully extracted.")
         mapped = isinstance(final["arr"], np.memmap)
