@@ -374,6 +374,22 @@ def test_features_are_written_in_place_when_the_output_is_known(tmp_path, fake, 
     assert np.load(tmp_path / "out2" / "features.npy").shape[0] == len(loader2) - 1
 
 
+def test_output_staging_path_gives_the_same_dataset(tmp_path, fake, lib_built, monkeypatch):
+    """B2A_OUT_STAGING=1: rows travel through staging buffers and helper-thread copies; windows of 4 clips so that both
+    buffers are used and reused, one broken file so that the compaction has to wait for the copies."""
+    from audio_edge_ml_pipeline_b200.loaders import AudioFolderLoader
+    _make_dataset(tmp_path / "ds", n=8000, per=5, broken={("axe", 2)})
+    loader = AudioFolderLoader(tmp_path / "ds")
+    plain = P.AudioMelSpectrogram(duration=0.5).extract_dataset(loader)
+    monkeypatch.setattr(extractors, "OUT_STAGING", True)
+    monkeypatch.setattr(extractors, "HOST_BATCH_CLIPS", 4)
+    ex = P.AudioMelSpectrogram(duration=0.5)
+    staged = ex.extract_dataset(loader)
+    ex.close()
+    assert np.array_equal(plain.features, staged.features) and np.array_equal(plain.labels, staged.labels)
+    assert plain.metadata == staged.metadata and len(staged.features) == len(loader) - 1
+
+
 def test_loader_metadata_same_through_native_and_python_probe(tmp_path, lib_built, monkeypatch):
     from audio_edge_ml_pipeline_b200 import loaders
     _make_dataset(tmp_path / "ds", n=8000, broken={("axe", 1)})
