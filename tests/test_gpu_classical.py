@@ -11,8 +11,10 @@ the B200 (tools/classical_check.py, 35 clips, two configurations) in brackets:
   flatness                            5e-4  [1.2e-4 of the 1e-3 floor: values ~1e-7 on tonal clips]
   zcr, rolloff                        exact on every clip so far; 2e-3 allowed for rolloff (a frame whose cumulative
                                       magnitude passes 0.85 of the total within fp32 rounding of a bin edge moves a bin)
-  contrast                            1e-2  [3.7e-3 = 0.07 dB]: the valley is the SMALLEST magnitude of a band, bins
-                                      ~100 dB under the frame's peak, where an fp32 FFT is good to a few per cent
+  contrast                            0.25 dB absolute (mean and std rows alike) [810 clips over two configurations:
+                                      0.065 dB worst on the means, 0.17 dB on the stds]: the valley is the SMALLEST
+                                      magnitude of a band, bins ~100 dB under the frame's peak, where an fp32 FFT is good
+                                      to a few per cent
   chroma / tonnetz                    1e-4 on clips whose tuning estimate agrees [1.3e-5; all 35 agreed]; the estimate
                                       is the arg-max of a 100-bin histogram — the extractor's one discontinuous step —
                                       and must agree on at least 90 % of the clips.
@@ -28,7 +30,7 @@ from oracle import librosa_restated as L
 pytestmark = pytest.mark.gpu
 
 GROUPS = [("mfcc", 40, 2e-5), ("delta_mfcc", 40, 2e-5), ("delta2_mfcc", 40, 2e-5), ("spectral_centroid", 1, 1e-5),
-          ("spectral_rolloff", 1, 2e-3), ("spectral_bandwidth", 1, 1e-5), ("spectral_contrast", 7, 1e-2),
+          ("spectral_rolloff", 1, 2e-3), ("spectral_bandwidth", 1, 1e-5), ("spectral_contrast", 7, 0.25),
           ("spectral_flatness", 1, 5e-4), ("chroma", 12, 1e-4), ("zcr", 1, 1e-6), ("rms", 1, 1e-5), ("tonnetz", 6, 1e-4)]
 HZ = ("spectral_centroid", "spectral_rolloff", "spectral_bandwidth")
 
@@ -48,6 +50,8 @@ def _check(got, ref, same_tuning, n_mfcc=40, slack=1.0):
             scale = np.maximum(np.abs(r).max(axis=1, keepdims=True), 1.0 if name in HZ else 1e-3)
             if name.endswith("mfcc"):
                 scale = np.maximum(np.abs(ref[:, :n_mfcc]).max(axis=1, keepdims=True), 1.0)
+            if name == "spectral_contrast":
+                scale = 1.0                                                # absolute, in dB
             err = (np.abs(g - r) / scale).max(axis=1)
             rows = same_tuning if name in ("chroma", "tonnetz") else np.ones(len(got), bool)
             assert err[rows].max() <= tol * slack, (name, _agg, float(err[rows].max()), int(err.argmax()))
